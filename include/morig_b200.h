@@ -1,0 +1,169 @@
+/*
+ * morig_b200 — C ABI of the B200-native (sm_100a) forward path of MoRig's rigging networks.
+ *
+ * The reference (zhan-xu/MoRig) is pure Python: it has no FFI of its own.  What it binds instead
+ * are third-party CUDA wheels (PyG 2.0.4, torch_scatter 2.0.9, cuBLAS via torch 1.11) reached from
+ * models/basic_modules.py and models/rignet.py.  Each entry point below replaces the group of those
+ * calls named in its comment (paths relative to the reference root).  The only caller is the
+ * Python host layer `morig_b200/` (ctypes), which mirrors the reference's nn.Module interface.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous memory owned by the caller (PyTorch);
+ *     the library never allocates, frees or retains device memory;
+ *   - all floating point is IEEE fp32, all indices int32 except the API edge lists (int64 as
+ *     delivered by the reference's datasets, datasets/dataset_rig.py:119-120);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises;
+ *   - return value 0 = success, otherwise a cudaError_t or MORIG_E_*; `morig_last_error()` gives
+ *     the thread-local message.  No exceptions, no exit(), nothing printed.
+ */
+#ifndef MORIG_B200_H
+#define MORIG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MORIG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MORIG_API __attribute__((visibility("default")))
+#else
+#define MORIG_API
+#endif
+
+#define MORIG_E_BADARG   1001   /* shape / alignment / flag combination not supported */
+#define MORIG_E_WORKSPACE 1002  /* workspace too small */
+
+MORIG_API int         morig_version(void);
+MORIG_API const char *morig_last_error(void);
+/* number of SMs of the current device (grid sizing by the host layer) */
+MORIG_API int         morig_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Graph preparation.  Replaces remove_self_loops + add_self_loops, which the reference re-runs in
+ * every EdgeConvMotion.forward (models/basic_modules.py:188-189; 36x per forward on the same two
+ * edge lists), and produces the target-sorted CSR the fused kernels consume.
+ *
+ *   edge_index  int64 [2, E]   row 0 = source j, row 1 = target i (PyG flow source_to_target)
+ *   rowptr      int32 [N+1]    out: segment start of every target vertex
+ *   col         int32 [E+N]    out: source vertex of every edge, grouped by target; inside a
+ *                              target the original edge order is kept and the self loop is last
+ *   tgt         int32 [E+N]    out: target vertex of every CSR slot (expanded rowptr)
+ *   The normalised edge count E' = (#edges with j != i) + N is rowptr[N] (device side only).
+ *   ws          scratch, at least morig_graph_prep_workspace(E, N) bytes
+ * ------------------------------------------------------------------------------------------- */
+MORIG_API size_t morig_graph_prep_workspace(int64_t E, int32_t N);
+MORIG_API int    morig_graph_prep(const int64_t *edge_index, int64_t E, int32_t N,
+                        int32_t *rowptr, int32_t *col, int32_t *tgt,
+                        void *ws, size_t ws_bytes, void *stream);
+
+/* Brute-force k-nearest-neighbour graph (fp32 squared distance ((a-b)^2).sum(), self excluded, ties
+ * to the lower index) inside each graph of a batch; the synthetic stand-in for the reference's
+ * offline geodesic-ball builder (data_proc/common_ops.py:214-226).  gptr int32 [B+1] = vertex range
+ * of each graph.  Output edge_index int64 [2, k*N]: row 0 = i, row 1 = neighbour. */
+MORIG_API int morig_knn_graph(const float *pos, const int32_t *gptr, int32_t n_graphs, int32_t N, int32_t k,
+                    int64_t *edge_index, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense row-wise layer with fused epilogue ("vertex MLP").  Replaces torch.cat + Linear + ReLU +
+ * BatchNorm1d chains on N rows (MLP, models/basic_modules.py:31-36; GCUMotion.mlp :217-218;
+ * GCNRig.mlp_glb / mlp_transform, models/rignet.py:62-66), the per-graph scatter_max +
+ * repeat_interleave (models/rignet.py:63-64) and, with layer-0 factorisation, the first Linear of
+ * the edge MLPs (models/basic_modules.py:193-194) evaluated once per vertex instead of per edge.
+ *
+ *   out[r, n] = post( sum_k A[r, k] * W[k, n] + bias[n] + rowbias[group(r), n] )
+ *   post(v)   = (relu ? max(v, 0) : v) * scale[n] + shift[n]        (scale/shift optional)
+ *   group(r)  = (r / n_vtx) * n_graphs + batch[r % n_vtx]           (key-frame block, graph)
+ *   pool[group(r), n] = max over rows of out[r, n]                  (optional; ordered atomics,
+ *                        pool must be pre-filled with -inf)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct morig_dense_desc {
+    const float   *A;        int32_t lda;     /* [M, K] activations, row stride lda            */
+    const float   *W;        int32_t ldw;     /* [K, ldw] packed weights (transposed Linear)   */
+    const float   *bias;                       /* [N] or NULL                                   */
+    const float   *scale;                      /* [N] or NULL  (eval BatchNorm scale)           */
+    const float   *shift;                      /* [N] or NULL  (eval BatchNorm shift)           */
+    const float   *rowbias;  int32_t ldrb;    /* [G, ldrb] or NULL; needs batch                */
+    const int32_t *batch;                      /* [n_vtx] graph id per vertex, sorted; or NULL  */
+    int32_t        n_vtx, n_graphs;
+    float         *C;        int32_t ldc;     /* [M, N] output or NULL (pool only)             */
+    float         *pool;     int32_t ldpool;  /* [G, N] or NULL                                */
+    int32_t        M, N, K;
+    int32_t        relu;
+} morig_dense_desc;
+
+MORIG_API int morig_dense_fwd(const morig_dense_desc *d, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused EdgeConv branch.  Replaces, for one of the two MLPs of EdgeConvMotion.message and for one
+ * edge set: the x_i/x_j index_select gathers, cat[x_i, x_j - x_i], Linear/ReLU/BN x2 on E rows and
+ * the scatter-max of PyG's aggregate (models/basic_modules.py:190-199, MLP :31-36).
+ *
+ *   PQ      [R, ldpq]  per-vertex halves of the factorised first Linear:
+ *           P[v] = (W0a - W0b) x_v + b0   at columns [p_off, p_off+H)
+ *           Q[v] =  W0b x_v               at columns [q_off, q_off+H)
+ *   edge e = (j -> i):   h = relu(P[i] + Q[j])                     (BN #1 folded into W1/b1)
+ *                        z = relu(h W1 + b1) * scale + shift       (BN #2 applied before max)
+ *   out[i, out_off + c] = max over in-edges of z[c]
+ *   R = n_frames * N rows: key-frame f uses rows [f*N, (f+1)*N) of PQ and out with the same CSR.
+ *   out_repeat > 1 (pos branch shared by all key-frames) stores the result to that many row
+ *   blocks of `out` while reading PQ rows [0, N).
+ *   out must be pre-filled with -inf where segments may straddle 128-edge tiles (use
+ *   morig_fill_f32); tiles combine with ordered atomics, so results are deterministic.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct morig_edge_desc {
+    const float   *PQ;     int32_t ldpq, p_off, q_off;
+    const int32_t *rowptr; const int32_t *col; const int32_t *tgt;
+    int32_t        N;            /* vertices per key-frame block                    */
+    int32_t        E_max;        /* allocated CSR slots (E + N); E' read on device  */
+    int32_t        n_frames;     /* key-frame blocks sharing the CSR                */
+    int32_t        out_repeat;   /* >=1                                             */
+    const float   *W1;     int32_t ldw;      /* [H, ldw] packed second Linear       */
+    const float   *b1, *scale, *shift;        /* [H]                                 */
+    float         *out;    int32_t ldo, out_off;
+    int32_t        H;
+} morig_edge_desc;
+
+MORIG_API int morig_edgeconv_fwd(const morig_edge_desc *d, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-vertex cls-token attention over key-frames.  Replaces TemporalAttn.forward up to and
+ * including w_o (models/rignet.py:36-44); only the cls query row is evaluated because only
+ * res[:, 0, :] is used (:45).  Constants are parameter-only products prepared by the host layer:
+ *   u      [heads, C]      = Wk_h^T (Wq_h cls) / sqrt(d)       logit of token x is u_h . x
+ *   l0     [heads]         = (Wq_h cls) . (Wk_h cls) / sqrt(d) logit of the cls key
+ *   Mv     [heads, D, C]   = Wo[:, h] Wv_h                     value+output projection
+ *   c0     [heads, D]      = Wo[:, h] (Wv_h cls)
+ *   x      [N, T, C] -> out [N, D]
+ * ------------------------------------------------------------------------------------------- */
+MORIG_API int morig_temporal_attn_fwd(const float *x, int32_t N, int32_t T, int32_t C, int32_t heads, int32_t D,
+                            const float *u, const float *l0, const float *Mv, const float *c0,
+                            float *out, int32_t ldo, void *stream);
+
+/* x[r, 0:C] /= max(||x[r, 0:C]||_2, 1e-12)  — F.normalize(dim=1), models/rignet.py:87,98,120,131,199,203.
+ * If dst2 != NULL the normalised row r = f*N + v is also written to dst2[v, f, 0:C]
+ * (the torch.stack of key-frames, models/rignet.py:89). */
+MORIG_API int morig_row_normalize(float *x, int32_t ldx, int32_t R, int32_t C,
+                        float *dst2, int32_t N, int32_t n_frames, void *stream);
+
+/* Key-frame reductions of the non-attention aggregators (models/rignet.py:92-95):
+ * mode 0 = mean, 1 = max over T of x[N, T, C] -> out[N, C] (row stride ldo). */
+MORIG_API int morig_frame_reduce(const float *x, int32_t N, int32_t T, int32_t C, int32_t mode,
+                       float *out, int32_t ldo, void *stream);
+
+/* Scatter source columns into a strided destination, replacing the torch.cat / column slicing on the
+ * path (models/rignet.py:65,86,159-173).  For r in [0, n_frames*N), c in [0, C):
+ *   dst[r, dst_off + c] = src[(r % N), src_off + (r / N) * frame_stride + cols ? cols[c] : c]   */
+MORIG_API int morig_gather_cols(const float *src, int32_t lds, int32_t src_off, int32_t frame_stride,
+                      const int32_t *cols, int32_t C, int32_t N, int32_t n_frames,
+                      float *dst, int32_t ldd, int32_t dst_off, void *stream);
+
+MORIG_API int morig_fill_f32(float *dst, int64_t n, float value, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MORIG_B200_H */

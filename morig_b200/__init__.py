@@ -1,0 +1,35 @@
+"""morig_b200 — B200-native (sm_100a) forward path of MoRig's motion-aware rigging networks.
+
+    import morig_b200
+    model = morig_b200.jointnet_motion(num_keyframes=5, chn_output=3, aggr_method="attn").cuda().eval()
+    model.load_state_dict(reference_checkpoint["state_dict"])        # same keys as the reference
+    motion_all, motion_aggr, pred = model(data, data.pred_flow)      # same call as training/train_rig.py:223
+
+or, to swap the networks inside an unmodified reference checkout:
+
+    import models, morig_b200
+    morig_b200.install(models)            # models.__dict__['jointnet_motion'] etc. now build the CUDA modules
+"""
+from __future__ import annotations
+
+from .basic_modules import MLP, EdgeConvMotion, GCUMotion
+from .rignet import (GCNRig, JointNetMotion, MaskNetMotion, SkinMotion, SkinNet_inner, TemporalAttn,
+                     jointnet_motion, masknet_motion, skinnet_motion)
+
+__all__ = ["jointnet_motion", "masknet_motion", "skinnet_motion", "JointNetMotion", "MaskNetMotion", "SkinMotion",
+           "SkinNet_inner", "GCNRig", "TemporalAttn", "GCUMotion", "EdgeConvMotion", "MLP", "install"]
+
+__version__ = "0.1.0"
+
+
+def install(models_module) -> None:
+    """Replace the rigging-network entries of the reference's `models` registry
+    (`models/__init__.py:1-3`; looked up as `models.__dict__[args.arch]` at training/train_rig.py:83)."""
+    for name in ("jointnet_motion", "masknet_motion", "skinnet_motion", "JointNetMotion", "MaskNetMotion",
+                 "SkinMotion", "SkinNet_inner", "GCNRig", "TemporalAttn"):
+        setattr(models_module, name, globals()[name])
+    sub = getattr(models_module, "rignet", None)
+    if sub is not None:
+        for name in ("jointnet_motion", "masknet_motion", "skinnet_motion", "JointNetMotion", "MaskNetMotion",
+                     "SkinMotion"):
+            setattr(sub, name, globals()[name])

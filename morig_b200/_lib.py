@@ -1,0 +1,111 @@
+"""ctypes binding of `libmorig_b200.so` (declared in include/morig_b200.h).
+
+There is no CPU or PyTorch fallback: if the library is missing or a call fails this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmorig_b200.so")
+
+c_f32p = C.c_void_p   # device pointers travel as integers
+c_i32p = C.c_void_p
+c_i64p = C.c_void_p
+
+
+class DenseDesc(C.Structure):
+    """mirror of `morig_dense_desc`"""
+    _fields_ = [
+        ("A", c_f32p), ("lda", C.c_int32),
+        ("W", c_f32p), ("ldw", C.c_int32),
+        ("bias", c_f32p), ("scale", c_f32p), ("shift", c_f32p),
+        ("rowbias", c_f32p), ("ldrb", C.c_int32),
+        ("batch", c_i32p),
+        ("n_vtx", C.c_int32), ("n_graphs", C.c_int32),
+        ("C", c_f32p), ("ldc", C.c_int32),
+        ("pool", c_f32p), ("ldpool", C.c_int32),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("relu", C.c_int32),
+    ]
+
+
+class EdgeDesc(C.Structure):
+    """mirror of `morig_edge_desc`"""
+    _fields_ = [
+        ("PQ", c_f32p), ("ldpq", C.c_int32), ("p_off", C.c_int32), ("q_off", C.c_int32),
+        ("rowptr", c_i32p), ("col", c_i32p), ("tgt", c_i32p),
+        ("N", C.c_int32), ("E_max", C.c_int32), ("n_frames", C.c_int32), ("out_repeat", C.c_int32),
+        ("W1", c_f32p), ("ldw", C.c_int32),
+        ("b1", c_f32p), ("scale", c_f32p), ("shift", c_f32p),
+        ("out", c_f32p), ("ldo", C.c_int32), ("out_off", C.c_int32),
+        ("H", C.c_int32),
+    ]
+
+
+_SIGNATURES = {
+    "morig_version": (C.c_int, []),
+    "morig_last_error": (C.c_char_p, []),
+    "morig_sm_count": (C.c_int, []),
+    "morig_graph_prep_workspace": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "morig_graph_prep": (C.c_int, [c_i64p, C.c_int64, C.c_int32, c_i32p, c_i32p, c_i32p, C.c_void_p, C.c_size_t,
+                                   C.c_void_p]),
+    "morig_knn_graph": (C.c_int, [c_f32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i64p, C.c_void_p]),
+    "morig_dense_fwd": (C.c_int, [C.POINTER(DenseDesc), C.c_void_p]),
+    "morig_edgeconv_fwd": (C.c_int, [C.POINTER(EdgeDesc), C.c_void_p]),
+    "morig_temporal_attn_fwd": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                          c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_void_p]),
+    "morig_row_normalize": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_int32, C.c_int32,
+                                      C.c_void_p]),
+    "morig_frame_reduce": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_int32,
+                                     C.c_void_p]),
+    "morig_gather_cols": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_int32, C.c_int32,
+                                    C.c_int32, c_f32p, C.c_int32, C.c_int32, C.c_void_p]),
+    "morig_fill_f32": (C.c_int, [c_f32p, C.c_int64, C.c_float, C.c_void_p]),
+}
+
+EXPORTS = tuple(_SIGNATURES)
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m morig_b200.build` "
+                "(morig_b200 has no CPU / PyTorch fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        if lib.morig_version() != 1:
+            raise ImportError(f"{LIB_PATH}: ABI version {lib.morig_version()} != 1; rebuild")
+        _lib = lib
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().morig_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {code}): {msg}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def require_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"morig_b200: `{name}` must live on a CUDA device (got {t.device}); "
+                           "there is no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"morig_b200: `{name}` must be {dtype} (got {t.dtype})")
+    return t.contiguous()

@@ -1,0 +1,157 @@
+"""Host-side mirror of the graph-conv building blocks of the reference (`models/basic_modules.py`):
+same constructor arguments, same `forward` signatures, same `state_dict` keys — but `forward` runs
+the fused sm_100a kernels of `libmorig_b200.so`.  Parameters live in ordinary torch containers purely
+so that reference checkpoints load unchanged (`training/train_rig.py:95`); the containers themselves
+are never executed.  Inference (eval-mode BatchNorm, no autograd) only in this round.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from . import _lib, engine, packing
+
+
+def MLP(channels: List[int], batch_norm: bool = True) -> nn.Sequential:
+    """Parameter container with the key layout of the reference's `MLP`
+    (`models/basic_modules.py:31-36`): `{i}.0` Linear, `{i}.1` ReLU, `{i}.2` BatchNorm1d(momentum=0.1)."""
+    if not batch_norm:
+        raise NotImplementedError("the rigging networks only use batch_norm=True")
+    blocks = []
+    for c_in, c_out in zip(channels[:-1], channels[1:]):
+        blocks.append(nn.Sequential(nn.Linear(c_in, c_out), nn.ReLU(), nn.BatchNorm1d(c_out, momentum=0.1)))
+    return nn.Sequential(*blocks)
+
+
+class FusedModule(nn.Module):
+    """Common behaviour of the drop-in modules: lazily packed device weights that are dropped whenever
+    the parameters may have changed (`load_state_dict`, `.to()`, `.train()`), a reusable workspace and
+    loud failure outside the supported regime."""
+
+    def __init__(self):
+        super().__init__()
+        self._packed = None
+        self._packed_key = None
+        self._ws = engine.Workspace()
+        self._graphs = engine.GraphCache()
+        self._batches = engine.BatchCache()
+        self._register_load_state_dict_pre_hook(self._drop_packed_hook)
+
+    # -- cache invalidation ----------------------------------------------------------------------
+    def _drop_packed_hook(self, *args, **kwargs):
+        self.invalidate_packed()
+
+    def invalidate_packed(self):
+        for m in self.modules():
+            if isinstance(m, FusedModule):
+                m._packed = None
+                m._packed_key = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_packed()
+        self._ws.clear()
+        return super()._apply(fn, *args, **kwargs)
+
+    def train(self, mode: bool = True):
+        self.invalidate_packed()
+        return super().train(mode)
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _device_state(self):
+        return {k: v for k, v in self.state_dict(keep_vars=True).items()}
+
+    def _guard(self, *tensors: torch.Tensor):
+        if self.training:
+            raise NotImplementedError(
+                "morig_b200 implements the inference forward (model.eval(), as training/train_rig.py:200); "
+                "train-mode BatchNorm / backward are not built yet")
+        _lib.load()
+        for t in tensors:
+            if not t.is_cuda:
+                raise RuntimeError(f"morig_b200 runs on CUDA tensors only (got {t.device}); there is no CPU path")
+
+    def _packed_for(self, key, builder):
+        if self._packed is None or self._packed_key != key:
+            with torch.no_grad():
+                self._packed = builder()
+            self._packed_key = key
+        return self._packed
+
+
+class EdgeConvMotion(FusedModule):
+    """`EdgeConvMotion(nn_x, nn_pos, aggr='max')` — models/basic_modules.py:179-199.
+    forward(pos, x, edge_index) -> [N, H + Dp]."""
+
+    def __init__(self, nn_x: nn.Sequential, nn_pos: nn.Sequential, aggr: str = "max", **kwargs):
+        super().__init__()
+        if aggr != "max":
+            raise NotImplementedError("only aggr='max' is used by the rigging networks")
+        self.nn_x = nn_x
+        self.nn_pos = nn_pos
+
+    def forward(self, pos: torch.Tensor, x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+        self._guard(pos, x, edge_index)
+        x = x.unsqueeze(-1) if x.dim() == 1 else x
+        pos = _lib.require_cuda(pos, "pos")
+        x = _lib.require_cuda(x, "x")
+        n, dev = x.shape[0], x.device
+
+        def build():
+            sd = self._device_state()
+            wp_x, wq_x, b_x, br_x = packing._edge_mlp_parts(sd, "nn_x")
+            wp_p, wq_p, b_p, br_p = packing._edge_mlp_parts(sd, "nn_pos")
+            pq_x = packing.DenseLayer(W=packing._pack_wt(torch.cat([wp_x, wq_x])), K=wp_x.shape[1], N=2 * br_x.H,
+                                      bias=packing._vec(torch.cat([b_x, torch.zeros_like(b_x)])))
+            pq_p = packing.DenseLayer(W=packing._pack_wt(torch.cat([wp_p, wq_p])), K=wp_p.shape[1], N=2 * br_p.H,
+                                      bias=packing._vec(torch.cat([b_p, torch.zeros_like(b_p)])))
+            return pq_x, br_x, pq_p, br_p
+
+        pq_x, br_x, pq_p, br_p = self._packed_for("edge", build)
+        g = self._graphs.get(edge_index, n)
+        H, Dp = br_x.H, br_p.H
+        out = torch.empty(n, H + Dp, device=dev, dtype=torch.float32)
+        engine.fill(out, engine.NEG_INF)
+        for layer, br, src, off in ((pq_x, br_x, x, 0), (pq_p, br_p, pos, H)):
+            buf = self._ws.get(f"pq{off}", (n, layer.N), dev)
+            engine.dense(layer, src, 0, src.shape[1], n, C=buf, ldc=layer.N)
+            engine.edgeconv(br, buf, layer.N, 0, br.H, g, 1, out, H + Dp, off)
+        return out
+
+
+class GCUMotion(FusedModule):
+    """`GCUMotion(in_channels, out_channels, in_channel_pos=3, dim_pos_feat=16, aggr='max')` —
+    models/basic_modules.py:205-219.  forward(pos, x, tpl_edge_index, geo_edge_index) -> [N, out]."""
+
+    def __init__(self, in_channels: int, out_channels: int, in_channel_pos: int = 3, dim_pos_feat: int = 16,
+                 aggr: str = "max"):
+        super().__init__()
+        half = out_channels // 2
+        self.edge_conv_tpl = EdgeConvMotion(nn_x=MLP([in_channels * 2, half, half]),
+                                            nn_pos=MLP([in_channel_pos * 2, dim_pos_feat, dim_pos_feat]), aggr=aggr)
+        self.edge_conv_geo = EdgeConvMotion(nn_x=MLP([in_channels * 2, half, half]),
+                                            nn_pos=MLP([in_channel_pos * 2, dim_pos_feat, dim_pos_feat]), aggr=aggr)
+        self.mlp = MLP([out_channels + dim_pos_feat * 2, out_channels])
+
+    def forward(self, pos, x, tpl_edge_index, geo_edge_index) -> torch.Tensor:
+        self._guard(pos, x, tpl_edge_index, geo_edge_index)
+        x = x.unsqueeze(-1) if x.dim() == 1 else x
+        pos = _lib.require_cuda(pos, "pos")
+        x = _lib.require_cuda(x, "x")
+        n, dev = x.shape[0], x.device
+
+        def build():
+            parts: list = []
+            sd ={"g." + k: v for k, v in self._device_state().items()}
+            gp = packing.pack_gcu(sd, "g", parts)
+            return gp, packing.fuse_pos_pq(parts)
+
+        gp, pq_pos = self._packed_for("gcu", build)
+        gt = self._graphs.get(tpl_edge_index, n)
+        gg = self._graphs.get(geo_edge_index, n)
+        pqpos = self._ws.get("pqpos", (n, pq_pos.N), dev)
+        engine.dense(pq_pos, pos, 0, pos.shape[1], n, C=pqpos, ldc=pq_pos.N)
+        out = torch.empty(n, gp.out, device=dev, dtype=torch.float32)
+        engine.run_gcu(self._ws, "gcu", gp, x, 0, x.shape[1], x.shape[1], pqpos, gt, gg, n, 1, out, 0, gp.out)
+        return out

@@ -1,0 +1,132 @@
+// Host launchers for the FP32 tile engine (vertex dense layers, fused EdgeConv branch) and the
+// narrow-channel EdgeConv branch kernel (H <= 32: warp per target vertex, lanes = channels).
+#include "gemm_simt.cuh"
+
+namespace morig {
+
+// ---- narrow EdgeConv branch --------------------------------------------------------------------
+// One warp per (key-frame, target vertex).  H lanes hold the H output channels; 32/H edges of the
+// segment are processed side by side.  h = relu(P[i] + Q[j]) lives one channel per lane and is
+// broadcast with shuffles for the H x H second layer, whose column sits in registers.
+// No atomics: the warp owns the whole segment.
+template <int H>
+__global__ void __launch_bounds__(256) edge_small_kernel(const morig_edge_desc d) {
+    constexpr int G = 32 / H;                       // edges in flight per warp
+    const int lane = threadIdx.x & 31;
+    const int c = lane % H, sub = lane / H;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= (int64_t)d.N * d.n_frames) return;
+    const int f = (int)(w / d.N), i = (int)(w % d.N);
+    const size_t fb = (size_t)f * d.N;
+
+    float wcol[H];
+#pragma unroll
+    for (int k = 0; k < H; ++k) wcol[k] = d.W1[(size_t)k * d.ldw + c];
+    const float b1 = d.b1[c], sc = d.scale[c], sh = d.shift[c];
+
+    const float pi = d.PQ[(fb + i) * (size_t)d.ldpq + d.p_off + c];
+    const int lo = d.rowptr[i], hi = d.rowptr[i + 1];
+    float m = neg_inf();
+    for (int e0 = lo; e0 < hi; e0 += G) {
+        const int e = e0 + sub;
+        const bool act = e < hi;
+        const int j = act ? d.col[e] : i;
+        const float h0 = fmaxf(pi + d.PQ[(fb + j) * (size_t)d.ldpq + d.q_off + c], 0.f);
+        float acc = b1;
+#pragma unroll
+        for (int k = 0; k < H; ++k) acc = fmaf(__shfl_sync(0xffffffffu, h0, k, H), wcol[k], acc);
+        const float z = fmaf(fmaxf(acc, 0.f), sc, sh);
+        if (act) m = fmaxf(m, z);
+    }
+#pragma unroll
+    for (int off = 16; off >= H; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (sub == 0) {
+        for (int r = 0; r < d.out_repeat; ++r)
+            d.out[((size_t)(f + r) * d.N + i) * (size_t)d.ldo + d.out_off + c] = m;
+    }
+}
+
+template <int BM, int BN, int AMODE, int EPI>
+static int launch_gemm(const GemmP &p, dim3 grid, cudaStream_t stream, const char *name) {
+    auto kern = gemm_simt_kernel<BM, BN, AMODE, EPI>;
+    constexpr size_t smem = gemm_smem_bytes<BM, BN, EPI>();
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    MORIG_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        MORIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured_dev = dev;
+    }
+    kern<<<grid, GEMM_THREADS, smem, stream>>>(p);
+    MORIG_LAUNCH_CHECK(name);
+    return 0;
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace morig
+
+using namespace morig;
+
+extern "C" MORIG_API int morig_dense_fwd(const morig_dense_desc *d, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MORIG_CHECK_ARG(d && d->A && d->W, "dense_fwd: null operand");
+    MORIG_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "dense_fwd: M=%d N=%d K=%d", d->M, d->N, d->K);
+    MORIG_CHECK_ARG(d->ldw % 4 == 0 && d->ldw >= d->N && aligned16(d->W), "dense_fwd: W must be 16B aligned with ldw%%4==0");
+    MORIG_CHECK_ARG(d->C || d->pool, "dense_fwd: no output");
+    MORIG_CHECK_ARG(!d->rowbias || d->batch, "dense_fwd: rowbias needs batch");
+    MORIG_CHECK_ARG(!d->batch || (d->n_vtx > 0 && d->n_graphs > 0 && d->M % d->n_vtx == 0),
+                    "dense_fwd: M=%d not a multiple of n_vtx=%d", d->M, d->n_vtx);
+    GemmP p{};
+    p.A = d->A; p.lda = d->lda;
+    p.a_vec = (d->lda % 4 == 0 && d->K % 4 == 0 && aligned16(d->A)) ? 1 : 0;
+    p.W = d->W; p.ldw = d->ldw;
+    p.bias = d->bias; p.scale = d->scale; p.shift = d->shift;
+    p.rowbias = d->rowbias; p.ldrb = d->ldrb;
+    p.batch = d->batch; p.n_vtx = d->batch ? d->n_vtx : d->M; p.n_graphs = d->batch ? d->n_graphs : 1;
+    p.C = d->C; p.ldc = d->ldc;
+    p.c_vec = (d->C && d->ldc % 4 == 0 && aligned16(d->C)) ? 1 : 0;
+    p.pool = d->pool; p.ldpool = d->ldpool;
+    p.M = d->M; p.N = d->N; p.K = d->K; p.relu = d->relu;
+    if (d->N <= 64) {
+        dim3 grid(ceil_div(d->M, 128), ceil_div(d->N, 64), 1);
+        return launch_gemm<128, 64, AMODE_PLAIN, EPI_STORE>(p, grid, stream, "dense<128,64>");
+    }
+    dim3 grid(ceil_div(d->M, 128), ceil_div(d->N, 128), 1);
+    return launch_gemm<128, 128, AMODE_PLAIN, EPI_STORE>(p, grid, stream, "dense<128,128>");
+}
+
+extern "C" MORIG_API int morig_edgeconv_fwd(const morig_edge_desc *d, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MORIG_CHECK_ARG(d && d->PQ && d->rowptr && d->col && d->tgt && d->W1 && d->b1 && d->scale && d->shift && d->out,
+                    "edgeconv_fwd: null operand");
+    MORIG_CHECK_ARG(d->N > 0 && d->E_max >= d->N && d->n_frames >= 1 && d->out_repeat >= 1, "edgeconv_fwd: bad sizes");
+    MORIG_CHECK_ARG(d->out_repeat == 1 || d->n_frames == 1, "edgeconv_fwd: out_repeat needs n_frames == 1");
+    const int H = d->H;
+    if (H == 16 || H == 32) {
+        const int64_t warps = (int64_t)d->N * d->n_frames;
+        const unsigned blocks = (unsigned)ceil_div64(warps * 32, 256);
+        if (H == 16) edge_small_kernel<16><<<blocks, 256, 0, stream>>>(*d);
+        else edge_small_kernel<32><<<blocks, 256, 0, stream>>>(*d);
+        MORIG_LAUNCH_CHECK("edge_small_kernel");
+        return 0;
+    }
+    MORIG_CHECK_ARG(H == 64 || H == 128 || H == 256, "edgeconv_fwd: H=%d unsupported (16,32,64,128,256)", H);
+    MORIG_CHECK_ARG(d->out_repeat == 1, "edgeconv_fwd: out_repeat only for H<=32");
+    MORIG_CHECK_ARG(d->ldpq % 4 == 0 && d->p_off % 4 == 0 && d->q_off % 4 == 0 && aligned16(d->PQ),
+                    "edgeconv_fwd: PQ must be 16B aligned (ldpq, p_off, q_off multiples of 4)");
+    MORIG_CHECK_ARG(d->ldw % 4 == 0 && d->ldw >= H && aligned16(d->W1), "edgeconv_fwd: W1 alignment");
+    GemmP p{};
+    p.P = d->PQ + d->p_off; p.Q = d->PQ + d->q_off; p.ldpq = d->ldpq;
+    p.rowptr = d->rowptr; p.col = d->col; p.tgt = d->tgt; p.n_vtx_frame = d->N;
+    p.W = d->W1; p.ldw = d->ldw;
+    p.bias = d->b1; p.scale = d->scale; p.shift = d->shift;
+    p.C = d->out + d->out_off; p.ldc = d->ldo;
+    p.M = d->E_max; p.N = H; p.K = H; p.relu = 1;
+    if (H == 64) {
+        dim3 grid(ceil_div(d->E_max, 128), 1, d->n_frames);
+        return launch_gemm<128, 64, AMODE_GATHER, EPI_SEGMAX>(p, grid, stream, "edge<128,64>");
+    }
+    dim3 grid(ceil_div(d->E_max, 128), H / 128, d->n_frames);
+    return launch_gemm<128, 128, AMODE_GATHER, EPI_SEGMAX>(p, grid, stream, "edge<128,128>");
+}

@@ -1,0 +1,187 @@
+// Small memory-bound kernels of the path: key-frame cls-token attention, row L2 normalise,
+// key-frame mean/max, strided column gather (replaces torch.cat / slicing), fill.
+#include "common.cuh"
+
+namespace morig {
+
+// ---- TemporalAttn (models/rignet.py:36-44), cls query row only -------------------------------
+// One warp per vertex, lane = input channel (C <= 32).  Per head h:
+//   logit_t = u_h . x_t  (t < T),  logit_cls = l0_h;  a = softmax over the T+1 logits
+//   y_h = sum_t a_t x_t
+//   out = sum_h ( Mv_h y_h + a_cls,h * c0_h )
+// u, l0, Mv, c0 are parameter-only products prepared once by the host layer.
+constexpr int ATT_MAX_T = 8;
+constexpr int ATT_MAX_HEADS = 4;
+
+__global__ void __launch_bounds__(256) temporal_attn_kernel(const float *__restrict__ x, int N, int T, int C, int heads,
+                                                            int D, const float *__restrict__ u,
+                                                            const float *__restrict__ l0, const float *__restrict__ Mv,
+                                                            const float *__restrict__ c0, float *__restrict__ out,
+                                                            int ldo) {
+    extern __shared__ float s_mv[];                 // [heads][C][D]  (transposed for lane-contiguous reads)
+    for (int idx = threadIdx.x; idx < heads * C * D; idx += blockDim.x) {
+        const int h = idx / (C * D), rem = idx % (C * D), cc = rem / D, dd = rem % D;
+        s_mv[idx] = Mv[((size_t)h * D + dd) * C + cc];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (n >= N) return;
+    float xt[ATT_MAX_T];
+#pragma unroll
+    for (int t = 0; t < ATT_MAX_T; ++t) xt[t] = (t < T && lane < C) ? x[((size_t)n * T + t) * C + lane] : 0.f;
+
+    float y[ATT_MAX_HEADS], a_cls[ATT_MAX_HEADS];
+#pragma unroll
+    for (int h = 0; h < ATT_MAX_HEADS; ++h) {
+        y[h] = 0.f; a_cls[h] = 0.f;
+        if (h >= heads) continue;
+        const float uh = lane < C ? u[h * C + lane] : 0.f;
+        float lg[ATT_MAX_T];
+        const float lc = l0[h];
+        float mx = lc;
+#pragma unroll
+        for (int t = 0; t < ATT_MAX_T; ++t) {
+            float v = uh * xt[t];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            lg[t] = v;
+            if (t < T) mx = fmaxf(mx, v);
+        }
+        float den = expf(lc - mx);
+        const float e_cls = den;
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < ATT_MAX_T; ++t) {
+            if (t < T) {
+                const float e = expf(lg[t] - mx);
+                den += e;
+                acc = fmaf(e, xt[t], acc);
+            }
+        }
+        y[h] = acc / den;
+        a_cls[h] = e_cls / den;
+    }
+    for (int d = lane; d < D; d += 32) {
+        float o = 0.f;
+#pragma unroll
+        for (int h = 0; h < ATT_MAX_HEADS; ++h) {
+            if (h >= heads) continue;
+            o = fmaf(a_cls[h], c0[h * D + d], o);
+            for (int cc = 0; cc < C; ++cc)
+                o = fmaf(__shfl_sync(0xffffffffu, y[h], cc), s_mv[(h * C + cc) * D + d], o);
+        }
+        out[(size_t)n * ldo + d] = o;
+    }
+}
+
+// ---- F.normalize(dim=1): warp per row ------------------------------------------------------------
+__global__ void __launch_bounds__(256) row_normalize_kernel(float *x, int ldx, int R, int C, float *dst2, int N,
+                                                            int n_frames) {
+    const int lane = threadIdx.x & 31;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= R) return;
+    float *row = x + (size_t)r * ldx;
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) { const float v = row[c]; ss = fmaf(v, v, ss); }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+    float *row2 = nullptr;
+    if (dst2) { const int f = r / N, v = r % N; row2 = dst2 + ((size_t)v * n_frames + f) * C; }
+    for (int c = lane; c < C; c += 32) {
+        const float v = row[c] / denom;
+        row[c] = v;
+        if (row2) row2[c] = v;
+    }
+}
+
+__global__ void frame_reduce_kernel(const float *__restrict__ x, int N, int T, int C, int mode, float *out, int ldo) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)N * C) return;
+    const int n = (int)(idx / C), c = (int)(idx % C);
+    const float *src = x + (size_t)n * T * C + c;
+    float acc = src[0];
+    for (int t = 1; t < T; ++t) acc = mode == 0 ? acc + src[(size_t)t * C] : fmaxf(acc, src[(size_t)t * C]);
+    out[(size_t)n * ldo + c] = mode == 0 ? acc / (float)T : acc;
+}
+
+__global__ void gather_cols_kernel(const float *__restrict__ src, int lds, int src_off, int frame_stride,
+                                   const int32_t *__restrict__ cols, int C, int N, int n_frames, float *dst, int ldd,
+                                   int dst_off) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)N * n_frames * C) return;
+    const int c = (int)(idx % C);
+    const int64_t r = idx / C;
+    const int f = (int)(r / N), v = (int)(r % N);
+    const int sc = src_off + f * frame_stride + (cols ? cols[c] : c);
+    dst[(size_t)r * ldd + dst_off + c] = src[(size_t)v * lds + sc];
+}
+
+__global__ void fill_kernel(float *dst, int64_t n, float value) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = value;
+}
+
+}  // namespace morig
+
+using namespace morig;
+
+extern "C" MORIG_API int morig_temporal_attn_fwd(const float *x, int32_t N, int32_t T, int32_t C, int32_t heads, int32_t D,
+                                       const float *u, const float *l0, const float *Mv, const float *c0, float *out,
+                                       int32_t ldo, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MORIG_CHECK_ARG(x && u && l0 && Mv && c0 && out && N > 0, "temporal_attn_fwd: null operand");
+    MORIG_CHECK_ARG(T >= 1 && T <= ATT_MAX_T, "temporal_attn_fwd: T=%d unsupported (1..%d key-frames)", T, ATT_MAX_T);
+    MORIG_CHECK_ARG(C >= 1 && C <= 32, "temporal_attn_fwd: C=%d unsupported (<=32)", C);
+    MORIG_CHECK_ARG(heads >= 1 && heads <= ATT_MAX_HEADS, "temporal_attn_fwd: heads=%d unsupported", heads);
+    MORIG_CHECK_ARG(D >= 32 && D % 32 == 0 && (size_t)heads * C * D * 4 <= 48 * 1024,
+                    "temporal_attn_fwd: D=%d unsupported (multiple of 32)", D);
+    const int T_ = 256;
+    temporal_attn_kernel<<<ceil_div(N * 32, T_), T_, (size_t)heads * C * D * sizeof(float), stream>>>(
+        x, N, T, C, heads, D, u, l0, Mv, c0, out, ldo);
+    MORIG_LAUNCH_CHECK("temporal_attn_kernel");
+    return 0;
+}
+
+extern "C" MORIG_API int morig_row_normalize(float *x, int32_t ldx, int32_t R, int32_t C, float *dst2, int32_t N, int32_t n_frames,
+                                   void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MORIG_CHECK_ARG(x && R > 0 && C > 0 && ldx >= C, "row_normalize: bad argument");
+    MORIG_CHECK_ARG(!dst2 || (N > 0 && n_frames > 0 && R == N * n_frames), "row_normalize: R != N * n_frames");
+    row_normalize_kernel<<<(unsigned)ceil_div64((int64_t)R * 32, 256), 256, 0, stream>>>(x, ldx, R, C, dst2, N, n_frames);
+    MORIG_LAUNCH_CHECK("row_normalize_kernel");
+    return 0;
+}
+
+extern "C" MORIG_API int morig_frame_reduce(const float *x, int32_t N, int32_t T, int32_t C, int32_t mode, float *out, int32_t ldo,
+                                  void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MORIG_CHECK_ARG(x && out && N > 0 && T > 0 && C > 0 && (mode == 0 || mode == 1), "frame_reduce: bad argument");
+    frame_reduce_kernel<<<(unsigned)ceil_div64((int64_t)N * C, 256), 256, 0, stream>>>(x, N, T, C, mode, out, ldo);
+    MORIG_LAUNCH_CHECK("frame_reduce_kernel");
+    return 0;
+}
+
+extern "C" MORIG_API int morig_gather_cols(const float *src, int32_t lds, int32_t src_off, int32_t frame_stride,
+                                 const int32_t *cols, int32_t C, int32_t N, int32_t n_frames, float *dst, int32_t ldd,
+                                 int32_t dst_off, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MORIG_CHECK_ARG(src && dst && C > 0 && N > 0 && n_frames > 0, "gather_cols: bad argument");
+    const int64_t total = (int64_t)N * n_frames * C;
+    gather_cols_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(src, lds, src_off, frame_stride, cols, C, N,
+                                                                            n_frames, dst, ldd, dst_off);
+    MORIG_LAUNCH_CHECK("gather_cols_kernel");
+    return 0;
+}
+
+extern "C" MORIG_API int morig_fill_f32(float *dst, int64_t n, float value, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MORIG_CHECK_ARG(dst && n >= 0, "fill_f32: bad argument");
+    if (n == 0) return 0;
+    const int64_t blocks = ceil_div64(n, 256);
+    fill_kernel<<<(unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, stream>>>(dst, n, value);
+    MORIG_LAUNCH_CHECK("fill_kernel");
+    return 0;
+}

@@ -1,0 +1,291 @@
+"""Host-side orchestration of the CUDA forward path: buffer reuse, graph preparation cache and the
+launch sequences for GCNRig / TemporalAttn / SkinNet_inner.  All arithmetic happens in
+`libmorig_b200.so`; this file only allocates torch tensors and fills descriptors.
+
+Data layout in HBM (fp32, row-major; R = n_frames * N rows, key-frame f owns rows [f*N, (f+1)*N)):
+
+  feat [R, ldf]         = [ x1 (64) | x2 (256) | x3 (512) | feature (F) | pos (3) | 0-pad to 32 ]
+                          written in place by the GCU layers, read (strided) by the next ones, so
+                          the reference's torch.cat calls (models/rignet.py:62,65) never happen
+  ec_k [R, 2(H+Dp)]     = [ tpl: x-branch (H) | pos-branch (Dp) | geo: x-branch | pos-branch ]
+                          EdgeConv outputs of GCU k in the order GCUMotion concatenates them
+                          (models/basic_modules.py:215-217)
+  pq_k [R, 4H]          = [ P_tpl | Q_tpl | P_geo | Q_geo ]   factorised first edge Linear
+  pqpos [N, 3*4*Dp]     = same for the pos branches of the three GCUs (key-frame independent)
+  xg / gb [n_frames*B, 1024]  per-graph max pool and the per-graph bias derived from it
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .packing import AttnPack, DenseLayer, EdgeBranch, GCNRigPack, GCUPack, SkinPack
+
+NEG_INF = float("-inf")
+
+
+class Workspace:
+    """Named device buffers reused across calls (stable pointers, no allocator traffic)."""
+
+    def __init__(self):
+        self._bufs: Dict[Tuple, torch.Tensor] = {}
+
+    def get(self, name: str, shape, device, dtype=torch.float32, zero: bool = False) -> torch.Tensor:
+        key = (name, tuple(shape), dtype, str(device))
+        t = self._bufs.get(key)
+        if t is None:
+            # drop stale shapes of the same name so the cache does not grow with varying batch sizes
+            for k in [k for k in self._bufs if k[0] == name and k[3] == str(device)]:
+                del self._bufs[k]
+            t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=device)
+            self._bufs[key] = t
+        return t
+
+    def clear(self):
+        self._bufs.clear()
+
+
+@dataclass
+class Graph:
+    rowptr: torch.Tensor
+    col: torch.Tensor
+    tgt: torch.Tensor
+    n: int
+    e_max: int
+
+
+def graph_prep(edge_index: torch.Tensor, n: int) -> Graph:
+    """`morig_graph_prep` on a [2, E] int64 CUDA tensor."""
+    lib = _lib.load()
+    if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise ValueError(f"edge_index must be [2, E], got {tuple(edge_index.shape)}")
+    ei = _lib.require_cuda(edge_index, "edge_index", torch.int64)
+    e = ei.shape[1]
+    dev = ei.device
+    rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(e + n, dtype=torch.int32, device=dev)
+    tgt = torch.empty(e + n, dtype=torch.int32, device=dev)
+    ws_bytes = lib.morig_graph_prep_workspace(e, n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.morig_graph_prep(ei.data_ptr(), e, n, rowptr.data_ptr(), col.data_ptr(), tgt.data_ptr(),
+                                    ws.data_ptr(), ws_bytes, _lib.stream_ptr()), "morig_graph_prep")
+    return Graph(rowptr=rowptr, col=col, tgt=tgt, n=n, e_max=e + n)
+
+
+class GraphCache:
+    """Keeps the CSR of the most recent edge-index tensors.  Entries are matched by tensor identity
+    and in-place version and hold a strong reference, so a recycled allocation can never alias."""
+
+    def __init__(self, slots: int = 4):
+        self._slots = slots
+        self._entries: list = []   # (tensor, version, n, Graph)
+
+    def get(self, edge_index: torch.Tensor, n: int) -> Graph:
+        for ent in self._entries:
+            if ent[0] is edge_index and ent[1] == edge_index._version and ent[2] == n:
+                return ent[3]
+        g = graph_prep(edge_index, n)
+        self._entries.insert(0, (edge_index, edge_index._version, n, g))
+        del self._entries[self._slots:]
+        return g
+
+
+@dataclass
+class BatchInfo:
+    batch32: torch.Tensor
+    n_graphs: int
+
+
+class BatchCache:
+    def __init__(self):
+        self._ent = None
+
+    def get(self, batch: torch.Tensor, data=None) -> BatchInfo:
+        ent = self._ent
+        if ent is not None and ent[0] is batch and ent[1] == batch._version:
+            return ent[2]
+        b = _lib.require_cuda(batch, "batch", torch.int64)
+        ng = getattr(data, "num_graphs", None) if data is not None else None
+        if ng is None:
+            ng = int(b[-1].item()) + 1         # `batch` is sorted (PyG collation): last id = B - 1
+        info = BatchInfo(batch32=b.to(torch.int32), n_graphs=int(ng))
+        self._ent = (batch, batch._version, info)
+        return info
+
+
+# ---- thin launch helpers ---------------------------------------------------------------------------
+
+def dense(layer: DenseLayer, A: torch.Tensor, a_off: int, lda: int, M: int, *, K: Optional[int] = None,
+          C: Optional[torch.Tensor] = None, c_off: int = 0, ldc: int = 0,
+          pool: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None,
+          binfo: Optional[BatchInfo] = None, n_vtx: int = 0) -> None:
+    lib = _lib.load()
+    d = _lib.DenseDesc()
+    d.A = A.data_ptr() + 4 * a_off
+    d.lda = lda
+    d.W, d.ldw = layer.W.data_ptr(), layer.ldw
+    d.bias, d.scale, d.shift = _lib.ptr(layer.bias), _lib.ptr(layer.scale), _lib.ptr(layer.shift)
+    d.rowbias, d.ldrb = _lib.ptr(rowbias), (rowbias.shape[1] if rowbias is not None else 0)
+    if binfo is not None:
+        d.batch, d.n_vtx, d.n_graphs = binfo.batch32.data_ptr(), n_vtx, binfo.n_graphs
+    d.C, d.ldc = (C.data_ptr() + 4 * c_off if C is not None else 0), ldc
+    d.pool, d.ldpool = _lib.ptr(pool), (pool.shape[1] if pool is not None else 0)
+    d.M, d.N, d.K = M, layer.N, (layer.K if K is None else K)
+    d.relu = 1 if layer.relu else 0
+    _lib.check(lib.morig_dense_fwd(ctypes.byref(d), _lib.stream_ptr()), "morig_dense_fwd")
+
+
+def edgeconv(br: EdgeBranch, pq: torch.Tensor, ldpq: int, p_off: int, q_off: int, g: Graph, n_frames: int,
+             out: torch.Tensor, ldo: int, out_off: int, out_repeat: int = 1) -> None:
+    lib = _lib.load()
+    d = _lib.EdgeDesc()
+    d.PQ, d.ldpq, d.p_off, d.q_off = pq.data_ptr(), ldpq, p_off, q_off
+    d.rowptr, d.col, d.tgt = g.rowptr.data_ptr(), g.col.data_ptr(), g.tgt.data_ptr()
+    d.N, d.E_max, d.n_frames, d.out_repeat = g.n, g.e_max, n_frames, out_repeat
+    d.W1, d.ldw = br.W1.data_ptr(), br.W1.shape[1]
+    d.b1, d.scale, d.shift = br.b1.data_ptr(), br.scale.data_ptr(), br.shift.data_ptr()
+    d.out, d.ldo, d.out_off = out.data_ptr(), ldo, out_off
+    d.H = br.H
+    _lib.check(lib.morig_edgeconv_fwd(ctypes.byref(d), _lib.stream_ptr()), "morig_edgeconv_fwd")
+
+
+def fill(t: torch.Tensor, value: float) -> None:
+    _lib.check(_lib.load().morig_fill_f32(t.data_ptr(), t.numel(), value, _lib.stream_ptr()), "morig_fill_f32")
+
+
+def gather_cols(src: torch.Tensor, lds: int, src_off: int, frame_stride: int, cols: Optional[torch.Tensor], c: int,
+                n: int, n_frames: int, dst: torch.Tensor, ldd: int, dst_off: int) -> None:
+    _lib.check(_lib.load().morig_gather_cols(src.data_ptr(), lds, src_off, frame_stride, _lib.ptr(cols), c, n,
+                                             n_frames, dst.data_ptr(), ldd, dst_off, _lib.stream_ptr()),
+               "morig_gather_cols")
+
+
+def row_normalize(x: torch.Tensor, ldx: int, rows: int, c: int, dst2: Optional[torch.Tensor] = None, n: int = 0,
+                  n_frames: int = 0) -> None:
+    _lib.check(_lib.load().morig_row_normalize(x.data_ptr(), ldx, rows, c, _lib.ptr(dst2), n, n_frames,
+                                               _lib.stream_ptr()), "morig_row_normalize")
+
+
+# ---- layer sequences -------------------------------------------------------------------------------
+
+def run_gcu(ws: Workspace, tag: str, gp: GCUPack, x: torch.Tensor, x_off: int, ldx: int, k_x: int,
+            pqpos: torch.Tensor, gt: Graph, gg: Graph, n: int, n_frames: int,
+            out: torch.Tensor, out_off: int, ldo: int) -> None:
+    """One GCUMotion (models/basic_modules.py:205-219): both EdgeConvMotion branches on both edge sets,
+    then the vertex mlp, written to out[:, out_off : out_off + gp.out]."""
+    dev = x.device
+    R = n * n_frames
+    H, Dp = gp.H, gp.Dp
+    wec = 2 * (H + Dp)
+    pq = ws.get(tag + ".pq", (R, 4 * H), dev)
+    ec = ws.get(tag + ".ec", (R, wec), dev)
+    dense(gp.pq_x, x, x_off, ldx, R, K=k_x, C=pq, ldc=4 * H)
+    if H >= 64 or Dp >= 64:
+        fill(ec, NEG_INF)       # tiles of the wide kernel merge straddling segments with atomic max
+    ldpp = pqpos.shape[1]
+    for s, (g, bx, bp) in enumerate(((gt, gp.x_tpl, gp.pos_tpl), (gg, gp.x_geo, gp.pos_geo))):
+        base = s * (H + Dp)
+        edgeconv(bx, pq, 4 * H, 2 * s * H, 2 * s * H + H, g, n_frames, ec, wec, base)
+        pc = gp.pos_col + 2 * s * Dp
+        if Dp >= 64:            # wide pos branch (skinning net): key-frame count is 1 there
+            edgeconv(bp, pqpos, ldpp, pc, pc + Dp, g, 1, ec, wec, base + H)
+        else:
+            edgeconv(bp, pqpos, ldpp, pc, pc + Dp, g, 1, ec, wec, base + H, out_repeat=n_frames)
+    dense(gp.mlp, ec, 0, wec, R, C=out, c_off=out_off, ldc=ldo)
+
+
+def run_gcn_rig(ws: Workspace, tag: str, pk: GCNRigPack, pos: torch.Tensor, feature: torch.Tensor,
+                feat_lds: int, feat_frame_stride: int, gt: Graph, gg: Graph, binfo: BatchInfo,
+                n_frames: int) -> torch.Tensor:
+    """GCNRig.forward (models/rignet.py:58-67) for `n_frames` key-frames at once (shared weights and
+    graph, models/rignet.py:85-86).  `feature` is [N, feat_lds]; key-frame f reads columns
+    [f*feat_frame_stride, f*feat_frame_stride + F).  Returns [n_frames*N, O] (workspace buffer)."""
+    dev = pos.device
+    n = pos.shape[0]
+    R = n * n_frames
+    G = n_frames * binfo.n_graphs
+    F, ldf = pk.F, pk.ldf
+    feat = ws.get(tag + ".feat", (R, ldf), dev, zero=True)       # pad columns stay zero forever
+    gather_cols(feature, feat_lds, 0, feat_frame_stride, None, F, n, n_frames, feat, ldf, pk.feat_off)
+    gather_cols(pos, 3, 0, 0, None, 3, n, n_frames, feat, ldf, pk.pos_off)
+    pqpos = ws.get(tag + ".pqpos", (n, pk.pq_pos.N), dev)
+    dense(pk.pq_pos, pos, 0, 3, n, C=pqpos, ldc=pk.pq_pos.N)
+    # GCU chain: input of gcu_1 is the feature block, of gcu_2 / gcu_3 the previous output block
+    srcs = [(pk.feat_off, pk.gcus[0].pq_x.K), (pk.x_off[0], pk.gcus[1].pq_x.K), (pk.x_off[1], pk.gcus[2].pq_x.K)]
+    for k, gp in enumerate(pk.gcus):
+        run_gcu(ws, f"{tag}.gcu{k}", gp, feat, srcs[k][0], ldf, srcs[k][1], pqpos, gt, gg, n, n_frames,
+                feat, pk.x_off[k], ldf)
+    xg = ws.get(tag + ".xg", (G, pk.glb.N), dev)
+    fill(xg, NEG_INF)
+    dense(pk.glb, feat, 0, ldf, R, pool=xg, binfo=binfo, n_vtx=n)                     # x_4 is never stored
+    gb = ws.get(tag + ".gb", (G, pk.t0_global.N), dev)
+    dense(pk.t0_global, xg, 0, pk.glb.N, G, C=gb, ldc=pk.t0_global.N)
+    h1 = ws.get(tag + ".h1", (R, pk.t0.N), dev)
+    dense(pk.t0, feat, 0, ldf, R, C=h1, ldc=pk.t0.N, rowbias=gb, binfo=binfo, n_vtx=n)
+    h2 = ws.get(tag + ".h2", (R, pk.t1.N), dev)
+    dense(pk.t1, h1, 0, pk.t0.N, R, C=h2, ldc=pk.t1.N)
+    out = ws.get(tag + ".out", (R, pk.O), dev)
+    dense(pk.head, h2, 0, pk.t1.N, R, C=out, ldc=pk.O)
+    return out
+
+
+def temporal_attn(pk: AttnPack, x: torch.Tensor, out: torch.Tensor) -> None:
+    n, t, c = x.shape
+    _lib.check(_lib.load().morig_temporal_attn_fwd(x.data_ptr(), n, t, c, pk.heads, pk.D, pk.u.data_ptr(),
+                                                   pk.l0.data_ptr(), pk.Mv.data_ptr(), pk.c0.data_ptr(),
+                                                   out.data_ptr(), out.shape[1], _lib.stream_ptr()),
+               "morig_temporal_attn_fwd")
+
+
+def frame_reduce(x: torch.Tensor, mode: str, out: torch.Tensor) -> None:
+    n, t, c = x.shape
+    _lib.check(_lib.load().morig_frame_reduce(x.data_ptr(), n, t, c, 0 if mode == "mean" else 1, out.data_ptr(),
+                                              out.shape[1], _lib.stream_ptr()), "morig_frame_reduce")
+
+
+def run_temporal_attn(ws: Workspace, tag: str, pk: AttnPack, x: torch.Tensor, out: torch.Tensor) -> None:
+    """TemporalAttn.forward (models/rignet.py:36-46): x [N, T, C] -> out [N, ff1.N] (not normalised)."""
+    n = x.shape[0]
+    dev = x.device
+    a = ws.get(tag + ".attn", (n, pk.D), dev)
+    temporal_attn(pk, x, a)
+    h = ws.get(tag + ".ff", (n, pk.ff0.N), dev)
+    dense(pk.ff0, a, 0, pk.D, n, C=h, ldc=pk.ff0.N)
+    dense(pk.ff1, h, 0, pk.ff0.N, n, C=out, ldc=out.shape[1])
+
+
+def run_skin(ws: Workspace, tag: str, pk: SkinPack, pos: torch.Tensor, skin_input: torch.Tensor,
+             motion: torch.Tensor, gt: Graph, gg: Graph, binfo: BatchInfo) -> torch.Tensor:
+    """SkinNet_inner.forward (models/rignet.py:158-182). Returns [N, nearest_bone] logits."""
+    dev = pos.device
+    n = pos.shape[0]
+    B = binfo.n_graphs
+    raw = ws.get(tag + ".raw", (n, pk.k_pos), dev, zero=True)                  # [pos | samples | 0-pad]
+    gather_cols(pos, 3, 0, 0, None, 3, n, 1, raw, pk.k_pos, 0)
+    gather_cols(skin_input, skin_input.shape[1], 0, 0, pk.skin_cols, pk.in_pos - 3, n, 1, raw, pk.k_pos, 3)
+    pqpos = ws.get(tag + ".pqpos", (n, pk.pq_pos.N), dev)
+    dense(pk.pq_pos, raw, 0, pk.k_pos, n, C=pqpos, ldc=pk.pq_pos.N)
+    c = pk.gcus[0].out
+    xs = [ws.get(f"{tag}.x{k}", (n, c), dev) for k in range(3)]
+    run_gcu(ws, tag + ".gcu0", pk.gcus[0], motion, 0, motion.shape[1], pk.gcus[0].pq_x.K, pqpos, gt, gg, n, 1,
+            xs[0], 0, c)
+    g0 = ws.get(tag + ".g0", (n, pk.g0.N), dev)
+    dense(pk.g0, xs[0], 0, c, n, C=g0, ldc=pk.g0.N)
+    xg = ws.get(tag + ".xg", (B, pk.g1.N), dev)
+    fill(xg, NEG_INF)
+    dense(pk.g1, g0, 0, pk.g0.N, n, pool=xg, binfo=binfo, n_vtx=n)
+    run_gcu(ws, tag + ".gcu1", pk.gcus[1], xs[0], 0, c, c, pqpos, gt, gg, n, 1, xs[1], 0, c)
+    run_gcu(ws, tag + ".gcu2", pk.gcus[2], xs[1], 0, c, c, pqpos, gt, gg, n, 1, xs[2], 0, c)
+    gb = ws.get(tag + ".gb", (B, pk.c0_global.N), dev)
+    dense(pk.c0_global, xg, 0, pk.g1.N, B, C=gb, ldc=pk.c0_global.N)
+    h1 = ws.get(tag + ".h1", (n, pk.c0.N), dev)
+    dense(pk.c0, xs[2], 0, c, n, C=h1, ldc=pk.c0.N, rowbias=gb, binfo=binfo, n_vtx=n)
+    h2 = ws.get(tag + ".h2", (n, pk.c1.N), dev)
+    dense(pk.c1, h1, 0, pk.c0.N, n, C=h2, ldc=pk.c1.N)
+    out = ws.get(tag + ".out", (n, pk.head.N), dev)
+    dense(pk.head, h2, 0, pk.c1.N, n, C=out, ldc=pk.head.N)
+    return out

@@ -1,0 +1,235 @@
+"""Drop-in replacements for the reference's motion-aware rigging networks (`models/rignet.py`):
+`jointnet_motion`, `masknet_motion`, `skinnet_motion` and the classes behind them, with the
+reference's constructor arguments, `forward(data, input_flow)` signatures, return triples and
+`state_dict` keys (including its spellings `aggragator`, `multi_layer_tranform2`), so they can be
+swapped into `training/train_rig.py:83`, `training/train_skin.py:83` and `evaluate/joint2rig.py:473`.
+
+Every forward launches the fused sm_100a kernels of `libmorig_b200.so` through `engine.py`; the five
+key-frame passes of the motion encoder (same weights, same graph: models/rignet.py:85-86) run as one
+5x-row batch.  Inference only (eval BatchNorm, no autograd) in this round.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import _lib, engine, packing
+from .basic_modules import MLP, FusedModule, GCUMotion
+
+__all__ = ["jointnet_motion", "masknet_motion", "skinnet_motion"]
+
+
+class TemporalAttn(FusedModule):
+    """`TemporalAttn(input_size, num_heads, hidden_size, dim_feedforward, output_size)` —
+    models/rignet.py:10-46.  forward(x [N, T, C]) -> [N, output_size]."""
+
+    def __init__(self, input_size, num_heads, hidden_size, dim_feedforward, output_size):
+        super().__init__()
+        self.num_heads = num_heads
+        self.w_qs = nn.Linear(input_size, hidden_size * num_heads, bias=False)
+        self.w_ks = nn.Linear(input_size, hidden_size * num_heads, bias=False)
+        self.w_vs = nn.Linear(input_size, hidden_size * num_heads, bias=False)
+        self.w_o = nn.Linear(hidden_size * num_heads, hidden_size, bias=False)
+        self.feedforward = MLP([hidden_size, dim_feedforward, output_size])
+        self.cls_token = nn.Parameter(torch.randn(1, 1, input_size))
+
+    def pack(self, sd=None, prefix="p") -> packing.AttnPack:
+        sd = {prefix + "." + k: v for k, v in self._device_state().items()} if sd is None else sd
+        return packing.pack_temporal_attn(sd, prefix, self.num_heads)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self._guard(x)
+        x = _lib.require_cuda(x, "x")
+        pk = self._packed_for("attn", self.pack)
+        out = torch.empty(x.shape[0], pk.ff1.N, device=x.device, dtype=torch.float32)
+        engine.run_temporal_attn(self._ws, "attn", pk, x, out)
+        return out
+
+
+class GCNRig(FusedModule):
+    """`GCNRig(chn_feature, chn_output, aggr='max')` — models/rignet.py:49-67.
+    forward(pos, feature, tpl_edge_index, geo_edge_index, batch) -> [N, chn_output]."""
+
+    def __init__(self, chn_feature, chn_output, aggr="max"):
+        super().__init__()
+        self.gcu_1 = GCUMotion(in_channels=chn_feature, out_channels=64, dim_pos_feat=16, aggr=aggr)
+        self.gcu_2 = GCUMotion(in_channels=64, out_channels=256, dim_pos_feat=16, aggr=aggr)
+        self.gcu_3 = GCUMotion(in_channels=256, out_channels=512, dim_pos_feat=16, aggr=aggr)
+        self.mlp_glb = MLP([(64 + 256 + 512), 1024])
+        self.mlp_transform = nn.Sequential(MLP([1024 + 3 + chn_feature + 64 + 256 + 512, 1024, 256]),
+                                           nn.Linear(256, chn_output))
+
+    def pack(self) -> packing.GCNRigPack:
+        sd = {"p." + k: v for k, v in self._device_state().items()}
+        return packing.pack_gcn_rig(sd, "p")
+
+    def run(self, ws, tag, pos, feature, feat_lds, frame_stride, gt, gg, binfo, n_frames):
+        pk = self._packed_for("rig", self.pack)
+        return engine.run_gcn_rig(ws, tag, pk, pos, feature, feat_lds, frame_stride, gt, gg, binfo, n_frames)
+
+    def forward(self, pos, feature, tpl_edge_index, geo_edge_index, batch) -> torch.Tensor:
+        self._guard(pos, feature, tpl_edge_index, geo_edge_index, batch)
+        pos = _lib.require_cuda(pos, "pos")
+        feature = feature.unsqueeze(-1) if feature.dim() == 1 else feature
+        feature = _lib.require_cuda(feature, "feature")
+        n = pos.shape[0]
+        gt = self._graphs.get(tpl_edge_index, n)
+        gg = self._graphs.get(geo_edge_index, n)
+        binfo = self._batches.get(batch)
+        out = self.run(self._ws, "rig", pos, feature, feature.shape[1], 0, gt, gg, binfo, 1)
+        return out.clone()
+
+
+class _MotionNet(FusedModule):
+    """Shared body of JointNetMotion / MaskNetMotion / SkinMotion: key-frame motion encoder, temporal
+    aggregation, then a task head (models/rignet.py:82-100, 115-133, 194-205)."""
+
+    num_keyframes: int
+
+    def _inputs(self, data, input_flow):
+        self._guard(data.pos, input_flow, data.tpl_edge_index, data.geo_edge_index, data.batch)
+        pos = _lib.require_cuda(data.pos, "data.pos")
+        flow = _lib.require_cuda(input_flow, "input_flow")
+        n = pos.shape[0]
+        if flow.shape[0] != n or flow.shape[1] < 3 * self.num_keyframes:
+            raise ValueError(f"input_flow must be [N, >= {3 * self.num_keyframes}], got {tuple(flow.shape)}")
+        gt = self._graphs.get(data.tpl_edge_index, n)
+        gg = self._graphs.get(data.geo_edge_index, n)
+        binfo = self._batches.get(data.batch, data)
+        return pos, flow, n, gt, gg, binfo
+
+    def _encode(self, pos, flow, n, gt, gg, binfo, dim):
+        """motionNet on all key-frames at once + per-row normalize + stack -> motion_all [N, T, dim]"""
+        T = self.num_keyframes
+        m = self.motionNet.run(self._ws, "motion", pos, flow, flow.shape[1], 3, gt, gg, binfo, T)   # [T*N, dim]
+        motion_all = torch.empty(n, T, dim, device=pos.device, dtype=torch.float32)
+        engine.row_normalize(m, dim, T * n, dim, dst2=motion_all, n=n, n_frames=T)
+        return motion_all
+
+    def _aggregate(self, motion_all, aggr_method, out_dim):
+        n, T, c = motion_all.shape
+        if aggr_method == "attn":
+            aggr = torch.empty(n, out_dim, device=motion_all.device, dtype=torch.float32)
+            pk = self.aggragator._packed_for("attn", self.aggragator.pack)
+            engine.run_temporal_attn(self._ws, "aggr", pk, motion_all, aggr)
+        elif aggr_method in ("mean", "max"):
+            aggr = torch.empty(n, c, device=motion_all.device, dtype=torch.float32)
+            engine.frame_reduce(motion_all, aggr_method, aggr)
+        else:
+            raise NotImplementedError(aggr_method)
+        engine.row_normalize(aggr, aggr.shape[1], n, aggr.shape[1])
+        return aggr
+
+
+class _JointMaskBase(_MotionNet):
+    _head_name = "jointnet"
+
+    def __init__(self, num_keyframes, chn_output, aggr_method, aggr="max"):
+        super().__init__()
+        self.num_keyframes = num_keyframes
+        self.aggr_method = aggr_method
+        self.motionNet = GCNRig(chn_feature=3, chn_output=32, aggr=aggr)
+        if self.aggr_method == "attn":
+            self.aggragator = TemporalAttn(input_size=32, num_heads=2, hidden_size=64, dim_feedforward=512,
+                                           output_size=64)
+            head = GCNRig(chn_feature=64, chn_output=chn_output, aggr=aggr)
+        else:
+            head = GCNRig(chn_feature=32, chn_output=chn_output, aggr=aggr)
+        setattr(self, self._head_name, head)
+
+    def forward(self, data, input_flow):
+        pos, flow, n, gt, gg, binfo = self._inputs(data, input_flow)
+        motion_all = self._encode(pos, flow, n, gt, gg, binfo, 32)
+        motion_aggr = self._aggregate(motion_all, self.aggr_method, 64)
+        head = getattr(self, self._head_name)
+        pred = head.run(self._ws, "head", pos, motion_aggr, motion_aggr.shape[1], 0, gt, gg, binfo, 1)
+        return motion_all, motion_aggr, pred.clone()
+
+
+class JointNetMotion(_JointMaskBase):
+    """models/rignet.py:70-100 — returns (motion_all [N,T,32], motion_aggr [N,64|32], pred_shift [N,chn_output])."""
+    _head_name = "jointnet"
+
+
+class MaskNetMotion(_JointMaskBase):
+    """models/rignet.py:103-133 — returns (motion_all, motion_aggr, pred_mask [N,chn_output])."""
+    _head_name = "masknet"
+
+
+class SkinNet_inner(FusedModule):
+    """`SkinNet_inner(nearest_bone, use_Dg, use_Lf, motion_dim, use_motion, aggr='max')` —
+    models/rignet.py:136-182.  forward(data, motion) -> [N, nearest_bone] logits."""
+
+    def __init__(self, nearest_bone, use_Dg, use_Lf, motion_dim, use_motion, aggr="max"):
+        super().__init__()
+        self.use_Dg = use_Dg
+        self.use_Lf = use_Lf
+        self.num_nearest_bone = nearest_bone
+        per_bone = 6 + int(bool(use_Dg)) + int(bool(use_Lf))
+        input_dim = 3 + nearest_bone * per_bone
+        self.gcu1 = GCUMotion(in_channels=motion_dim, out_channels=256, in_channel_pos=input_dim, dim_pos_feat=64, aggr=aggr)
+        self.gcu2 = GCUMotion(in_channels=256, out_channels=256, in_channel_pos=input_dim, dim_pos_feat=64, aggr=aggr)
+        self.gcu3 = GCUMotion(in_channels=256, out_channels=256, in_channel_pos=input_dim, dim_pos_feat=64, aggr=aggr)
+        self.multi_layer_tranform2 = MLP([256, 512, 1024])
+        self.cls_branch = nn.Sequential(MLP([1024 + 256, 1024, 512]), nn.Linear(512, nearest_bone))
+
+    def run(self, ws, tag, data, pos, motion, gt, gg, binfo):
+        skin = _lib.require_cuda(data.skin_input, "data.skin_input")
+        width = skin.shape[1]
+
+        def build():
+            sd = {"p." + k: v for k, v in self._device_state().items()}
+            return packing.pack_skin(sd, "p", width, self.num_nearest_bone, self.use_Dg, self.use_Lf)
+
+        pk = self._packed_for(("skin", width), build)
+        return engine.run_skin(ws, tag, pk, pos, skin, motion, gt, gg, binfo)
+
+    def forward(self, data, motion):
+        self._guard(data.pos, motion, data.tpl_edge_index, data.geo_edge_index, data.batch)
+        pos = _lib.require_cuda(data.pos, "data.pos")
+        motion = _lib.require_cuda(motion, "motion")
+        n = pos.shape[0]
+        gt = self._graphs.get(data.tpl_edge_index, n)
+        gg = self._graphs.get(data.geo_edge_index, n)
+        binfo = self._batches.get(data.batch, data)
+        return self.run(self._ws, "skin", data, pos, motion, gt, gg, binfo).clone()
+
+
+class SkinMotion(_MotionNet):
+    """`SkinMotion(nearest_bone, use_Dg, use_Lf, num_keyframes, use_motion, motion_dim, aggr='max')` —
+    models/rignet.py:185-205 — returns (motion_all [N,T,motion_dim], motion_aggr [N,motion_dim], skin logits)."""
+
+    def __init__(self, nearest_bone, use_Dg, use_Lf, num_keyframes, use_motion, motion_dim, aggr="max"):
+        super().__init__()
+        self.num_keyframes = num_keyframes
+        self.motion_dim = motion_dim
+        self.motionNet = GCNRig(chn_feature=3, chn_output=motion_dim, aggr=aggr)
+        self.aggragator = TemporalAttn(input_size=motion_dim, num_heads=2, hidden_size=64, dim_feedforward=512,
+                                       output_size=motion_dim)
+        self.skinNet = SkinNet_inner(nearest_bone, use_Dg, use_Lf, motion_dim, use_motion, aggr)
+
+    def forward(self, data, input_flow):
+        pos, flow, n, gt, gg, binfo = self._inputs(data, input_flow)
+        motion_all = self._encode(pos, flow, n, gt, gg, binfo, self.motion_dim)
+        motion_aggr = self._aggregate(motion_all, "attn", self.motion_dim)
+        pred = self.skinNet.run(self._ws, "skin", data, pos, motion_aggr, gt, gg, binfo)
+        return motion_all, motion_aggr, pred.clone()
+
+
+def jointnet_motion(**kwargs):
+    """factory, kwargs as models/rignet.py:208-210 (extra keys such as motion_dim are ignored)."""
+    return JointNetMotion(num_keyframes=kwargs["num_keyframes"], chn_output=kwargs["chn_output"],
+                          aggr_method=kwargs["aggr_method"])
+
+
+def masknet_motion(**kwargs):
+    """factory, kwargs as models/rignet.py:212-214."""
+    return MaskNetMotion(num_keyframes=kwargs["num_keyframes"], chn_output=kwargs["chn_output"],
+                         aggr_method=kwargs["aggr_method"])
+
+
+def skinnet_motion(**kwargs):
+    """factory, kwargs as models/rignet.py:216-220."""
+    return SkinMotion(nearest_bone=kwargs["nearest_bone"], use_Dg=kwargs["use_Dg"], use_Lf=kwargs["use_Lf"],
+                      num_keyframes=kwargs["num_keyframes"], use_motion=kwargs["use_motion"],
+                      motion_dim=kwargs["motion_dim"])
