@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: meshes/sec of the `jointnet_motion` forward on synthetic 4096-vertex
+meshes (BASELINE.json `metric`, configs[1]: batch = 4 meshes per GPU), fp32, eval mode.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]           # reference CPU path (oracle port)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...               # one rank per GPU, weak scaling
+
+A "step" is one forward over one batch of 4 meshes per GPU (graph preparation included: the reference
+feeds a new Batch every iteration, training/train_rig.py:206-223).  Prints ONE JSON line on rank 0.
+
+  value   meshes/s, inputs resident in HBM, each step timed with CUDA events on the launch stream,
+          an L2 flush (256 MiB write) between steps, max over ranks
+  e2e     the same metric through the public nn.Module call with HOST (pinned) inputs: H2D copy of the
+          batch + forward + D2H copy of the three outputs inside the timed region
+  roofline / cpu_baseline: see DESIGN.md "Measurement"
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+ARCH = "jointnet_motion"
+MESHES_PER_GPU = 4
+N_VTX = 4096
+METRIC = "meshes/sec jointnet_motion fwd, 4K-vtx synthetic"
+UNIT = "meshes/s"
+# canonical algorithmic FLOPs of the reference formulation, SURVEY.md §8(d): 105.25 MFLOP per vertex
+ALG_FLOP_PER_VERTEX = 105.25e6
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                    bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(steps: int, warmup: int, n_meshes: int = 1):
+    """Reference CPU path (oracle port = op-for-op restatement of models/rignet.py pinned to the unmodified
+    reference) on all host threads.  One step = forward of `n_meshes` 4096-vertex meshes."""
+    from morig_b200 import synth
+    from oracle import rignet_port
+    import morig_b200
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kw = synth.ARCH_KWARGS[ARCH]
+    model = getattr(morig_b200, ARCH)(**kw).eval()
+    sd = synth.seeded_state_dict(model, 1)
+    data = synth.make_batch(n_meshes, N_VTX, seed=0)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            rignet_port.jointnet_motion_forward(sd, data, data.pred_flow, num_keyframes=kw["num_keyframes"],
+                                                aggr_method=kw["aggr_method"])
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    total = sum(times)
+    return dict(value=n_meshes * len(times) / total, unit=UNIT, cores=cores, kind="port",
+                sample=f"{len(times)} timed forwards of {n_meshes} x {N_VTX}-vertex mesh after {warmup} warm-up, "
+                       f"torch {torch.__version__} CPU fp32, {cores} threads",
+                ms_per_step=1e3 * total / len(times))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, args.warmup, n_meshes=1)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{ARCH} forward, batch={MESHES_PER_GPU} x {N_VTX}-vertex synthetic meshes per GPU "
+                                   "(BASELINE.json configs[1]); reference arm step = bounded sample of 1 mesh",
+                       "arch": ARCH, "n_vtx": N_VTX, "meshes_per_step": 1},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import morig_b200
+    from morig_b200 import _lib, engine, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.load()                                       # fail loudly if the extension is missing
+    peaks = load_peaks()
+
+    kw = synth.ARCH_KWARGS[ARCH]
+    model = getattr(morig_b200, ARCH)(**kw).eval()
+    model.load_state_dict(synth.seeded_state_dict(model, 1))
+    model = model.to(dev)
+    host = synth.make_batch(MESHES_PER_GPU, N_VTX, seed=rank * MESHES_PER_GPU).pin_memory()
+    resident = host.to(dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def fresh_views(b):
+        # new tensor objects every step, like `data.to(device)` per iteration: graph prep is part of the step
+        return synth.Batch(**{k: (v.view_as(v) if torch.is_tensor(v) else v) for k, v in b.__dict__.items()})
+
+    counter = engine.LaunchCounter()
+    prof = engine.KernelTimer()
+
+    def step_resident():
+        d = fresh_views(resident)
+        return model(d, d.pred_flow)
+
+    def step_e2e():
+        d = host.to(dev, non_blocking=True)
+        out = model(d, d.pred_flow)
+        return [o.to("cpu", non_blocking=True) for o in out]
+
+    def timed(fn, steps, warmup, profile=False):
+        with torch.no_grad():
+            for _ in range(warmup):
+                fn()
+            barrier()
+            evs = []
+            for _ in range(steps):
+                flush_buf.fill_(1)                    # L2 flush between timed iterations
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(stream)
+                fn()
+                e.record(stream)
+                evs.append((s, e))
+            barrier()
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    engine.set_hooks(counter, prof)
+    counter.reset(); prof.reset()
+    ms_total = timed(step_resident, args.steps, args.warmup)
+    launches = counter.count // (args.steps + args.warmup) * args.steps
+    kstats = prof.summary()
+    engine.set_hooks(None, None)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+
+    # cached-graph variant (same Batch object re-submitted): informational
+    def step_cached():
+        return model(resident, resident.pred_flow)
+    ms_cached = timed(step_cached, args.steps, args.warmup)
+
+    if rank == 0:
+        meshes = MESHES_PER_GPU * world * args.steps
+        value = meshes / (ms_total / 1e3)
+        h2d = sum(v.numel() * v.element_size() for v in host.__dict__.values() if torch.is_tensor(v))
+        with torch.no_grad():
+            outs = step_resident()
+        d2h = sum(o.numel() * o.element_size() for o in outs)
+        alg_flops_step = ALG_FLOP_PER_VERTEX * N_VTX * MESHES_PER_GPU
+        roof = engine.roofline_report(kstats, peaks, ms_total / args.steps, alg_flops_step)
+        cpu = cpu_reference_run(steps=3, warmup=1, n_meshes=1) if world == 1 else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{ARCH} forward, batch={MESHES_PER_GPU} x {N_VTX}-vertex synthetic meshes "
+                                       "per GPU (BASELINE.json configs[1]), graph preparation included every step",
+                           "arch": ARCH, "n_vtx": N_VTX, "meshes_per_gpu": MESHES_PER_GPU,
+                           "l2": "256 MiB flush write between timed steps; per-step workspace ~1 GB >> L2",
+                           "parallelism": f"dp{world}: whole meshes per rank, no forward collective"},
+                "clocks": clocks,
+                "e2e": {"value": meshes / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches,
+                "cached_graph": {"value": meshes / (ms_cached / 1e3), "unit": UNIT,
+                                 "note": "same Batch object re-submitted: CSR cache hit, informational"},
+                "roofline": roof,
+                "model_tflops_algorithmic": alg_flops_step * world / (ms_total / args.steps / 1e3) / 1e12,
+                "kernels": kstats}
+        if cpu is not None:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -71,8 +71,10 @@ def graph_prep(edge_index: torch.Tensor, n: int) -> Graph:
     tgt = torch.empty(e + n, dtype=torch.int32, device=dev)
     ws_bytes = lib.morig_graph_prep_workspace(e, n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    tok = _begin(f"graph_prep E={e} N={n}", 5, 0.0, 16.0 * e + 8.0 * (e + n)) if (_counter is not None or _timer is not None) else None
     _lib.check(lib.morig_graph_prep(ei.data_ptr(), e, n, rowptr.data_ptr(), col.data_ptr(), tgt.data_ptr(),
                                     ws.data_ptr(), ws_bytes, _lib.stream_ptr()), "morig_graph_prep")
+    _end(tok)
     return Graph(rowptr=rowptr, col=col, tgt=tgt, n=n, e_max=e + n)
 
 
@@ -117,6 +119,95 @@ class BatchCache:
         return info
 
 
+# ---- instrumentation (bench.py): launch counting and per-kernel CUDA-event timing ------------------------
+
+class LaunchCounter:
+    """counts kernels launched by this package (a graph_prep call launches 5)"""
+
+    def __init__(self):
+        self.count = 0
+
+    def reset(self):
+        self.count = 0
+
+
+class KernelTimer:
+    """CUDA events on the launch stream around every helper call; summarised per kernel label with
+    the algorithmic FLOPs / bytes of one launch (DESIGN.md 'Measurement')."""
+
+    def __init__(self):
+        self.records = []
+
+    def reset(self):
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for label, flops, nbytes, s, e in self.records:
+            a = agg.setdefault(label, dict(launches=0, ms=0.0, flops=flops, bytes=nbytes))
+            a["launches"] += 1
+            a["ms"] += s.elapsed_time(e)
+        out = []
+        for label, a in agg.items():
+            avg = a["ms"] / a["launches"]
+            out.append(dict(kernel=label, launches=a["launches"], total_ms=round(a["ms"], 4), avg_ms=round(avg, 5),
+                            alg_gflop_per_launch=round(a["flops"] / 1e9, 4), alg_mb_per_launch=round(a["bytes"] / 1e6, 4),
+                            tflops=round(a["flops"] / (avg * 1e-3) / 1e12, 3) if avg > 0 else None,
+                            gbs=round(a["bytes"] / (avg * 1e-3) / 1e9, 1) if avg > 0 else None))
+        out.sort(key=lambda r: -r["total_ms"])
+        return out
+
+
+_counter: Optional[LaunchCounter] = None
+_timer: Optional[KernelTimer] = None
+
+
+def set_hooks(counter: Optional[LaunchCounter], timer: Optional[KernelTimer]) -> None:
+    global _counter, _timer
+    _counter, _timer = counter, timer
+
+
+def _begin(label: str, kernels: int, flops: float, nbytes: float):
+    if _counter is not None:
+        _counter.count += kernels
+    if _timer is None:
+        return None
+    s = torch.cuda.Event(enable_timing=True)
+    s.record(torch.cuda.current_stream())
+    return (label, flops, nbytes, s)
+
+
+def _end(tok) -> None:
+    if tok is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream())
+        _timer.records.append(tok + (e,))
+
+
+FP32_FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # nominal CUDA-core peak at max clock (74.4)
+
+
+def roofline_report(kstats, peaks, ms_per_step: float, alg_flops_step: float) -> dict:
+    """`roofline` object of the bench line for the dominant kernel (largest share of the step)."""
+    if not kstats:
+        return {"bound": "tensor", "achieved": None, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": None, "traffic": None}
+    top = kstats[0]
+    per_step_ms = sum(k["total_ms"] for k in kstats)
+    achieved = top["tflops"]
+    peak = peaks["bf16_tflops_sustained"]
+    return {"bound": "tensor", "kernel": top["kernel"], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": (achieved / peak if achieved else None), "traffic": None,
+            "peak_source": peaks["source"] + " bf16 dense, sustained (kernel timed inside a long step)",
+            "avg_launch_ms": top["avg_ms"], "alg_gflop_per_launch": top["alg_gflop_per_launch"],
+            "share_of_kernel_time": round(top["total_ms"] / per_step_ms, 4) if per_step_ms else None,
+            "pipe": "fp32 FFMA (CUDA cores)", "fp32_ffma_nominal_peak": round(FP32_FFMA_PEAK_TFLOPS, 1),
+            "frac_of_fp32_ffma_peak": (round(achieved / FP32_FFMA_PEAK_TFLOPS, 4) if achieved else None),
+            "hbm_gbs_same_kernel": top["gbs"], "hbm_frac_same_kernel": (round(top["gbs"] / peaks["hbm_gbs"], 4)
+                                                                       if top["gbs"] else None)}
+
+
 # ---- thin launch helpers ---------------------------------------------------------------------------
 
 def dense(layer: DenseLayer, A: torch.Tensor, a_off: int, lda: int, M: int, *, K: Optional[int] = None,
@@ -136,7 +227,13 @@ def dense(layer: DenseLayer, A: torch.Tensor, a_off: int, lda: int, M: int, *, K
     d.pool, d.ldpool = _lib.ptr(pool), (pool.shape[1] if pool is not None else 0)
     d.M, d.N, d.K = M, layer.N, (layer.K if K is None else K)
     d.relu = 1 if layer.relu else 0
+    tok = None
+    if _counter is not None or _timer is not None:
+        kk = d.K
+        tok = _begin(f"dense M={M} N={layer.N} K={kk}" + (" +pool" if pool is not None else ""), 1,
+                     2.0 * M * layer.N * kk, 4.0 * (M * kk + kk * layer.N + (M * layer.N if C is not None else 0)))
     _lib.check(lib.morig_dense_fwd(ctypes.byref(d), _lib.stream_ptr()), "morig_dense_fwd")
+    _end(tok)
 
 
 def edgeconv(br: EdgeBranch, pq: torch.Tensor, ldpq: int, p_off: int, q_off: int, g: Graph, n_frames: int,
@@ -150,24 +247,36 @@ def edgeconv(br: EdgeBranch, pq: torch.Tensor, ldpq: int, p_off: int, q_off: int
     d.b1, d.scale, d.shift = br.b1.data_ptr(), br.scale.data_ptr(), br.shift.data_ptr()
     d.out, d.ldo, d.out_off = out.data_ptr(), ldo, out_off
     d.H = br.H
+    tok = None
+    if _counter is not None or _timer is not None:
+        H, e = br.H, g.e_max
+        tok = _begin(f"edgeconv H={H} E={e} N={g.n} frames={n_frames}", 1, 2.0 * e * H * H * n_frames,
+                     n_frames * 4.0 * g.n * 2 * H + 8.0 * e + 4.0 * g.n * H * n_frames * out_repeat + 4.0 * (H * H + 3 * H))
     _lib.check(lib.morig_edgeconv_fwd(ctypes.byref(d), _lib.stream_ptr()), "morig_edgeconv_fwd")
+    _end(tok)
 
 
 def fill(t: torch.Tensor, value: float) -> None:
+    tok = _begin("fill", 1, 0.0, 4.0 * t.numel()) if (_counter is not None or _timer is not None) else None
     _lib.check(_lib.load().morig_fill_f32(t.data_ptr(), t.numel(), value, _lib.stream_ptr()), "morig_fill_f32")
+    _end(tok)
 
 
 def gather_cols(src: torch.Tensor, lds: int, src_off: int, frame_stride: int, cols: Optional[torch.Tensor], c: int,
                 n: int, n_frames: int, dst: torch.Tensor, ldd: int, dst_off: int) -> None:
+    tok = _begin("gather_cols", 1, 0.0, 8.0 * n * n_frames * c) if (_counter is not None or _timer is not None) else None
     _lib.check(_lib.load().morig_gather_cols(src.data_ptr(), lds, src_off, frame_stride, _lib.ptr(cols), c, n,
                                              n_frames, dst.data_ptr(), ldd, dst_off, _lib.stream_ptr()),
                "morig_gather_cols")
+    _end(tok)
 
 
 def row_normalize(x: torch.Tensor, ldx: int, rows: int, c: int, dst2: Optional[torch.Tensor] = None, n: int = 0,
                   n_frames: int = 0) -> None:
+    tok = _begin("row_normalize", 1, 0.0, 8.0 * rows * c) if (_counter is not None or _timer is not None) else None
     _lib.check(_lib.load().morig_row_normalize(x.data_ptr(), ldx, rows, c, _lib.ptr(dst2), n, n_frames,
                                                _lib.stream_ptr()), "morig_row_normalize")
+    _end(tok)
 
 
 # ---- layer sequences -------------------------------------------------------------------------------
@@ -235,10 +344,12 @@ def run_gcn_rig(ws: Workspace, tag: str, pk: GCNRigPack, pos: torch.Tensor, feat
 
 def temporal_attn(pk: AttnPack, x: torch.Tensor, out: torch.Tensor) -> None:
     n, t, c = x.shape
+    tok = _begin("temporal_attn", 1, 0.0, 4.0 * n * (t * c + pk.D)) if (_counter is not None or _timer is not None) else None
     _lib.check(_lib.load().morig_temporal_attn_fwd(x.data_ptr(), n, t, c, pk.heads, pk.D, pk.u.data_ptr(),
                                                    pk.l0.data_ptr(), pk.Mv.data_ptr(), pk.c0.data_ptr(),
                                                    out.data_ptr(), out.shape[1], _lib.stream_ptr()),
                "morig_temporal_attn_fwd")
+    _end(tok)
 
 
 def frame_reduce(x: torch.Tensor, mode: str, out: torch.Tensor) -> None:

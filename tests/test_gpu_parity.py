@@ -1,0 +1,200 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the oracle and the golden
+fixtures produced by the unmodified reference.  Run with `pytest -m gpu` on a B200."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from morig_b200 import _lib, engine, packing, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_library_loaded_is_in_tree():
+    lib = _lib.load()
+    assert lib.morig_version() == 1
+    assert lib.morig_sm_count() > 0
+
+
+# ---- integer work: bit-exact ---------------------------------------------------------------------
+@pytest.mark.parametrize("n,e,seed", [(1, 0, 0), (7, 30, 1), (64, 500, 2), (1000, 9000, 3), (4096, 61440, 4)])
+def test_graph_prep_bit_exact(n, e, seed):
+    from oracle import graph_port
+    rng = np.random.default_rng(seed)
+    ei = rng.integers(0, n, size=(2, e)).astype(np.int64)          # duplicates and self loops included
+    if e:
+        ei[1, : e // 4] = ei[1, 0]                                   # one heavy target
+    g = engine.graph_prep(torch.from_numpy(ei).to(DEV), n)
+    rowptr, col = graph_port.csr_by_target(ei, n)
+    e_real = int(rowptr[-1])
+    assert np.array_equal(g.rowptr.cpu().numpy(), rowptr)
+    assert np.array_equal(g.col.cpu().numpy()[:e_real], col)
+    assert np.array_equal(g.tgt.cpu().numpy()[:e_real], np.repeat(np.arange(n, dtype=np.int32), np.diff(rowptr)))
+
+
+def test_graph_prep_on_dataset_style_input():
+    """edge lists as the dataset delivers them (self loops already appended, datasets/dataset_rig.py:121-122)"""
+    from oracle import graph_port
+    m = synth.make_mesh(1024, 0)
+    for key in ("tpl_edge_index", "geo_edge_index"):
+        ei = m[key]
+        g = engine.graph_prep(torch.from_numpy(ei).to(DEV), 1024)
+        rowptr, col = graph_port.csr_by_target(ei, 1024)
+        assert np.array_equal(g.rowptr.cpu().numpy(), rowptr)
+        assert np.array_equal(g.col.cpu().numpy()[: rowptr[-1]], col)
+        assert int(rowptr[-1]) == ei.shape[1]
+
+
+@pytest.mark.parametrize("n,b", [(256, 1), (1024, 2), (4096, 1)])
+def test_knn_graph_bit_exact(n, b):
+    lib = _lib.load()
+    pos = np.concatenate([synth.torus_vertices(n, np.random.default_rng(s)) for s in range(b)])
+    gptr = torch.arange(0, (b + 1) * n, n, dtype=torch.int32, device=DEV)
+    out = torch.empty(2, 15 * n * b, dtype=torch.int64, device=DEV)
+    p = torch.from_numpy(pos).to(DEV)
+    _lib.check(lib.morig_knn_graph(p.data_ptr(), gptr.data_ptr(), b, n * b, 15, out.data_ptr(), _lib.stream_ptr()), "knn")
+    ref = np.concatenate([synth.knn_edges(pos[s * n:(s + 1) * n], 15) + s * n for s in range(b)], axis=1)
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+# ---- kernels against straightforward torch fp32 references -------------------------------------------
+@pytest.mark.parametrize("M,K,N", [(1, 3, 5), (130, 36, 64), (257, 838, 1024), (1000, 256, 3), (4099, 544, 512)])
+def test_dense_fwd(M, K, N):
+    g = torch.Generator().manual_seed(M + K + N)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b, s, t = torch.randn(N, generator=g), torch.randn(N, generator=g), torch.randn(N, generator=g)
+    layer = packing.DenseLayer(W=packing._pack_wt(W.double()).to(DEV), K=K, N=N, bias=b.to(DEV), scale=s.to(DEV),
+                               shift=t.to(DEV), relu=True)
+    C = torch.empty(M, N, device=DEV)
+    engine.dense(layer, A.to(DEV), 0, K, M, C=C, ldc=N)
+    ref = torch.relu(A.double() @ W.double().t() + b.double()) * s.double() + t.double()
+    assert helpers.max_abs_diff(C, ref) < 2e-5
+
+
+def test_dense_pool_and_rowbias():
+    n, frames, B, K, N = 700, 3, 4, 64, 200
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(n * frames, K, generator=g)
+    W = torch.randn(N, K, generator=g) / 8
+    rb = torch.randn(frames * B, N, generator=g)
+    batch = torch.sort(torch.randint(0, B, (n,), generator=g)).values
+    batch[0], batch[-1] = 0, B - 1
+    binfo = engine.BatchInfo(batch32=batch.to(torch.int32).to(DEV), n_graphs=B)
+    layer = packing.DenseLayer(W=packing._pack_wt(W.double()).to(DEV), K=K, N=N, relu=True)
+    C = torch.empty(n * frames, N, device=DEV)
+    pool = torch.full((frames * B, N), float("-inf"), device=DEV)
+    engine.dense(layer, A.to(DEV), 0, K, n * frames, C=C, ldc=N, pool=pool, rowbias=rb.to(DEV), binfo=binfo, n_vtx=n)
+    grp = (torch.arange(n * frames) // n) * B + batch[torch.arange(n * frames) % n]
+    ref = torch.relu(A.double() @ W.double().t() + rb.double()[grp])
+    assert helpers.max_abs_diff(C, ref) < 2e-5
+    ref_pool = torch.full((frames * B, N), float("-inf"), dtype=torch.float64).scatter_reduce(
+        0, grp[:, None].expand_as(ref), ref, "amax")
+    got = pool.cpu().double()
+    present = torch.zeros(frames * B, dtype=torch.bool); present[grp] = True
+    assert float((got[present] - ref_pool[present]).abs().max()) < 2e-5
+    # pooled value must be bit-identical to the max of the stored rows (ordered atomics are exact)
+    stored_max = torch.full((frames * B, N), float("-inf")).scatter_reduce(0, grp[:, None].expand(-1, N), C.cpu(), "amax")
+    assert torch.equal(pool.cpu()[present], stored_max[present])
+
+
+@pytest.mark.parametrize("C_x,H,C_p,Dp", [(3, 32, 3, 16), (64, 128, 3, 16), (256, 256, 3, 16), (32, 128, 33, 64)])
+def test_edge_conv_motion_module(C_x, H, C_p, Dp):
+    """one EdgeConvMotion (models/basic_modules.py:179-199) on a ragged graph with a heavy target, duplicate
+    edges, pre-existing self loops and isolated vertices"""
+    import morig_b200
+    from oracle import rignet_port
+    n = 777
+    g = torch.Generator().manual_seed(C_x + H)
+    ei = torch.randint(0, n - 20, (2, 6000), generator=g)            # last 20 vertices isolated
+    ei[1, :700] = 5
+    mod = morig_b200.EdgeConvMotion(morig_b200.MLP([2 * C_x, H, H]), morig_b200.MLP([2 * C_p, Dp, Dp])).eval()
+    mod.load_state_dict(synth.seeded_state_dict(mod, 7))
+    pos, x = torch.randn(n, C_p, generator=g), torch.randn(n, C_x, generator=g)
+    ref = rignet_port.edge_conv_motion({"m." + k: v for k, v in mod.state_dict().items()}, "m", pos, x, ei)
+    out = mod.to(DEV)(pos.to(DEV), x.to(DEV), ei.to(DEV))
+    assert helpers.max_abs_diff(out, ref) < 2e-5
+    # edge order must not matter (max is exact): permuted edge list -> bit-identical output
+    perm = torch.randperm(ei.shape[1], generator=g)
+    out2 = mod(pos.to(DEV), x.to(DEV), ei[:, perm].contiguous().to(DEV))
+    assert torch.equal(out, out2)
+
+
+def test_temporal_attn_module():
+    import morig_b200
+    from oracle import rignet_port
+    mod = morig_b200.TemporalAttn(32, 2, 64, 512, 64).eval()
+    mod.load_state_dict(synth.seeded_state_dict(mod, 3))
+    x = torch.nn.functional.normalize(torch.randn(1000, 5, 32, generator=torch.Generator().manual_seed(1)), dim=2)
+    ref = rignet_port.temporal_attn({"a." + k: v for k, v in mod.state_dict().items()}, "a", x)
+    out = mod.to(DEV)(x.to(DEV))
+    assert helpers.max_abs_diff(out, ref) < 2e-5
+
+
+# ---- whole networks -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", helpers.golden_names())
+def test_models_match_golden_fixtures(name):
+    """outputs of the unmodified reference (tests/golden, made by oracle/gen_golden.py)"""
+    arch, kw, wseed, data, expect = helpers.load_golden(name)
+    model = helpers.build_model(arch, kw, wseed, DEV)
+    with torch.no_grad():
+        out = model(data.to(DEV), data.pred_flow.to(DEV))
+    for o, e, k in zip(out, expect, helpers.OUT_KEYS):
+        assert o.shape == e.shape, k
+        assert helpers.max_abs_diff(o, e) < helpers.TOL, k
+
+
+@pytest.mark.parametrize("arch,b,n", [("jointnet_motion", 2, 1024), ("masknet_motion", 1, 2048), ("skinnet_motion", 2, 1024)])
+def test_models_match_oracle(arch, b, n):
+    kw = synth.ARCH_KWARGS[arch]
+    data = synth.make_batch(b, n, seed=100, with_skin=(arch == "skinnet_motion"))
+    model = helpers.build_model(arch, kw, 11, DEV)
+    expect = helpers.oracle_forward(arch, kw, model, data, data.pred_flow)
+    with torch.no_grad():
+        out = model(data.to(DEV), data.pred_flow.to(DEV))
+    for o, e, k in zip(out, expect, helpers.OUT_KEYS):
+        assert helpers.max_abs_diff(o, e) < helpers.TOL, k
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[1] size (4 x 4096 vertices): properties that need no oracle —
+    run-to-run bit equality, data-parallel shard concatenation == single batch, edge-order invariance."""
+    kw = synth.ARCH_KWARGS["jointnet_motion"]
+    model = helpers.build_model("jointnet_motion", kw, 5, DEV)
+    data = synth.make_batch(4, 4096, seed=0)
+    dd = data.to(DEV)
+    with torch.no_grad():
+        a = [t.clone() for t in model(dd, dd.pred_flow)]
+        b = model(dd, dd.pred_flow)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+        assert all(torch.isfinite(t).all() for t in a)
+        # unit rows
+        assert float((a[0].norm(dim=2) - 1).abs().max()) < 1e-5
+        # shards of whole meshes give the same rows as the full batch (BatchNorm is eval-mode, pooling per graph)
+        parts = []
+        for s in range(2):
+            sh = synth.make_batch(2, 4096, seed=2 * s).to(DEV)
+            parts.append([t.clone() for t in model(sh, sh.pred_flow)])
+        for k in range(3):
+            cat = torch.cat([parts[0][k], parts[1][k]], dim=0)
+            assert helpers.max_abs_diff(cat, a[k]) < 1e-5
+        # shuffled edge order
+        g = torch.Generator().manual_seed(0)
+        d2 = synth.Batch(**dd.__dict__)
+        d2.geo_edge_index = dd.geo_edge_index[:, torch.randperm(dd.geo_edge_index.shape[1], generator=g).to(DEV)].contiguous()
+        c = model(d2, d2.pred_flow)
+        for x, y in zip(a, c):
+            assert torch.equal(x, y)
+
+
+def test_rejects_cpu_tensors_and_train_mode():
+    kw = synth.ARCH_KWARGS["jointnet_motion"]
+    model = helpers.build_model("jointnet_motion", kw, 5, DEV)
+    data = synth.make_batch(1, 256, seed=0)
+    with pytest.raises(RuntimeError):
+        model(data, data.pred_flow)                      # CPU tensors: no fallback
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model(data.to(DEV), data.pred_flow.to(DEV))
