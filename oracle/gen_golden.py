@@ -37,6 +37,12 @@ def main() -> None:
     models = pyg_shim.import_reference_models()
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    # state_dict key names + shapes of the unmodified reference (checkpoint compatibility contract)
+    import json
+    keys = {a: {k: list(v.shape) for k, v in models.__dict__[a](**kw).state_dict().items()}
+            for a, kw in synth.ARCH_KWARGS.items()}
+    with open(os.path.join(out_dir, "state_dict_keys.json"), "w") as f:
+        json.dump(keys, f)
     for name, arch, b, n, dseed, wseed in CASES:
         kw = dict(synth.ARCH_KWARGS[arch])
         if "_mean_" in name:

@@ -1,0 +1,156 @@
+"""Host-side logic on CPU (no GPU in the build container): weight folding / packing, buffer layouts and
+launch sequences are exercised through the CPU emulation of the C-ABI in tests/emu.py and compared with
+the golden outputs of the unmodified reference; plus the C-ABI library's exports and the module protocol
+(state_dict, cache invalidation, loud failures)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import helpers
+from morig_b200 import _lib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", helpers.golden_names())
+def test_packing_and_launch_sequence_reproduce_golden(emulated, name):
+    arch, kw, wseed, data, expect = helpers.load_golden(name)
+    model = helpers.build_model(arch, kw, wseed)
+    with torch.no_grad():
+        out = model(data, data.pred_flow)
+    for o, e, k in zip(out, expect, helpers.OUT_KEYS):
+        assert o.shape == e.shape
+        assert helpers.max_abs_diff(o, e) < 5e-6, k
+
+
+def test_submodules_keep_reference_signatures(emulated):
+    """EdgeConvMotion / GCUMotion / GCNRig / TemporalAttn called the way the reference calls them
+    (models/basic_modules.py:185,214; models/rignet.py:36,58)"""
+    from oracle import rignet_port
+    import morig_b200
+    data = synth.make_batch(2, 100, seed=5)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(200, 64, generator=g)
+    gcu = morig_b200.GCUMotion(64, 256).eval()
+    gcu.load_state_dict(synth.seeded_state_dict(gcu, 1))
+    sd = {"g." + k: v for k, v in gcu.state_dict().items()}
+    want = rignet_port.gcu_motion(sd, "g", data.pos, x, data.tpl_edge_index, data.geo_edge_index)
+    got = gcu(data.pos, x, data.tpl_edge_index, data.geo_edge_index)
+    assert helpers.max_abs_diff(got, want) < 5e-6
+    ec = gcu.edge_conv_geo
+    want = rignet_port.edge_conv_motion(sd, "g.edge_conv_geo", data.pos, x, data.geo_edge_index)
+    assert helpers.max_abs_diff(ec(data.pos, x, data.geo_edge_index), want) < 5e-6
+    rig = morig_b200.GCNRig(64, 3).eval()
+    rig.load_state_dict(synth.seeded_state_dict(rig, 2))
+    sd = {"r." + k: v for k, v in rig.state_dict().items()}
+    want = rignet_port.gcn_rig(sd, "r", data.pos, x, data.tpl_edge_index, data.geo_edge_index, data.batch)
+    got = rig(data.pos, x, data.tpl_edge_index, data.geo_edge_index, data.batch)
+    assert helpers.max_abs_diff(got, want) < 5e-6
+    att = morig_b200.TemporalAttn(32, 2, 64, 512, 64).eval()
+    att.load_state_dict(synth.seeded_state_dict(att, 3))
+    xs = torch.randn(50, 5, 32, generator=g)
+    want = rignet_port.temporal_attn({"a." + k: v for k, v in att.state_dict().items()}, "a", xs)
+    assert helpers.max_abs_diff(att(xs), want) < 5e-6
+
+
+def test_negative_bn_scale_is_not_commuted_through_max(emulated):
+    """BN after ReLU with gamma < 0: max(s*h+t) != s*max(h)+t.  All second-layer BN scales negative."""
+    from oracle import rignet_port
+    import morig_b200
+    data = synth.make_batch(1, 64, seed=2)
+    ec = morig_b200.EdgeConvMotion(morig_b200.MLP([6, 32, 32]), morig_b200.MLP([6, 16, 16])).eval()
+    sd = synth.seeded_state_dict(ec, 4)
+    for k in list(sd):
+        if k.endswith(".1.2.weight"):
+            sd[k] = -sd[k].abs()
+    ec.load_state_dict(sd)
+    x = torch.randn(64, 3, generator=torch.Generator().manual_seed(1))
+    want = rignet_port.edge_conv_motion({"e." + k: v for k, v in sd.items()}, "e", data.pos, x, data.geo_edge_index)
+    assert helpers.max_abs_diff(ec(data.pos, x, data.geo_edge_index), want) < 5e-6
+
+
+def test_packed_weights_follow_load_state_dict(emulated):
+    arch, kw, wseed, data, expect = helpers.load_golden("jointnet_b2_n256")
+    model = helpers.build_model(arch, kw, wseed + 100)            # wrong weights first
+    with torch.no_grad():
+        wrong = model(data, data.pred_flow)
+        assert helpers.max_abs_diff(wrong[2], expect[2]) > 1e-3
+        model.load_state_dict(synth.seeded_state_dict(model, wseed))
+        right = model(data, data.pred_flow)
+    assert helpers.max_abs_diff(right[2], expect[2]) < 5e-6
+
+
+def test_graph_cache_never_aliases_a_different_tensor(emulated):
+    from morig_b200 import engine
+    cache = engine.GraphCache()
+    a = torch.tensor([[0, 1, 2], [1, 2, 0]])
+    g1 = cache.get(a, 3)
+    assert cache.get(a, 3) is g1                                  # same object, same version: hit
+    b = a.clone()
+    assert cache.get(b, 3) is not g1                              # equal content, different tensor: miss
+    a[0, 0] = 2                                                   # in-place edit bumps the version: miss
+    assert cache.get(a, 3) is not g1
+
+
+def test_train_mode_and_cpu_tensors_fail_loudly():
+    import morig_b200
+    kw = synth.ARCH_KWARGS["jointnet_motion"]
+    model = morig_b200.jointnet_motion(**kw)
+    data = synth.make_batch(1, 64, seed=0)
+    with pytest.raises(NotImplementedError):
+        model.train()(data, data.pred_flow)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        model.eval()(data, data.pred_flow)                        # CPU tensors and no fallback
+
+
+def test_factories_ignore_extra_kwargs_like_the_reference():
+    import morig_b200
+    m = morig_b200.jointnet_motion(num_keyframes=5, chn_output=3, aggr_method="attn", motion_dim=32, foo=1)
+    assert isinstance(m, morig_b200.JointNetMotion)
+    with pytest.raises(KeyError):
+        morig_b200.skinnet_motion(num_keyframes=5)
+
+
+def test_install_replaces_registry_entries():
+    import types
+    import morig_b200
+    fake = types.ModuleType("models")
+    fake.rignet = types.ModuleType("models.rignet")
+    morig_b200.install(fake)
+    assert fake.__dict__["jointnet_motion"] is morig_b200.jointnet_motion
+    assert fake.rignet.SkinMotion is morig_b200.SkinMotion
+
+
+def _declared_symbols():
+    names = []
+    for fn in os.listdir(os.path.join(ROOT, "include")):
+        if fn.endswith(".h"):
+            with open(os.path.join(ROOT, "include", fn)) as f:
+                names += re.findall(r"MORIG_API[^;(]*?\b(morig_\w+)\s*\(", f.read())
+    return sorted(set(names))
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    from morig_b200 import build
+    build.build()                                                 # nvcc cross-compiles without a GPU
+    declared = _declared_symbols()
+    assert len(declared) >= 12
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(_lib.EXPORTS) == declared                      # the ctypes table covers the whole header
+    assert _lib.load().morig_version() == 1
+
+
+def test_c_abi_argument_validation_without_gpu():
+    """entry points must reject bad descriptors with a code + message instead of launching"""
+    lib = _lib.load()
+    d = _lib.DenseDesc()
+    assert lib.morig_dense_fwd(ctypes.byref(d), None) == 1001
+    assert b"null operand" in lib.morig_last_error()
+    e = _lib.EdgeDesc()
+    assert lib.morig_edgeconv_fwd(ctypes.byref(e), None) == 1001
+    assert lib.morig_graph_prep(None, 10, 0, None, None, None, None, 0, None) == 1001

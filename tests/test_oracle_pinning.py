@@ -1,0 +1,139 @@
+"""Pins the CPU oracle (oracle/rignet_port.py):
+  * against the golden fixtures written by the reference's own unmodified models/rignet.py;
+  * live against that unmodified code when /root/reference is present (build container only);
+  * the PyG / torch_scatter stand-ins against an independent python loop on tiny ragged graphs.
+The reference repo has no tests or golden vectors of its own for this path."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from morig_b200 import synth
+from oracle import graph_port, pyg_shim, rignet_port
+
+HAVE_REF = os.path.isdir(os.path.join(pyg_shim.REFERENCE_ROOT, "models"))
+
+
+@pytest.mark.parametrize("name", helpers.golden_names())
+def test_port_reproduces_golden(name):
+    arch, kw, wseed, data, expect = helpers.load_golden(name)
+    model = helpers.build_model(arch, kw, wseed)           # parameter container only (never executed)
+    out = helpers.oracle_forward(arch, kw, model, data, data.pred_flow)
+    for o, e, k in zip(out, expect, helpers.OUT_KEYS):
+        assert o.shape == e.shape
+        # same code path, possibly different host BLAS kernels: allow a few ulp
+        assert helpers.max_abs_diff(o, e) < 2e-6, k
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("arch", ["jointnet_motion", "masknet_motion", "skinnet_motion"])
+def test_port_is_bit_identical_to_unmodified_reference(arch):
+    models = pyg_shim.import_reference_models()
+    kw = synth.ARCH_KWARGS[arch]
+    ref = models.__dict__[arch](**kw).eval()
+    ref.load_state_dict(synth.seeded_state_dict(ref, 9))
+    data = synth.make_batch(2, 144, seed=77, with_skin=(arch == "skinnet_motion"))
+    with torch.no_grad():
+        expect = ref(data, data.pred_flow)
+    out = helpers.oracle_forward(arch, kw, ref, data, data.pred_flow)
+    for o, e in zip(out, expect):
+        assert torch.equal(o, e)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference only exists in the build container")
+def test_state_dict_keys_match_reference():
+    import morig_b200
+    models = pyg_shim.import_reference_models()
+    for arch, kw in synth.ARCH_KWARGS.items():
+        ref = models.__dict__[arch](**kw)
+        ours = getattr(morig_b200, arch)(**kw)
+        a = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+        b = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+        assert a == b, arch
+
+
+def test_state_dict_keys_match_recorded_reference_keys():
+    """key list recorded from the unmodified reference (tests/golden/state_dict_keys.json)"""
+    import json
+    import morig_b200
+    with open(os.path.join(helpers.GOLDEN_DIR, "state_dict_keys.json")) as f:
+        rec = json.load(f)
+    for arch, kw in synth.ARCH_KWARGS.items():
+        ours = {k: list(v.shape) for k, v in getattr(morig_b200, arch)(**kw).state_dict().items()}
+        assert ours == rec[arch], arch
+
+
+def test_shim_max_aggregation_against_python_loop():
+    """scatter-max / propagate stand-ins vs an O(E) loop: isolated vertices, duplicate edges,
+    pre-existing self loops, one heavy target"""
+    rng = np.random.default_rng(0)
+    n = 23
+    ei = rng.integers(0, n - 3, size=(2, 90)).astype(np.int64)      # vertices n-3.. isolated
+    ei[:, :5] = np.stack([np.arange(5), np.arange(5)])              # explicit self loops
+    ei[:, 5:10] = ei[:, 10:15]                                      # duplicates
+    ei[1, 20:50] = 4                                                # heavy target
+    pos = rng.standard_normal((n, 3)).astype(np.float32)
+    x = rng.standard_normal((n, 2)).astype(np.float32)
+
+    def msg(pi, pj, xi, xj):
+        return np.concatenate([xi + 2 * (xj - xi), pi * (pj - pi)]).astype(np.float32)
+
+    want = graph_port.brute_force_edgeconv_max(msg, pos, x, ei, n)
+
+    class Conv(pyg_shim.MessagePassing):
+        def __init__(self):
+            super().__init__(aggr="max")
+
+        def message(self, pos_i, pos_j, x_i, x_j):
+            return torch.cat([x_i + 2 * (x_j - x_i), pos_i * (pos_j - pos_i)], dim=1)
+
+    e, _ = pyg_shim.remove_self_loops(torch.from_numpy(ei))
+    e, _ = pyg_shim.add_self_loops(e, num_nodes=n)
+    got = Conv().propagate(e, pos=torch.from_numpy(pos), x=torch.from_numpy(x)).numpy()
+    assert np.array_equal(got, want)
+    # the port's own segment max agrees too
+    m = torch.from_numpy(np.stack([msg(pos[i], pos[j], x[i], x[j]) for j, i in e.t().numpy()]))
+    assert np.array_equal(rignet_port._segment_max(m, e[1], n).numpy(), want)
+
+
+def test_scatter_max_semantics():
+    src = torch.tensor([[1.0, -5.0], [3.0, -5.0], [3.0, -7.0], [0.5, 2.0]])
+    idx = torch.tensor([0, 0, 0, 2])
+    out, arg = pyg_shim.scatter_max(src, idx, dim=0, dim_size=4)
+    assert out.tolist() == [[3.0, -5.0], [0.0, 0.0], [0.5, 2.0], [0.0, 0.0]]      # empty segment -> 0
+    assert arg.tolist() == [[1, 0], [4, 4], [3, 3], [4, 4]]                        # first max wins, empty -> len(src)
+
+
+def test_csr_port_properties():
+    rng = np.random.default_rng(3)
+    n = 50
+    ei = rng.integers(0, n, size=(2, 400)).astype(np.int64)
+    rowptr, col = graph_port.csr_by_target(ei, n)
+    norm = graph_port.normalized_edges(ei, n)
+    assert rowptr[0] == 0 and rowptr[-1] == norm.shape[1] == col.shape[0]
+    for i in range(n):
+        seg = col[rowptr[i]:rowptr[i + 1]]
+        assert seg[-1] == i                                         # self loop last
+        assert list(seg[:-1]) == [int(j) for j, t in ei.T if t == i and j != i]   # input order kept
+    assert np.array_equal(graph_port.normalized_edges(norm, n), norm)            # idempotent
+
+
+def test_skin_column_selection_matches_reference_slicing():
+    """models/rignet.py:159-171 restated with index lists"""
+    from morig_b200 import packing
+    x = torch.arange(160.0).repeat(2, 1)
+    for dg, lf in [(False, False), (True, False), (False, True), (True, True)]:
+        s = x
+        if dg and lf:
+            s = s[:, 0:8 * 5]
+        elif dg and not lf:
+            s = s[:, np.arange(s.shape[1]) % 8 != 7][:, 0:7 * 5]
+        elif lf and not dg:
+            s = s[:, np.arange(s.shape[1]) % 8 != 6][:, 0:7 * 5]
+        else:
+            s = s[:, np.arange(s.shape[1]) % 8 != 7]
+            s = s[:, np.arange(s.shape[1]) % 7 != 6][:, 0:6 * 5]
+        assert s[0].long().tolist() == packing.skin_columns(160, 5, dg, lf)
+        assert s[0].long().tolist() == rignet_port.skin_columns(160, 5, dg, lf).tolist()
