@@ -93,6 +93,11 @@ typedef struct morig_dense_desc {
     float         *pool;     int32_t ldpool;  /* [G, N] or NULL                                */
     int32_t        M, N, K;
     int32_t        relu;
+    /* optional tensor-core operand: W pre-split into tf32 hi|lo halves and pre-swizzled into the shared-
+     * memory image of each (n-tile of tc_bn rows, k-chunk of 32) -- see morig_b200/packing.py:pack_tc_blob.
+     * When non-NULL (and A is 16-byte aligned with lda % 4 == 0, K % 4 == 0) the layer runs on the tcgen05
+     * 3xTF32 engine, otherwise on the fp32 CUDA-core engine using W. */
+    const float   *Wtc;      int32_t tc_bn;   /* tc_bn in {64, 128, 256}                        */
 } morig_dense_desc;
 
 MORIG_API int morig_dense_fwd(const morig_dense_desc *d, void *stream);
@@ -125,6 +130,7 @@ typedef struct morig_edge_desc {
     const float   *b1, *scale, *shift;        /* [H]                                 */
     float         *out;    int32_t ldo, out_off;
     int32_t        H;
+    const float   *W1tc;                      /* optional tcgen05 image of W1 (n-tile = H <= 256) */
 } morig_edge_desc;
 
 MORIG_API int morig_edgeconv_fwd(const morig_edge_desc *d, void *stream);

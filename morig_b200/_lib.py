@@ -30,6 +30,7 @@ class DenseDesc(C.Structure):
         ("pool", c_f32p), ("ldpool", C.c_int32),
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
         ("relu", C.c_int32),
+        ("Wtc", c_f32p), ("tc_bn", C.c_int32),
     ]
 
 
@@ -43,6 +44,7 @@ class EdgeDesc(C.Structure):
         ("b1", c_f32p), ("scale", c_f32p), ("shift", c_f32p),
         ("out", c_f32p), ("ldo", C.c_int32), ("out_off", C.c_int32),
         ("H", C.c_int32),
+        ("W1tc", c_f32p),
     ]
 
 

@@ -1,6 +1,7 @@
 // Host launchers for the FP32 tile engine (vertex dense layers, fused EdgeConv branch) and the
 // narrow-channel EdgeConv branch kernel (H <= 32: warp per target vertex, lanes = channels).
-#include "gemm_simt.cuh"
+#include <stdlib.h>
+#include "gemm_tc.cuh"
 
 namespace morig {
 
@@ -64,6 +65,36 @@ static int launch_gemm(const GemmP &p, dim3 grid, cudaStream_t stream, const cha
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+template <int BN, int AMODE, int EPI>
+static int launch_tc(const GemmP &p, const float *blob, int frames, cudaStream_t stream, const char *name) {
+    auto kern = tc::tc_gemm_kernel<BN, AMODE, EPI>;
+    constexpr int smem = tc::Cfg<BN>::SMEM_BYTES;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    MORIG_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        MORIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured_dev = dev;
+    }
+    tc::TcP tp;
+    tp.g = p;
+    tp.Bblob = blob;
+    tp.nK = ceil_div(p.K, tc::KC);
+    dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, tc::BM), frames);
+    kern<<<grid, tc::THREADS, smem, stream>>>(tp);
+    MORIG_LAUNCH_CHECK(name);
+    return 0;
+}
+
+static bool tc_disabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MORIG_NO_TC");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 }  // namespace morig
 
 using namespace morig;
@@ -88,6 +119,16 @@ extern "C" MORIG_API int morig_dense_fwd(const morig_dense_desc *d, void *stream
     p.c_vec = (d->C && d->ldc % 4 == 0 && aligned16(d->C)) ? 1 : 0;
     p.pool = d->pool; p.ldpool = d->ldpool;
     p.M = d->M; p.N = d->N; p.K = d->K; p.relu = d->relu;
+    if (d->Wtc && p.a_vec && !tc_disabled()) {
+        MORIG_CHECK_ARG(aligned16(d->Wtc), "dense_fwd: Wtc must be 16B aligned");
+        MORIG_CHECK_ARG(ceil_div(d->M, 128) <= 65535, "dense_fwd: M=%d too large for one launch", d->M);
+        switch (d->tc_bn) {
+            case 64:  return launch_tc<64, AMODE_PLAIN, EPI_STORE>(p, d->Wtc, 1, stream, "tc_dense<64>");
+            case 128: return launch_tc<128, AMODE_PLAIN, EPI_STORE>(p, d->Wtc, 1, stream, "tc_dense<128>");
+            case 256: return launch_tc<256, AMODE_PLAIN, EPI_STORE>(p, d->Wtc, 1, stream, "tc_dense<256>");
+            default:  MORIG_CHECK_ARG(false, "dense_fwd: tc_bn=%d unsupported (64,128,256)", d->tc_bn);
+        }
+    }
     if (d->N <= 64) {
         dim3 grid(ceil_div(d->M, 128), ceil_div(d->N, 64), 1);
         return launch_gemm<128, 64, AMODE_PLAIN, EPI_STORE>(p, grid, stream, "dense<128,64>");
@@ -123,6 +164,13 @@ extern "C" MORIG_API int morig_edgeconv_fwd(const morig_edge_desc *d, void *stre
     p.bias = d->b1; p.scale = d->scale; p.shift = d->shift;
     p.C = d->out + d->out_off; p.ldc = d->ldo;
     p.M = d->E_max; p.N = H; p.K = H; p.relu = 1;
+    if (d->W1tc && !tc_disabled()) {
+        MORIG_CHECK_ARG(aligned16(d->W1tc), "edgeconv_fwd: W1tc must be 16B aligned");
+        MORIG_CHECK_ARG(ceil_div(d->E_max, 128) <= 65535, "edgeconv_fwd: E=%d too large for one launch", d->E_max);
+        if (H == 64)  return launch_tc<64, AMODE_GATHER, EPI_SEGMAX>(p, d->W1tc, d->n_frames, stream, "tc_edge<64>");
+        if (H == 128) return launch_tc<128, AMODE_GATHER, EPI_SEGMAX>(p, d->W1tc, d->n_frames, stream, "tc_edge<128>");
+        return launch_tc<256, AMODE_GATHER, EPI_SEGMAX>(p, d->W1tc, d->n_frames, stream, "tc_edge<256>");
+    }
     if (H == 64) {
         dim3 grid(ceil_div(d->E_max, 128), 1, d->n_frames);
         return launch_gemm<128, 64, AMODE_GATHER, EPI_SEGMAX>(p, grid, stream, "edge<128,64>");

@@ -227,6 +227,8 @@ def dense(layer: DenseLayer, A: torch.Tensor, a_off: int, lda: int, M: int, *, K
     d.pool, d.ldpool = _lib.ptr(pool), (pool.shape[1] if pool is not None else 0)
     d.M, d.N, d.K = M, layer.N, (layer.K if K is None else K)
     d.relu = 1 if layer.relu else 0
+    if layer.Wtc is not None and d.K == layer.K:
+        d.Wtc, d.tc_bn = layer.Wtc.data_ptr(), layer.tc_bn
     tok = None
     if _counter is not None or _timer is not None:
         kk = d.K
@@ -247,6 +249,7 @@ def edgeconv(br: EdgeBranch, pq: torch.Tensor, ldpq: int, p_off: int, q_off: int
     d.b1, d.scale, d.shift = br.b1.data_ptr(), br.scale.data_ptr(), br.shift.data_ptr()
     d.out, d.ldo, d.out_off = out.data_ptr(), ldo, out_off
     d.H = br.H
+    d.W1tc = _lib.ptr(br.W1tc)
     tok = None
     if _counter is not None or _timer is not None:
         H, e = br.H, g.e_max

@@ -58,6 +58,41 @@ def _vec(v: torch.Tensor) -> torch.Tensor:
     return v.to(torch.float32).contiguous()
 
 
+def tf32_rna(x32: torch.Tensor) -> torch.Tensor:
+    """round-to-nearest (ties away) of fp32 to TF32 (10 explicit mantissa bits), like cvt.rna.tf32.f32"""
+    bits = x32.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def tc_tile_n(n: int) -> int:
+    """n-tile (UMMA N) used by the tcgen05 engine for a layer with n outputs"""
+    return 64 if n <= 64 else (128 if n <= 128 else 256)
+
+
+def pack_tc_blob(w_out_in: torch.Tensor, k: int, bn: int) -> torch.Tensor:
+    """Tensor-core image of a Linear weight [N, K'] (fp64): split into TF32 hi + lo (W ~ hi + lo, 3xTF32
+    compensation) and laid out as the byte image of the kernel's shared-memory B stage:
+
+        blob[n_tile][k_chunk][half = hi|lo][row n (bn)][16-byte chunk c ^ (n % 8)][4 floats]
+
+    i.e. K-major rows of 32 fp32 (128 bytes) with the SWIZZLE_128B pattern already applied, so that one
+    cp.async.bulk per (n_tile, k_chunk) fills the stage (csrc/gemm_tc.cuh).  K is zero-padded to a multiple
+    of 32 (`k` = the K the kernel will be launched with), N to a multiple of bn."""
+    n, kin = w_out_in.shape
+    nk = (k + 31) // 32
+    nt = (n + bn - 1) // bn
+    wp = torch.zeros(nt * bn, nk * 32, dtype=torch.float64, device=w_out_in.device)
+    wp[:n, :kin] = w_out_in
+    hi = tf32_rna(wp.to(torch.float32))
+    lo = tf32_rna((wp - hi.to(torch.float64)).to(torch.float32))
+    both = torch.stack([hi, lo], dim=0)                               # [2, nt*bn, nk*32]
+    both = both.reshape(2, nt, bn, nk, 8, 4).permute(1, 3, 0, 2, 4, 5)  # [nt, nk, 2, bn, chunk, 4]
+    rows = torch.arange(bn, device=wp.device)
+    src_chunk = torch.arange(8, device=wp.device).unsqueeze(0) ^ (rows % 8).unsqueeze(1)   # dst chunk d holds src d^(n%8)
+    idx = src_chunk.view(1, 1, 1, bn, 8, 1).expand(nt, nk, 2, bn, 8, 4)
+    return torch.gather(both, 4, idx).contiguous().reshape(-1)
+
+
 @dataclass
 class DenseLayer:
     """one `morig_dense_fwd` worth of parameters"""
@@ -68,10 +103,19 @@ class DenseLayer:
     scale: Optional[torch.Tensor] = None
     shift: Optional[torch.Tensor] = None
     relu: bool = False
+    Wtc: Optional[torch.Tensor] = None     # tcgen05 image (pack_tc_blob) or None -> CUDA-core engine
+    tc_bn: int = 0
 
     @property
     def ldw(self) -> int:
         return self.W.shape[1]
+
+    def with_tc(self, w_out_in: torch.Tensor) -> "DenseLayer":
+        """attach the tensor-core image when the layer is large enough to benefit (K >= 32, N >= 48)"""
+        if self.K >= 32 and self.K % 4 == 0 and self.N >= 48:
+            self.tc_bn = tc_tile_n(self.N)
+            self.Wtc = pack_tc_blob(w_out_in, self.K, self.tc_bn)
+        return self
 
 
 def pack_mlp_layer(sd, prefix: str, k_pad: Optional[int] = None, cols: Optional[torch.Tensor] = None) -> DenseLayer:
@@ -82,13 +126,13 @@ def pack_mlp_layer(sd, prefix: str, k_pad: Optional[int] = None, cols: Optional[
         w = w[:, cols]
     s, t = bn_affine(sd, prefix + ".2")
     return DenseLayer(W=_pack_wt(w, k_pad), K=(w.shape[1] if k_pad is None else k_pad), N=w.shape[0],
-                      bias=_vec(_f64(sd[prefix + ".0.bias"])), scale=_vec(s), shift=_vec(t), relu=True)
+                      bias=_vec(_f64(sd[prefix + ".0.bias"])), scale=_vec(s), shift=_vec(t), relu=True).with_tc(w)
 
 
 def pack_linear(sd, prefix: str, bias: bool = True) -> DenseLayer:
     w = _f64(sd[prefix + ".weight"])
     return DenseLayer(W=_pack_wt(w), K=w.shape[1], N=w.shape[0],
-                      bias=_vec(_f64(sd[prefix + ".bias"])) if bias else None)
+                      bias=_vec(_f64(sd[prefix + ".bias"])) if bias else None).with_tc(w)
 
 
 @dataclass
@@ -99,6 +143,7 @@ class EdgeBranch:
     scale: torch.Tensor
     shift: torch.Tensor
     H: int
+    W1tc: Optional[torch.Tensor] = None    # tcgen05 image of W1 (H >= 64)
 
 
 def _edge_mlp_parts(sd, prefix: str):
@@ -115,6 +160,8 @@ def _edge_mlp_parts(sd, prefix: str):
     w1f = w1 * s0.unsqueeze(0)
     b1f = b1 + w1 @ t0
     br = EdgeBranch(W1=_pack_wt(w1f), b1=_vec(b1f), scale=_vec(s1), shift=_vec(t1), H=w1.shape[0])
+    if br.H in (64, 128, 256):
+        br.W1tc = pack_tc_blob(w1f, br.H, br.H)
     return wa - wb, wb, b0, br
 
 
@@ -143,7 +190,8 @@ def pack_gcu(sd, prefix: str, pos_parts: list, k_pad_x: Optional[int] = None) ->
     H, Dp = px_t[3].H, pp_t[3].H
     w = torch.cat([px_t[0], px_t[1], px_g[0], px_g[1]], dim=0)              # [4H, C]
     b = torch.cat([px_t[2], torch.zeros_like(px_t[2]), px_g[2], torch.zeros_like(px_g[2])])
-    pq_x = DenseLayer(W=_pack_wt(w, k_pad_x), K=(w.shape[1] if k_pad_x is None else k_pad_x), N=4 * H, bias=_vec(b))
+    pq_x = DenseLayer(W=_pack_wt(w, k_pad_x), K=(w.shape[1] if k_pad_x is None else k_pad_x), N=4 * H,
+                      bias=_vec(b)).with_tc(w)
     pos_col = sum(p[0].shape[0] for p in pos_parts)
     for part in (pp_t, pp_g):
         pos_parts.append((part[0], part[2]))                               # P block (+bias)
@@ -156,7 +204,8 @@ def pack_gcu(sd, prefix: str, pos_parts: list, k_pad_x: Optional[int] = None) ->
 def fuse_pos_pq(pos_parts: list, k_pad: Optional[int] = None) -> DenseLayer:
     w = torch.cat([p[0] for p in pos_parts], dim=0)
     b = torch.cat([p[1] for p in pos_parts])
-    return DenseLayer(W=_pack_wt(w, k_pad), K=(w.shape[1] if k_pad is None else k_pad), N=w.shape[0], bias=_vec(b))
+    return DenseLayer(W=_pack_wt(w, k_pad), K=(w.shape[1] if k_pad is None else k_pad), N=w.shape[0],
+                      bias=_vec(b)).with_tc(w)
 
 
 @dataclass
@@ -188,7 +237,7 @@ def pack_gcn_rig(sd: Dict[str, torch.Tensor], prefix: str) -> GCNRigPack:
     G = glb.N                                                               # 1024
     # mlp_transform.0.0 input columns: [x_global (G) | pos (3) | feature (F) | x1 | x2 | x3]
     w_t0 = _f64(sd[prefix + ".mlp_transform.0.0.0.weight"])
-    t0_global = DenseLayer(W=_pack_wt(w_t0[:, :G]), K=G, N=w_t0.shape[0])
+    t0_global = DenseLayer(W=_pack_wt(w_t0[:, :G]), K=G, N=w_t0.shape[0]).with_tc(w_t0[:, :G])
     dev = w_t0.device
     cols = torch.cat([torch.arange(G + 3 + F, G + 3 + F + xw, device=dev),  # x1|x2|x3
                       torch.arange(G + 3, G + 3 + F, device=dev),           # feature
@@ -279,7 +328,7 @@ def pack_skin(sd, prefix: str, skin_width: int, nearest_bone: int, use_Dg: bool,
     w_c0 = _f64(sd[prefix + ".cls_branch.0.0.0.weight"])                    # [1024, 256 + 1024]
     c_x = gcus[2].out
     c0 = pack_mlp_layer(sd, prefix + ".cls_branch.0.0", cols=torch.arange(0, c_x, device=dev))
-    c0_global = DenseLayer(W=_pack_wt(w_c0[:, c_x:]), K=w_c0.shape[1] - c_x, N=w_c0.shape[0])
+    c0_global = DenseLayer(W=_pack_wt(w_c0[:, c_x:]), K=w_c0.shape[1] - c_x, N=w_c0.shape[0]).with_tc(w_c0[:, c_x:])
     return SkinPack(in_pos=in_pos, k_pos=k_pos, skin_cols=torch.tensor(cols, dtype=torch.int32, device=dev),
                     gcus=gcus, pq_pos=fuse_pos_pq(pos_parts, k_pad=k_pos),
                     g0=pack_mlp_layer(sd, prefix + ".multi_layer_tranform2.0"),

@@ -73,6 +73,47 @@ def test_dense_fwd(M, K, N):
     assert helpers.max_abs_diff(C, ref) < 2e-5
 
 
+@pytest.mark.parametrize("M,K,N", [(128, 32, 64), (300, 96, 64), (1000, 64, 128), (257, 288, 256), (4099, 544, 512),
+                                   (640, 840, 1024), (20, 1024, 1024), (513, 36, 768)])
+def test_dense_fwd_tensor_core(M, K, N):
+    """tcgen05 3xTF32 engine against an fp64 reference: fp32-class accuracy is required (tolerance of the path
+    is 1e-4 absolute after ~20 chained layers, so a single layer must stay near fp32 rounding)"""
+    g = torch.Generator().manual_seed(M + K + N)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b, s, t = torch.randn(N, generator=g), torch.randn(N, generator=g), torch.randn(N, generator=g)
+    layer = packing.DenseLayer(W=packing._pack_wt(W.double()).to(DEV), K=K, N=N, bias=b.to(DEV), scale=s.to(DEV),
+                               shift=t.to(DEV), relu=True).with_tc(W.double())
+    assert layer.Wtc is not None
+    layer.Wtc = layer.Wtc.to(DEV)
+    C = torch.full((M, N), float("nan"), device=DEV)
+    engine.dense(layer, A.to(DEV), 0, K, M, C=C, ldc=N)
+    ref = torch.relu(A.double() @ W.double().t() + b.double()) * s.double() + t.double()
+    assert helpers.max_abs_diff(C, ref) < 2e-5
+
+
+def test_dense_tensor_core_pool_and_rowbias():
+    n, frames, B, K, N = 700, 3, 4, 64, 200
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(n * frames, K, generator=g)
+    W = torch.randn(N, K, generator=g) / 8
+    rb = torch.randn(frames * B, N, generator=g)
+    batch = torch.sort(torch.randint(0, B, (n,), generator=g)).values
+    batch[0], batch[-1] = 0, B - 1
+    binfo = engine.BatchInfo(batch32=batch.to(torch.int32).to(DEV), n_graphs=B)
+    layer = packing.DenseLayer(W=packing._pack_wt(W.double()).to(DEV), K=K, N=N, relu=True).with_tc(W.double())
+    layer.Wtc = layer.Wtc.to(DEV)
+    C = torch.empty(n * frames, N, device=DEV)
+    pool = torch.full((frames * B, N), float("-inf"), device=DEV)
+    engine.dense(layer, A.to(DEV), 0, K, n * frames, C=C, ldc=N, pool=pool, rowbias=rb.to(DEV), binfo=binfo, n_vtx=n)
+    grp = (torch.arange(n * frames) // n) * B + batch[torch.arange(n * frames) % n]
+    ref = torch.relu(A.double() @ W.double().t() + rb.double()[grp])
+    assert helpers.max_abs_diff(C, ref) < 2e-5
+    present = torch.zeros(frames * B, dtype=torch.bool); present[grp] = True
+    stored_max = torch.full((frames * B, N), float("-inf")).scatter_reduce(0, grp[:, None].expand(-1, N), C.cpu(), "amax")
+    assert torch.equal(pool.cpu()[present], stored_max[present])
+
+
 def test_dense_pool_and_rowbias():
     n, frames, B, K, N = 700, 3, 4, 64, 200
     g = torch.Generator().manual_seed(0)

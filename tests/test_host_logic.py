@@ -145,6 +145,36 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert _lib.load().morig_version() == 1
 
 
+def test_tensor_core_weight_image_layout():
+    """pack_tc_blob: TF32 hi/lo split + SWIZZLE_128B K-major stage image, checked with an independent
+    address computation (byte offset = row*128 + ((chunk ^ (row % 8)) * 16) inside each [bn x 32] half)"""
+    import numpy as np
+    from morig_b200 import packing
+    g = torch.Generator().manual_seed(0)
+    n, k, bn = 300, 70, 256
+    w = torch.randn(n, k, generator=g, dtype=torch.float64)
+    blob = packing.pack_tc_blob(w, 72, bn).numpy()
+    nk, nt = 3, 2
+    assert blob.size == nt * nk * 2 * bn * 32
+    img = blob.reshape(nt, nk, 2, bn * 32)
+    rec = np.zeros((2, nt * bn, nk * 32), dtype=np.float32)
+    for t in range(nt):
+        for kc in range(nk):
+            for half in range(2):
+                flat = img[t, kc, half]
+                for row in range(bn):
+                    for c in range(8):
+                        off = (row * 128 + ((c ^ (row % 8)) * 16)) // 4
+                        rec[half, t * bn + row, kc * 32 + 4 * c: kc * 32 + 4 * c + 4] = flat[off:off + 4]
+    hi, lo = rec
+    assert not (hi.view(np.uint32) & 0x1FFF).any() and not (lo.view(np.uint32) & 0x1FFF).any()   # valid TF32 values
+    full = np.zeros((nt * bn, nk * 32))
+    full[:n, :k] = w.numpy()
+    err = np.abs(hi.astype(np.float64) + lo.astype(np.float64) - full)
+    assert err.max() <= 2.0 ** -21 * np.abs(full).max()
+    assert np.abs(hi - full).max() <= 2.0 ** -11 * np.abs(full).max()
+
+
 def test_c_abi_argument_validation_without_gpu():
     """entry points must reject bad descriptors with a code + message instead of launching"""
     lib = _lib.load()
