@@ -80,7 +80,12 @@ static int launch_tc(const GemmP &p, const float *blob, int frames, cudaStream_t
     tp.g = p;
     tp.Bblob = blob;
     tp.nK = ceil_div(p.K, tc::KC);
-    dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, tc::BM), frames);
+    tp.ntn = ceil_div(p.N, BN);
+    tp.ntm = ceil_div(p.M, tc::BM);
+    tp.frames = frames;
+    const long long tiles = (long long)tp.ntn * tp.ntm * frames;
+    const int sms = sm_count();
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);     // persistent: one CTA per SM
     kern<<<grid, tc::THREADS, smem, stream>>>(tp);
     MORIG_LAUNCH_CHECK(name);
     return 0;

@@ -1,18 +1,22 @@
-// tcgen05 tile engine (sm_100a): 3xTF32 error-compensated GEMM with fp32 accumulation in TMEM.
+// tcgen05 tile engine (sm_100a): persistent, warp-specialised 3xTF32 GEMM with fp32 accumulation in TMEM.
 //
-//   D[128 x BN] (+)= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi        (kind::tf32, cta_group::1, M=128, N=BN, K=8)
+//   D[128 x BN] (+)= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi        (kind::tf32, cta_group::1, M=128, N=BN, K=8)
 //
-// fp32 inputs are split x = hi + lo with hi = rna_tf32(x); dropping lo*lo leaves ~2^-21 relative error per
-// product, i.e. fp32-class results (the 1e-4 absolute tolerance of the path rules out plain TF32/BF16).
+// fp32 inputs are split x = hi + lo with hi = rna_tf32(x); dropping lo*lo leaves fp32-class results (the 1e-4
+// absolute tolerance of the path rules out plain TF32/BF16).
 //
-//   A operand  produced by 8 warps straight into 128B-swizzled K-major shared memory, 32 k-columns per stage:
+// One CTA per SM walks tiles t = blockIdx.x, +gridDim.x, ... ; three roles run decoupled through mbarriers:
+//   warps 0-3  A producers: 32 k-columns per stage written straight into 128B-swizzled K-major shared memory;
 //              plain activation rows, or relu(P[tgt[e]] + Q[col[e]]) gathered per CSR slot (fused EdgeConv)
-//   B operand  weights pre-split (hi|lo) and pre-swizzled on the host into per-(n-tile, k-chunk) blobs that are
-//              byte images of the shared-memory stage; one cp.async.bulk (TMA engine, mbarrier complete_tx) each
-//   MMA        one elected thread of warp 8 issues 12 tcgen05.mma per stage and tcgen05.commit's to mbarriers
-//   epilogue   the 8 producer warps read the accumulator with tcgen05.ld (32 lanes x 32 columns per warp):
-//              bias (+ per-graph bias) -> ReLU -> BatchNorm affine, then store / per-graph column max /
-//              segmented max over the CSR target (tile staged in shared memory, column-parallel walk)
+//   warp  8    one elected lane: cp.async.bulk of the pre-split / pre-swizzled weight image of each
+//              (n-tile, k-chunk) (TMA engine, mbarrier complete_tx) and the 12 tcgen05.mma per stage;
+//              tcgen05.commit releases stages and publishes accumulators
+//   warps 4-7  epilogue: tcgen05.ld of one of the TWO accumulator buffers (so the next tile's MMAs overlap),
+//              bias (+ per-graph bias) -> ReLU -> BatchNorm affine, then
+//                 store rows / per-graph column max (warp shuffles + ordered atomics) /
+//                 segmented max over the CSR target: in-register segmented scan across the 32 rows of the warp,
+//                 segment tails transposed through a 4 KB per-warp staging tile for coalesced row stores;
+//                 segments crossing a warp's 32 rows merge with ordered-int atomic max (exact, deterministic)
 #pragma once
 #include "gemm_simt.cuh"
 
@@ -22,19 +26,21 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int KC = 32;                       // fp32 k-columns per stage = one 128-byte swizzle row
 constexpr int A_HALF_BYTES = BM * 128;       // 16 KB: hi (then lo) image of the A stage
-constexpr int PRODUCER_THREADS = 256;
-constexpr int THREADS = PRODUCER_THREADS + 32;
+constexpr int PRODUCER_WARPS = 4;
+constexpr int EPILOGUE_WARPS = 4;
+constexpr int THREADS = 32 * (PRODUCER_WARPS + EPILOGUE_WARPS + 1);
+constexpr int ROWS_PER_THREAD = BM / (PRODUCER_WARPS * 4);       // 8 rows, one 16-byte chunk each
 
 template <int BN> struct Cfg {
     static constexpr int B_HALF_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = 2 * A_HALF_BYTES + 2 * B_HALF_BYTES;
     static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
     static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int CS_LD = BN + 1;                         // epilogue staging tile row stride (floats)
-    static constexpr int CS_BYTES = BM * CS_LD * 4;
-    static constexpr int MAIN_BYTES = PIPE_BYTES > CS_BYTES ? PIPE_BYTES : CS_BYTES;
-    static constexpr int AUX_BYTES = 1024;                       // barriers, tmem pointer, row targets
-    static constexpr int SMEM_BYTES = MAIN_BYTES + AUX_BYTES + 1024;   // + slack for 1024B alignment
+    static constexpr int STG_LD = 33;                                        // staging tile row stride (floats)
+    static constexpr int STG_BYTES = EPILOGUE_WARPS * 32 * STG_LD * 4;       // 16.5 KB
+    static constexpr int AUX_BYTES = 512;                                    // barriers + tmem pointer
+    static constexpr int SMEM_BYTES = PIPE_BYTES + STG_BYTES + AUX_BYTES + 1024;   // + slack for 1024B alignment
+    static constexpr int TMEM_COLS = 2 * BN;                                 // two accumulator buffers
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -137,7 +143,10 @@ struct TcP {
     GemmP g;                 // shared operand/epilogue description (W/ldw unused here)
     const float *Bblob;      // [n_tiles][nK][hi|lo][BN*32] pre-swizzled weight images
     int nK;                  // k-chunks of 32
+    int ntn, ntm, frames;    // tile grid (ntm is an upper bound in gather mode)
 };
+
+struct TileCoord { int n_tile, m0, frame; };
 
 template <int BN, int AMODE, int EPI>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
@@ -147,42 +156,50 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;          // swizzle atoms need 1024 B alignment
     uint8_t *smem = smem_raw + (base - raw_addr);
-    uint8_t *aux = smem + C::MAIN_BYTES;
-    const uint32_t aux_addr = base + C::MAIN_BYTES;
-    // aux: [0,8S) a_full, [64,64+8S) b_full, [128,..) mma_done, 192 acc_full, 200 tmem ptr, 256.. row targets
+    float *stg_all = reinterpret_cast<float *>(smem + C::PIPE_BYTES);
+    uint8_t *aux = smem + C::PIPE_BYTES + C::STG_BYTES;
+    const uint32_t aux_addr = base + C::PIPE_BYTES + C::STG_BYTES;
+    // aux: a_full[S] @0, b_full[S] @64, mma_done[S] @128, acc_full[2] @192, acc_empty[2] @208, tmem ptr @224
     auto bar_a = [&](int s) { return aux_addr + 8u * s; };
     auto bar_b = [&](int s) { return aux_addr + 64u + 8u * s; };
     auto bar_m = [&](int s) { return aux_addr + 128u + 8u * s; };
-    const uint32_t bar_acc = aux_addr + 192u;
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(aux + 200);
-    int32_t *s_tgt = reinterpret_cast<int32_t *>(aux + 256);
+    auto bar_accf = [&](int b) { return aux_addr + 192u + 8u * b; };
+    auto bar_acce = [&](int b) { return aux_addr + 208u + 8u * b; };
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(aux + 224);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_tile = blockIdx.x;                   // n-tiles fastest: CTAs sharing A rows run together
-    const int m0 = blockIdx.y * BM;
-    const int n0 = n_tile * BN;
-    const int frame = (AMODE == AMODE_GATHER) ? blockIdx.z : 0;
-    int M = p.M;
-    if (AMODE == AMODE_GATHER) {
-        M = p.rowptr[p.n_vtx_frame];
-        if (m0 >= M) return;
-    }
     const int nK = tp.nK;
+    int M = p.M, ntm = tp.ntm;
+    if (AMODE == AMODE_GATHER) {
+        M = p.rowptr[p.n_vtx_frame];                 // E' lives on the device only
+        ntm = (M + BM - 1) / BM;
+    }
+    const int total_tiles = tp.ntn * ntm * tp.frames;
+    auto decode = [&](int t) {
+        TileCoord c;
+        c.n_tile = t % tp.ntn;
+        const int r = t / tp.ntn;
+        c.m0 = (r % ntm) * BM;
+        c.frame = r / ntm;
+        return c;
+    };
 
     if (warp == 8) {
         if (lane == 0) {
             for (int s = 0; s < C::STAGES; ++s) {
-                mbar_init(bar_a(s), PRODUCER_THREADS);
+                mbar_init(bar_a(s), PRODUCER_WARPS);
                 mbar_init(bar_b(s), 1);
                 mbar_init(bar_m(s), 1);
             }
-            mbar_init(bar_acc, 1);
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(bar_accf(b), 1);
+                mbar_init(bar_acce(b), EPILOGUE_WARPS);
+            }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(aux_addr + 200u, BN);
+        tmem_alloc(aux_addr + 224u, C::TMEM_COLS);
     }
-    if (EPI == EPI_SEGMAX && tid < BM) s_tgt[tid] = (m0 + tid < M) ? p.tgt[m0 + tid] : -1;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -193,71 +210,87 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc<BN>();
             const uint32_t b_bytes = 2u * C::B_HALF_BYTES;
-            const uint8_t *gB = reinterpret_cast<const uint8_t *>(tp.Bblob) + (size_t)n_tile * nK * b_bytes;
-            auto issue_b = [&](int kc) {
-                const int s = kc % C::STAGES;
+            const uint8_t *gB = reinterpret_cast<const uint8_t *>(tp.Bblob);
+            const int my_tiles = (total_tiles > (int)blockIdx.x) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+            const long long my_chunks = (long long)my_tiles * nK;
+            auto issue_b = [&](long long it) {                     // it = CTA-local running chunk index
+                const int li = (int)(it / nK), kc = (int)(it % nK);
+                const TileCoord tc_ = decode((int)blockIdx.x + li * (int)gridDim.x);
+                const int s = (int)(it % C::STAGES);
                 const uint32_t dst = base + s * C::STAGE_BYTES + 2 * A_HALF_BYTES;
                 mbar_arrive_expect_tx(bar_b(s), b_bytes);
-                bulk_g2s(dst, gB + (size_t)kc * b_bytes, b_bytes, bar_b(s));
+                bulk_g2s(dst, gB + ((size_t)tc_.n_tile * nK + kc) * b_bytes, b_bytes, bar_b(s));
             };
-            for (int kc = 0; kc < C::STAGES - 1 && kc < nK; ++kc) issue_b(kc);
-            for (int kc = 0; kc < nK; ++kc) {
-                const int s = kc % C::STAGES;
-                const uint32_t ph = (kc / C::STAGES) & 1;
-                mbar_wait(bar_a(s), ph);
-                mbar_wait(bar_b(s), ph);
+            for (long long it = 0; it < C::STAGES - 1 && it < my_chunks; ++it) issue_b(it);
+            long long it = 0;
+            for (int li = 0; li < my_tiles; ++li) {
+                const int buf = li & 1;
+                mbar_wait(bar_acce(buf), ((li >> 1) & 1) ^ 1);     // accumulator buffer drained by the epilogue
                 tc_fence_after();
-                const uint32_t a_hi = base + s * C::STAGE_BYTES, a_lo = a_hi + A_HALF_BYTES;
-                const uint32_t b_hi = a_hi + 2 * A_HALF_BYTES, b_lo = b_hi + C::B_HALF_BYTES;
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+                for (int kc = 0; kc < nK; ++kc, ++it) {
+                    const int s = (int)(it % C::STAGES);
+                    const uint32_t ph = (uint32_t)((it / C::STAGES) & 1);
+                    mbar_wait(bar_a(s), ph);
+                    mbar_wait(bar_b(s), ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = base + s * C::STAGE_BYTES, a_lo = a_hi + A_HALF_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * A_HALF_BYTES, b_lo = b_hi + C::B_HALF_BYTES;
 #pragma unroll
-                for (int k = 0; k < KC / 8; ++k) {
-                    const uint32_t ko = k * 32;                  // 8 tf32 = 32 bytes along the swizzled row
-                    const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
-                    const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
-                    umma_tf32(tmem_base, dal, dbh, idesc, (kc | k) != 0);
-                    umma_tf32(tmem_base, dah, dbl, idesc, 1);
-                    umma_tf32(tmem_base, dah, dbh, idesc, 1);
+                    for (int k = 0; k < KC / 8; ++k) {
+                        const uint32_t ko = k * 32;              // 8 tf32 = 32 bytes along the swizzled row
+                        const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
+                        const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
+                        umma_tf32(tmem_d, dal, dbh, idesc, (kc | k) != 0);
+                        umma_tf32(tmem_d, dah, dbl, idesc, 1);
+                        umma_tf32(tmem_d, dah, dbh, idesc, 1);
+                    }
+                    umma_commit(bar_m(s));                       // frees stage s when these MMAs retire
+                    const long long nxt = it + C::STAGES - 1;
+                    if (nxt < my_chunks) {
+                        if (it >= 1) mbar_wait(bar_m((int)((it - 1) % C::STAGES)), (uint32_t)(((it - 1) / C::STAGES) & 1));
+                        issue_b(nxt);
+                    }
                 }
-                umma_commit(bar_m(s));                           // frees stage s when these MMAs retire
-                const int nxt = kc + C::STAGES - 1;
-                if (nxt < nK) {
-                    if (kc >= 1) mbar_wait(bar_m((kc - 1) % C::STAGES), ((kc - 1) / C::STAGES) & 1);
-                    issue_b(nxt);
-                }
+                umma_commit(bar_accf(buf));                      // accumulator complete -> epilogue
             }
-            umma_commit(bar_acc);
         }
         __syncwarp();
-    } else {
+    } else if (warp < PRODUCER_WARPS) {
         // ================= producer warps: A stage images =================
-        // thread -> 16-byte chunk c of rows (tid>>3) + 32*pass
-        const int c = tid & 7;
-        const int row0 = tid >> 3;
-        const float *src0[4];
-        const float *src1[4];
-        bool ok[4];
+        const int c = tid & 7;                       // 16-byte chunk of the 128-byte row
+        const int row0 = tid >> 3;                   // rows row0 + 16*ps
+        long long it = 0;
+        float4 cur[ROWS_PER_THREAD], nxt[ROWS_PER_THREAD];
+        const float *src0[ROWS_PER_THREAD];
+        const float *src1[ROWS_PER_THREAD];
+        uint32_t okmask = 0;
+
+        auto setup_rows = [&](const TileCoord &t) {
+            okmask = 0;
 #pragma unroll
-        for (int ps = 0; ps < 4; ++ps) {
-            const int r = m0 + row0 + 32 * ps;
-            ok[ps] = r < M;
-            if (AMODE == AMODE_GATHER) {
-                int i = 0, j = 0;
-                if (ok[ps]) { i = p.tgt[r]; j = p.col[r]; }
-                const size_t fb = (size_t)frame * p.n_vtx_frame;
-                src0[ps] = p.P + (fb + i) * (size_t)p.ldpq + 4 * c;
-                src1[ps] = p.Q + (fb + j) * (size_t)p.ldpq + 4 * c;
-            } else {
-                src0[ps] = p.A + (size_t)(ok[ps] ? r : 0) * p.lda + 4 * c;
-                src1[ps] = nullptr;
+            for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
+                const int r = t.m0 + row0 + 16 * ps;
+                const bool ok = r < M;
+                okmask |= (ok ? 1u : 0u) << ps;
+                if (AMODE == AMODE_GATHER) {
+                    int i = 0, j = 0;
+                    if (ok) { i = p.tgt[r]; j = p.col[r]; }
+                    const size_t fb = (size_t)t.frame * p.n_vtx_frame;
+                    src0[ps] = p.P + (fb + i) * (size_t)p.ldpq + 4 * c;
+                    src1[ps] = p.Q + (fb + j) * (size_t)p.ldpq + 4 * c;
+                } else {
+                    src0[ps] = p.A + (size_t)(ok ? r : 0) * p.lda + 4 * c;
+                    src1[ps] = nullptr;
+                }
             }
-        }
-        float4 cur[4], nxt[4];
-        auto load_chunk = [&](int kc, float4 (&dst)[4]) {
+        };
+        auto load_chunk = [&](int kc, float4 (&dst)[ROWS_PER_THREAD]) {
             const int k = kc * KC + 4 * c;
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
+            for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok[ps] && k < p.K) {
+                if (((okmask >> ps) & 1u) && k < p.K) {
                     v = *reinterpret_cast<const float4 *>(src0[ps] + kc * KC);
                     if (AMODE == AMODE_GATHER) {
                         const float4 q = *reinterpret_cast<const float4 *>(src1[ps] + kc * KC);
@@ -268,130 +301,177 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
                 dst[ps] = v;
             }
         };
-        load_chunk(0, cur);
-        for (int kc = 0; kc < nK; ++kc) {
-            if (kc + 1 < nK) load_chunk(kc + 1, nxt);
-            const int s = kc % C::STAGES;
-            if (kc >= C::STAGES) mbar_wait(bar_m(s), ((kc / C::STAGES) - 1) & 1);
-            uint8_t *a_hi = smem + s * C::STAGE_BYTES;
-            uint8_t *a_lo = a_hi + A_HALF_BYTES;
-#pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                const int row = row0 + 32 * ps;
-                const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
-                const float4 v = cur[ps];
-                float4 h, l;
-                h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-                *reinterpret_cast<float4 *>(a_hi + off) = h;
-                *reinterpret_cast<float4 *>(a_lo + off) = l;
-            }
-            fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core (async proxy)
-            mbar_arrive(bar_a(s));
-            if (kc + 1 < nK) {
-#pragma unroll
-                for (int ps = 0; ps < 4; ++ps) cur[ps] = nxt[ps];
-            }
-        }
 
-        // ================= epilogue =================
-        mbar_wait(bar_acc, 0);
-        tc_fence_after();
-        const int q = warp & 3;                      // TMEM lane quarter of this warp
-        const int half = warp >> 2;                  // column half handled by this warp
-        const int row = q * 32 + lane;
-        const int r = m0 + row;
-        const bool row_ok = r < M;
-        int g = 0;
-        if (EPI == EPI_STORE && p.batch && row_ok) g = (r / p.n_vtx) * p.n_graphs + p.batch[r % p.n_vtx];
-        float *Cs = reinterpret_cast<float *>(smem);
-#pragma unroll 1
-        for (int cb = 0; cb < BN / 64; ++cb) {
-            const int col0 = half * (BN / 2) + cb * 32;
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int n = n0 + col0 + j;
-                const bool n_ok = n < p.N;
-                float x = v[j] + ((n_ok && p.bias) ? p.bias[n] : 0.f);
-                if (EPI == EPI_STORE && p.rowbias && n_ok && row_ok) x += p.rowbias[(size_t)g * p.ldrb + n];
-                if (EPI == EPI_SEGMAX || p.relu) x = fmaxf(x, 0.f);
-                x = fmaf(x, (n_ok && p.scale) ? p.scale[n] : 1.f, (n_ok && p.shift) ? p.shift[n] : 0.f);
-                v[j] = x;
-            }
-            if (EPI == EPI_SEGMAX) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) Cs[row * C::CS_LD + col0 + j] = v[j];
-            } else {
-                if (p.C && row_ok) {
-                    float *dst = p.C + (size_t)r * p.ldc + n0 + col0;
-                    if (p.c_vec && n0 + col0 + 31 < p.N) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (n0 + col0 + j < p.N) dst[j] = v[j];
-                    }
+        int t = blockIdx.x;
+        if (t < total_tiles) {
+            setup_rows(decode(t));
+            load_chunk(0, cur);
+        }
+        for (; t < total_tiles; t += gridDim.x) {
+            for (int kc = 0; kc < nK; ++kc, ++it) {
+                const bool last = kc + 1 == nK;
+                const int tn = t + gridDim.x;
+                if (!last) {
+                    load_chunk(kc + 1, nxt);
+                } else if (tn < total_tiles) {       // cross the tile boundary: next tile's rows and first chunk
+                    setup_rows(decode(tn));
+                    load_chunk(0, nxt);
                 }
-                if (p.pool) {
-                    const int g0 = __shfl_sync(0xffffffffu, g, 0);
-                    const bool uniform = __all_sync(0xffffffffu, row_ok && g == g0);
-                    if (uniform) {
-                        float mine = neg_inf();
+                const int s = (int)(it % C::STAGES);
+                if (it >= C::STAGES) mbar_wait(bar_m(s), (uint32_t)(((it / C::STAGES) - 1) & 1));
+                uint8_t *a_hi = smem + s * C::STAGE_BYTES;
+                uint8_t *a_lo = a_hi + A_HALF_BYTES;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float m = v[j];
-#pragma unroll
-                            for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-                            if (lane == j) mine = m;
-                        }
-                        const int n = n0 + col0 + lane;
-                        if (n < p.N) atomic_max_f32(p.pool + (size_t)g0 * p.ldpool + n, mine);
-                    } else if (row_ok) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (n0 + col0 + j < p.N) atomic_max_f32(p.pool + (size_t)g * p.ldpool + n0 + col0 + j, v[j]);
-                    }
+                for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
+                    const int row = row0 + 16 * ps;
+                    const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
+                    const float4 v = cur[ps];
+                    float4 h, l;
+                    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+                    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+                    *reinterpret_cast<float4 *>(a_hi + off) = h;
+                    *reinterpret_cast<float4 *>(a_lo + off) = l;
                 }
+                fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_a(s));
+#pragma unroll
+                for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) cur[ps] = nxt[ps];
             }
         }
-        if (EPI == EPI_SEGMAX) {
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            constexpr int PARTS = PRODUCER_THREADS / BN;
-            constexpr int ROWS_PER = BM / PARTS;
-            const int cc = tid % BN, part = tid / BN;
-            const int n = n0 + cc;
-            if (n < p.N) {
-                const int ra = part * ROWS_PER, rb = ra + ROWS_PER;
-                const size_t fb = (size_t)frame * p.n_vtx_frame;
-                int cur_t = -1;
-                float m = neg_inf();
-                auto flush = [&]() {
-                    const int lo = p.rowptr[cur_t], hi = p.rowptr[cur_t + 1];
-                    float *dst = p.C + (fb + cur_t) * (size_t)p.ldc + n;
-                    if (lo >= m0 + ra && hi <= m0 + rb) *dst = m;
-                    else atomic_max_f32(dst, m);
-                };
-                for (int rr = ra; rr < rb; ++rr) {
-                    const int t = s_tgt[rr];
-                    if (t < 0) break;
-                    if (t != cur_t) {
-                        if (cur_t >= 0) flush();
-                        cur_t = t;
-                        m = neg_inf();
-                    }
-                    m = fmaxf(m, Cs[rr * C::CS_LD + cc]);
+    } else {
+        // ================= epilogue warps =================
+        const int q = warp & 3;                      // TMEM lane quarter of this warp (warp 4..7 -> 0..3)
+        float *stg = stg_all + q * 32 * C::STG_LD;
+        int li = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+            const TileCoord tcd = decode(t);
+            const int buf = li & 1;
+            const int n0 = tcd.n_tile * BN;
+            const int row = q * 32 + lane;
+            const int r = tcd.m0 + row;
+            const bool row_ok = r < M;
+            // per-row bookkeeping that does not depend on the accumulator: do it before waiting
+            int g = 0;
+            int tg = -1, d = 0;
+            bool is_tail = false, complete = false;
+            uint32_t tail_mask = 0;
+            if (EPI == EPI_STORE) {
+                if (p.batch && row_ok) g = (r / p.n_vtx) * p.n_graphs + p.batch[r % p.n_vtx];
+            } else {
+                tg = row_ok ? p.tgt[r] : -1;
+                const int up = __shfl_up_sync(0xffffffffu, tg, 1);
+                const int dn = __shfl_down_sync(0xffffffffu, tg, 1);
+                const bool is_head = (lane == 0) || (tg != up);
+                is_tail = (tg >= 0) && ((lane == 31) || (tg != dn));
+                const uint32_t head_mask = __ballot_sync(0xffffffffu, is_head);
+                tail_mask = __ballot_sync(0xffffffffu, is_tail);
+                const int my_head = 31 - __clz(head_mask & (0xffffffffu >> (31 - lane)));
+                d = lane - my_head;
+                if (is_tail) {
+                    const int e0w = tcd.m0 + q * 32;
+                    complete = p.rowptr[tg] >= e0w && p.rowptr[tg + 1] <= e0w + 32;
                 }
-                if (cur_t >= 0) flush();
             }
+            mbar_wait(bar_accf(buf), (uint32_t)((li >> 1) & 1));
+            tc_fence_after();
+#pragma unroll 1
+            for (int cb = 0; cb < BN / 32; ++cb) {
+                const int col0 = cb * 32;
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + col0), v);
+                const int nl = n0 + col0 + lane;     // this lane's column when lanes index columns
+                const bool nl_ok = nl < p.N;
+                const float bias_l = (nl_ok && p.bias) ? p.bias[nl] : 0.f;
+                const float scale_l = (nl_ok && p.scale) ? p.scale[nl] : 1.f;
+                const float shift_l = (nl_ok && p.shift) ? p.shift[nl] : 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = v[j] + __shfl_sync(0xffffffffu, bias_l, j);
+                    if (EPI == EPI_STORE && p.rowbias && row_ok && n0 + col0 + j < p.N)
+                        x += p.rowbias[(size_t)g * p.ldrb + n0 + col0 + j];
+                    if (EPI == EPI_SEGMAX || p.relu) x = fmaxf(x, 0.f);
+                    v[j] = fmaf(x, __shfl_sync(0xffffffffu, scale_l, j), __shfl_sync(0xffffffffu, shift_l, j));
+                }
+                if (EPI == EPI_SEGMAX) {
+                    // inclusive segmented max scan over the rows (lanes) of this warp
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = v[j];
+#pragma unroll
+                        for (int off = 1; off < 32; off <<= 1) {
+                            const float o = __shfl_up_sync(0xffffffffu, x, off);
+                            if (d >= off) x = fmaxf(x, o);
+                        }
+                        v[j] = x;
+                    }
+                    // tails -> staging rows (by tail rank); then lanes become columns for coalesced row stores
+                    __syncwarp();
+                    if (is_tail) {
+                        const int rank = __popc(tail_mask & ((1u << lane) - 1u));
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) stg[rank * C::STG_LD + j] = v[j];
+                    }
+                    __syncwarp();
+                    uint32_t mleft = tail_mask;
+                    int rank = 0;
+                    while (mleft) {
+                        const int tl = __ffs(mleft) - 1;
+                        mleft &= mleft - 1;
+                        const int t_row = __shfl_sync(0xffffffffu, tg, tl);
+                        const bool t_complete = __shfl_sync(0xffffffffu, (int)complete, tl) != 0;
+                        const float x = stg[rank * C::STG_LD + lane];
+                        ++rank;
+                        if (nl_ok) {
+                            float *dst = p.C + ((size_t)tcd.frame * p.n_vtx_frame + t_row) * (size_t)p.ldc + nl;
+                            if (t_complete) *dst = x;
+                            else atomic_max_f32(dst, x);
+                        }
+                    }
+                } else {
+                    if (p.C) {
+                        // transpose through the per-warp staging tile: lanes become columns, so every row is
+                        // written as one coalesced 128-byte segment whatever the destination row stride
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) stg[lane * C::STG_LD + j] = v[j];
+                        __syncwarp();
+                        const int rows_here = min(32, M - (tcd.m0 + q * 32));
+                        float *dst = p.C + (size_t)(tcd.m0 + q * 32) * p.ldc + nl;
+                        if (nl_ok) {
+#pragma unroll 4
+                            for (int rr = 0; rr < rows_here; ++rr) dst[(size_t)rr * p.ldc] = stg[rr * C::STG_LD + lane];
+                        }
+                    }
+                    if (p.pool) {
+                        const int g0 = __shfl_sync(0xffffffffu, g, 0);
+                        const bool uniform = __all_sync(0xffffffffu, row_ok && g == g0);
+                        if (uniform) {
+                            float mine = neg_inf();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float m = v[j];
+#pragma unroll
+                                for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+                                if (lane == j) mine = m;
+                            }
+                            if (nl_ok) atomic_max_f32(p.pool + (size_t)g0 * p.ldpool + nl, mine);
+                        } else if (row_ok) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (n0 + col0 + j < p.N) atomic_max_f32(p.pool + (size_t)g * p.ldpool + n0 + col0 + j, v[j]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acce(buf));           // buffer may be overwritten by tile li + 2
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, BN);
+    if (warp == 8) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 }  // namespace tc

@@ -184,7 +184,8 @@ def collate(meshes: list) -> Batch:
                  tpl_edge_index=torch.from_numpy(np.concatenate(tpl, 1)),
                  geo_edge_index=torch.from_numpy(np.concatenate(geo, 1)),
                  batch=torch.from_numpy(np.concatenate(bat)),
-                 pred_flow=torch.from_numpy(np.concatenate(flow)))
+                 pred_flow=torch.from_numpy(np.concatenate(flow)),
+                 num_graphs=len(meshes))                   # PyG `Batch.num_graphs`
     if skin:
         data.skin_input = torch.from_numpy(np.concatenate(skin))
     return data

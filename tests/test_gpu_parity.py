@@ -89,7 +89,9 @@ def test_dense_fwd_tensor_core(M, K, N):
     C = torch.full((M, N), float("nan"), device=DEV)
     engine.dense(layer, A.to(DEV), 0, K, M, C=C, ldc=N)
     ref = torch.relu(A.double() @ W.double().t() + b.double()) * s.double() + t.double()
-    assert helpers.max_abs_diff(C, ref) < 2e-5
+    # 3xTF32 keeps ~21 mantissa bits per product but the tensor core accumulates K/8 partial sums with
+    # truncation: allow 1e-5 of the output range (plain TF32 would be ~1e-3, fp32 FFMA ~1e-6)
+    assert helpers.max_abs_diff(C, ref) < 1e-5 * max(1.0, float(ref.abs().max()))
 
 
 def test_dense_tensor_core_pool_and_rowbias():
