@@ -209,14 +209,20 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    engine.set_hooks(counter, prof)
-    counter.reset(); prof.reset()
+    # timed region: after two sightings of the batch shape the module replays the whole forward (graph
+    # preparation included) as one CUDA graph on static input buffers, so warm-up >= 3 covers the capture
     ms_total = timed(step_resident, args.steps, args.warmup)
-    launches = counter.count // (args.steps + args.warmup) * args.steps
-    kstats = prof.summary()
-    engine.set_hooks(None, None)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    # instrumented pass (same steps, plain stream launches): per-kernel CUDA events + launch count.  Events cannot
+    # be placed between the nodes of a replayed graph, so the per-kernel durations come from this pass.
+    engine.set_hooks(counter, prof)
+    timed(step_resident, 1, 1)
+    counter.reset(); prof.reset()
+    ms_instr = timed(step_resident, args.steps, 0)
+    launches = counter.count
+    kstats = prof.summary()
+    engine.set_hooks(None, None)
 
     # cached-graph variant (same Batch object re-submitted): informational
     def step_cached():
@@ -245,6 +251,9 @@ def run_ours(args):
                 "e2e": {"value": meshes / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches,
+                "launch_mode": "timed steps replay one CUDA graph per step (same kernels, graph preparation included); "
+                               "gpu_launches / kernels / roofline come from an instrumented pass of the same "
+                               f"{args.steps} steps with plain stream launches ({ms_instr / args.steps:.3f} ms/step)",
                 "cached_graph": {"value": meshes / (ms_cached / 1e3), "unit": UNIT,
                                  "note": "same Batch object re-submitted: CSR cache hit, informational"},
                 "roofline": roof,

@@ -25,6 +25,11 @@ def MLP(channels: List[int], batch_norm: bool = True) -> nn.Sequential:
     return nn.Sequential(*blocks)
 
 
+# bumped whenever any module's parameters may have changed; captured CUDA graphs remember the epoch they
+# were built in and are rebuilt when it moved (they bake packed-weight pointers)
+WEIGHTS_EPOCH = [0]
+
+
 class FusedModule(nn.Module):
     """Common behaviour of the drop-in modules: lazily packed device weights that are dropped whenever
     the parameters may have changed (`load_state_dict`, `.to()`, `.train()`), a reusable workspace and
@@ -44,6 +49,7 @@ class FusedModule(nn.Module):
         self.invalidate_packed()
 
     def invalidate_packed(self):
+        WEIGHTS_EPOCH[0] += 1
         for m in self.modules():
             if isinstance(m, FusedModule):
                 m._packed = None

@@ -168,6 +168,10 @@ def set_hooks(counter: Optional[LaunchCounter], timer: Optional[KernelTimer]) ->
     _counter, _timer = counter, timer
 
 
+def hooks_active() -> bool:
+    return _counter is not None or _timer is not None
+
+
 def _begin(label: str, kernels: int, flops: float, nbytes: float):
     if _counter is not None:
         _counter.count += kernels

@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from . import _lib, engine, packing
-from .basic_modules import MLP, FusedModule, GCUMotion
+from .basic_modules import MLP, WEIGHTS_EPOCH, FusedModule, GCUMotion
 
 __all__ = ["jointnet_motion", "masknet_motion", "skinnet_motion"]
 
@@ -80,38 +80,123 @@ class GCNRig(FusedModule):
         return out.clone()
 
 
+class _GraphReplay:
+    """One captured forward for one batch shape: static input buffers, private workspace, CUDA graph."""
+
+    _FIELDS = ("pos", "tpl_edge_index", "geo_edge_index", "batch", "skin_input")
+
+    def __init__(self, model, data, input_flow, num_graphs):
+        import types
+        self.epoch = WEIGHTS_EPOCH[0]
+        self.static = types.SimpleNamespace(num_graphs=num_graphs)
+        for f in self._FIELDS:
+            v = getattr(data, f, None)
+            if torch.is_tensor(v):
+                setattr(self.static, f, v.detach().clone().contiguous())
+        self.flow = input_flow.detach().clone().contiguous()
+        self.ws = engine.Workspace()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():
+            # warm-up on the capture stream: allocates the workspace, packs weights, sets kernel attributes
+            model._forward_impl(self.static, self.flow, self.ws, engine.GraphCache(), engine.BatchCache())
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        self.caches = (engine.GraphCache(), engine.BatchCache())      # fresh: graph prep is captured too
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.outs = model._forward_impl(self.static, self.flow, self.ws, *self.caches)
+
+    def run(self, data, input_flow):
+        for f in self._FIELDS:
+            dst = getattr(self.static, f, None)
+            if dst is not None:
+                src = getattr(data, f)
+                if src.dtype != dst.dtype or not src.is_cuda:
+                    raise TypeError(f"morig_b200: data.{f} must be a CUDA tensor of dtype {dst.dtype}")
+                dst.copy_(src, non_blocking=True)
+        if input_flow.dtype != self.flow.dtype or not input_flow.is_cuda:
+            raise TypeError("morig_b200: input_flow must be a CUDA float32 tensor")
+        self.flow.copy_(input_flow, non_blocking=True)
+        self.graph.replay()
+        return tuple(o.clone() for o in self.outs)
+
+
 class _MotionNet(FusedModule):
     """Shared body of JointNetMotion / MaskNetMotion / SkinMotion: key-frame motion encoder, temporal
     aggregation, then a task head (models/rignet.py:82-100, 115-133, 194-205)."""
 
     num_keyframes: int
 
-    def _inputs(self, data, input_flow):
+    # Launch-bound regime (73 small launches per forward): once a batch shape has been seen twice, the whole
+    # forward (graph preparation included) is captured into a CUDA graph and replayed on static input buffers.
+    use_cuda_graph = True
+    _GRAPH_SLOTS = 4
+
+    def _shape_key(self, data, input_flow):
+        ng = getattr(data, "num_graphs", None)
+        if ng is None:
+            ng = self._batches.get(data.batch, data).n_graphs          # one 8-byte read of batch[-1]
+        skin = getattr(data, "skin_input", None)
+        return (tuple(data.pos.shape), tuple(data.tpl_edge_index.shape), tuple(data.geo_edge_index.shape),
+                tuple(input_flow.shape), tuple(skin.shape) if skin is not None and self._needs_skin else None,
+                int(ng), str(data.pos.device))
+
+    _needs_skin = False
+
+    def invalidate_packed(self):
+        super().invalidate_packed()
+        self.__dict__.get("_replays", {}).clear()
+        self.__dict__.get("_seen", {}).clear()
+
+    def forward(self, data, input_flow):
+        if not (self.use_cuda_graph and not engine.hooks_active() and not self.training
+                and torch.is_tensor(data.pos) and data.pos.is_cuda):
+            return self._forward_impl(data, input_flow, self._ws, self._graphs, self._batches)
+        replays = self.__dict__.setdefault("_replays", {})
+        seen = self.__dict__.setdefault("_seen", {})
+        key = self._shape_key(data, input_flow)
+        ent = replays.get(key)
+        if ent is not None and ent.epoch != WEIGHTS_EPOCH[0]:
+            replays.pop(key)
+            ent = None
+        if ent is None:
+            seen[key] = seen.get(key, 0) + 1
+            if seen[key] < 2:                        # first sight of this shape: plain launches
+                return self._forward_impl(data, input_flow, self._ws, self._graphs, self._batches)
+            ent = _GraphReplay(self, data, input_flow, key[5])
+            while len(replays) >= self._GRAPH_SLOTS:
+                replays.pop(next(iter(replays)))
+            replays[key] = ent
+        return ent.run(data, input_flow)
+
+    def _inputs(self, data, input_flow, graphs, batches):
         self._guard(data.pos, input_flow, data.tpl_edge_index, data.geo_edge_index, data.batch)
         pos = _lib.require_cuda(data.pos, "data.pos")
         flow = _lib.require_cuda(input_flow, "input_flow")
         n = pos.shape[0]
         if flow.shape[0] != n or flow.shape[1] < 3 * self.num_keyframes:
             raise ValueError(f"input_flow must be [N, >= {3 * self.num_keyframes}], got {tuple(flow.shape)}")
-        gt = self._graphs.get(data.tpl_edge_index, n)
-        gg = self._graphs.get(data.geo_edge_index, n)
-        binfo = self._batches.get(data.batch, data)
+        gt = graphs.get(data.tpl_edge_index, n)
+        gg = graphs.get(data.geo_edge_index, n)
+        binfo = batches.get(data.batch, data)
         return pos, flow, n, gt, gg, binfo
 
-    def _encode(self, pos, flow, n, gt, gg, binfo, dim):
+    def _encode(self, ws, pos, flow, n, gt, gg, binfo, dim):
         """motionNet on all key-frames at once + per-row normalize + stack -> motion_all [N, T, dim]"""
         T = self.num_keyframes
-        m = self.motionNet.run(self._ws, "motion", pos, flow, flow.shape[1], 3, gt, gg, binfo, T)   # [T*N, dim]
+        m = self.motionNet.run(ws, "motion", pos, flow, flow.shape[1], 3, gt, gg, binfo, T)   # [T*N, dim]
         motion_all = torch.empty(n, T, dim, device=pos.device, dtype=torch.float32)
         engine.row_normalize(m, dim, T * n, dim, dst2=motion_all, n=n, n_frames=T)
         return motion_all
 
-    def _aggregate(self, motion_all, aggr_method, out_dim):
+    def _aggregate(self, ws, motion_all, aggr_method, out_dim):
         n, T, c = motion_all.shape
         if aggr_method == "attn":
             aggr = torch.empty(n, out_dim, device=motion_all.device, dtype=torch.float32)
             pk = self.aggragator._packed_for("attn", self.aggragator.pack)
-            engine.run_temporal_attn(self._ws, "aggr", pk, motion_all, aggr)
+            engine.run_temporal_attn(ws, "aggr", pk, motion_all, aggr)
         elif aggr_method in ("mean", "max"):
             aggr = torch.empty(n, c, device=motion_all.device, dtype=torch.float32)
             engine.frame_reduce(motion_all, aggr_method, aggr)
@@ -137,12 +222,12 @@ class _JointMaskBase(_MotionNet):
             head = GCNRig(chn_feature=32, chn_output=chn_output, aggr=aggr)
         setattr(self, self._head_name, head)
 
-    def forward(self, data, input_flow):
-        pos, flow, n, gt, gg, binfo = self._inputs(data, input_flow)
-        motion_all = self._encode(pos, flow, n, gt, gg, binfo, 32)
-        motion_aggr = self._aggregate(motion_all, self.aggr_method, 64)
+    def _forward_impl(self, data, input_flow, ws, graphs, batches):
+        pos, flow, n, gt, gg, binfo = self._inputs(data, input_flow, graphs, batches)
+        motion_all = self._encode(ws, pos, flow, n, gt, gg, binfo, 32)
+        motion_aggr = self._aggregate(ws, motion_all, self.aggr_method, 64)
         head = getattr(self, self._head_name)
-        pred = head.run(self._ws, "head", pos, motion_aggr, motion_aggr.shape[1], 0, gt, gg, binfo, 1)
+        pred = head.run(ws, "head", pos, motion_aggr, motion_aggr.shape[1], 0, gt, gg, binfo, 1)
         return motion_all, motion_aggr, pred.clone()
 
 
@@ -208,11 +293,13 @@ class SkinMotion(_MotionNet):
                                        output_size=motion_dim)
         self.skinNet = SkinNet_inner(nearest_bone, use_Dg, use_Lf, motion_dim, use_motion, aggr)
 
-    def forward(self, data, input_flow):
-        pos, flow, n, gt, gg, binfo = self._inputs(data, input_flow)
-        motion_all = self._encode(pos, flow, n, gt, gg, binfo, self.motion_dim)
-        motion_aggr = self._aggregate(motion_all, "attn", self.motion_dim)
-        pred = self.skinNet.run(self._ws, "skin", data, pos, motion_aggr, gt, gg, binfo)
+    _needs_skin = True
+
+    def _forward_impl(self, data, input_flow, ws, graphs, batches):
+        pos, flow, n, gt, gg, binfo = self._inputs(data, input_flow, graphs, batches)
+        motion_all = self._encode(ws, pos, flow, n, gt, gg, binfo, self.motion_dim)
+        motion_aggr = self._aggregate(ws, motion_all, "attn", self.motion_dim)
+        pred = self.skinNet.run(ws, "skin", data, pos, motion_aggr, gt, gg, binfo)
         return motion_all, motion_aggr, pred.clone()
 
 

@@ -232,6 +232,32 @@ def test_full_size_properties():
             assert torch.equal(x, y)
 
 
+@pytest.mark.parametrize("arch", ["jointnet_motion", "skinnet_motion"])
+def test_cuda_graph_replay_equals_plain_launches(arch):
+    """third call with the same batch shape replays a captured CUDA graph on static buffers: results must be
+    bit-identical to plain launches for NEW data of that shape, and follow load_state_dict"""
+    kw = synth.ARCH_KWARGS[arch]
+    skin = arch == "skinnet_motion"
+    model = helpers.build_model(arch, kw, 5, DEV)
+    batches = [synth.make_batch(2, 256, seed=s, with_skin=skin).to(DEV) for s in (1, 2, 3, 4)]
+    with torch.no_grad():
+        model.use_cuda_graph = False
+        plain = [[t.clone() for t in model(b, b.pred_flow)] for b in batches]
+        model.use_cuda_graph = True
+        for b, want in zip(batches, plain):                    # calls 1-2 plain, 3-4 replayed
+            got = model(b, b.pred_flow)
+            for x, y in zip(got, want):
+                assert torch.equal(x, y)
+        assert len(model._replays) == 1
+        model.load_state_dict(synth.seeded_state_dict(model, 6))
+        new = model(batches[0], batches[0].pred_flow)           # stale graph must not be replayed
+        assert not torch.equal(new[2], plain[0][2])
+        model.use_cuda_graph = False
+        ref = model(batches[0], batches[0].pred_flow)
+        for x, y in zip(new, ref):
+            assert torch.equal(x, y)
+
+
 def test_rejects_cpu_tensors_and_train_mode():
     kw = synth.ARCH_KWARGS["jointnet_motion"]
     model = helpers.build_model("jointnet_motion", kw, 5, DEV)
