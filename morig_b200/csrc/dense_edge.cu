@@ -83,6 +83,9 @@ static int launch_tc(const GemmP &p, const float *blob, int frames, cudaStream_t
     tp.ntn = ceil_div(p.N, BN);
     tp.ntm = ceil_div(p.M, tc::BM);
     tp.frames = frames;
+    using C = tc::Cfg<BN>;
+    tp.resident_b = (tp.ntn == 1 && C::res_stages(tp.nK) >= 2) ? 1 : 0;
+    tp.stages = tp.resident_b ? C::res_stages(tp.nK) : C::STAGES;
     const long long tiles = (long long)tp.ntn * tp.ntm * frames;
     const int sms = sm_count();
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);     // persistent: one CTA per SM

@@ -26,10 +26,12 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int KC = 32;                       // fp32 k-columns per stage = one 128-byte swizzle row
 constexpr int A_HALF_BYTES = BM * 128;       // 16 KB: hi (then lo) image of the A stage
-constexpr int PRODUCER_WARPS = 4;
+constexpr int PRODUCER_WARPS = 8;
 constexpr int EPILOGUE_WARPS = 4;
+constexpr int CONTROL_WARP = PRODUCER_WARPS + EPILOGUE_WARPS;
 constexpr int THREADS = 32 * (PRODUCER_WARPS + EPILOGUE_WARPS + 1);
-constexpr int ROWS_PER_THREAD = BM / (PRODUCER_WARPS * 4);       // 8 rows, one 16-byte chunk each
+constexpr int ROWS_PER_THREAD = BM / (PRODUCER_WARPS * 4);       // 4 rows, one 16-byte chunk each
+constexpr int ROW_STEP = PRODUCER_WARPS * 4;                     // rows handled by one warp-wide instruction group
 
 template <int BN> struct Cfg {
     static constexpr int B_HALF_BYTES = BN * 128;
@@ -41,6 +43,16 @@ template <int BN> struct Cfg {
     static constexpr int AUX_BYTES = 512;                                    // barriers + tmem pointer
     static constexpr int SMEM_BYTES = PIPE_BYTES + STG_BYTES + AUX_BYTES + 1024;   // + slack for 1024B alignment
     static constexpr int TMEM_COLS = 2 * BN;                                 // two accumulator buffers
+    static constexpr int A_STAGE_BYTES = 2 * A_HALF_BYTES;
+    static constexpr int B_CHUNK_BYTES = 2 * B_HALF_BYTES;
+    static constexpr int PIPE_BUDGET = PIPE_BYTES;                           // 192 KB for every BN
+    // resident-B mode (all k-chunks of the weight image stay in shared memory for the whole kernel):
+    // possible when the CTA only ever sees one n-tile and the image leaves room for >= 2 A stages
+    static constexpr int res_stages(int nK) {
+        const int left = PIPE_BUDGET - nK * B_CHUNK_BYTES;
+        const int s = left / A_STAGE_BYTES;
+        return s > 4 ? 4 : s;
+    }
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -144,6 +156,8 @@ struct TcP {
     const float *Bblob;      // [n_tiles][nK][hi|lo][BN*32] pre-swizzled weight images
     int nK;                  // k-chunks of 32
     int ntn, ntm, frames;    // tile grid (ntm is an upper bound in gather mode)
+    int stages;              // A (and, when streaming, B) ring depth
+    int resident_b;          // 1: the whole weight image is loaded once and kept in shared memory
 };
 
 struct TileCoord { int n_tile, m0, frame; };
@@ -156,6 +170,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;          // swizzle atoms need 1024 B alignment
     uint8_t *smem = smem_raw + (base - raw_addr);
+    const int nK = tp.nK;
+    const int S = tp.stages;
+    const bool resb = tp.resident_b != 0;
+    // stage s: A image at a_off(s); B image of the stage (streaming) or of k-chunk kc (resident) at b_off(.)
+    const uint32_t a_stride = resb ? (uint32_t)C::A_STAGE_BYTES : (uint32_t)C::STAGE_BYTES;
+    const uint32_t b_region = resb ? (uint32_t)(S * C::A_STAGE_BYTES) : (uint32_t)C::A_STAGE_BYTES;
+    const uint32_t b_stride = resb ? (uint32_t)C::B_CHUNK_BYTES : (uint32_t)C::STAGE_BYTES;
     float *stg_all = reinterpret_cast<float *>(smem + C::PIPE_BYTES);
     uint8_t *aux = smem + C::PIPE_BYTES + C::STG_BYTES;
     const uint32_t aux_addr = base + C::PIPE_BYTES + C::STG_BYTES;
@@ -168,7 +189,6 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(aux + 224);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nK = tp.nK;
     int M = p.M, ntm = tp.ntm;
     if (AMODE == AMODE_GATHER) {
         M = p.rowptr[p.n_vtx_frame];                 // E' lives on the device only
@@ -184,9 +204,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
         return c;
     };
 
-    if (warp == 8) {
+    if (warp == CONTROL_WARP) {
         if (lane == 0) {
-            for (int s = 0; s < C::STAGES; ++s) {
+            for (int s = 0; s < 4; ++s) {
                 mbar_init(bar_a(s), PRODUCER_WARPS);
                 mbar_init(bar_b(s), 1);
                 mbar_init(bar_m(s), 1);
@@ -205,37 +225,53 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == CONTROL_WARP) {
         // ================= control warp: B bulk copies + MMA issue (one elected lane) =================
         if (lane == 0) {
             const uint32_t idesc = make_idesc<BN>();
             const uint32_t b_bytes = 2u * C::B_HALF_BYTES;
             const uint8_t *gB = reinterpret_cast<const uint8_t *>(tp.Bblob);
             const int my_tiles = (total_tiles > (int)blockIdx.x) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-            const long long my_chunks = (long long)my_tiles * nK;
-            auto issue_b = [&](long long it) {                     // it = CTA-local running chunk index
-                const int li = (int)(it / nK), kc = (int)(it % nK);
-                const TileCoord tc_ = decode((int)blockIdx.x + li * (int)gridDim.x);
-                const int s = (int)(it % C::STAGES);
-                const uint32_t dst = base + s * C::STAGE_BYTES + 2 * A_HALF_BYTES;
-                mbar_arrive_expect_tx(bar_b(s), b_bytes);
-                bulk_g2s(dst, gB + ((size_t)tc_.n_tile * nK + kc) * b_bytes, b_bytes, bar_b(s));
+            // All ring positions are tracked incrementally (no div/mod on this latency-critical thread).
+            // fetch cursor: next (tile, k-chunk) whose weight image has to be requested, and its stage
+            int f_li = 0, f_kc = 0, f_s = 0, f_ntile = (my_tiles > 0) ? decode((int)blockIdx.x).n_tile : 0;
+            auto fetch_next = [&]() {                              // streaming mode only
+                const uint32_t dst = base + b_region + f_s * b_stride;
+                mbar_arrive_expect_tx(bar_b(f_s), b_bytes);
+                bulk_g2s(dst, gB + ((size_t)f_ntile * nK + f_kc) * b_bytes, b_bytes, bar_b(f_s));
+                if (++f_s == S) f_s = 0;
+                if (++f_kc == nK) {
+                    f_kc = 0;
+                    ++f_li;
+                    if (f_li < my_tiles) f_ntile = decode((int)blockIdx.x + f_li * (int)gridDim.x).n_tile;
+                }
             };
-            for (long long it = 0; it < C::STAGES - 1 && it < my_chunks; ++it) issue_b(it);
-            long long it = 0;
+            if (resb) {
+                // one n-tile for the whole kernel: fetch every k-chunk of the image once
+                if (my_tiles > 0) {
+                    mbar_arrive_expect_tx(bar_b(0), b_bytes * (uint32_t)nK);
+                    for (int kc = 0; kc < nK; ++kc)
+                        bulk_g2s(base + b_region + kc * b_stride, gB + ((size_t)f_ntile * nK + kc) * b_bytes, b_bytes,
+                                 bar_b(0));
+                    mbar_wait(bar_b(0), 0);
+                }
+            } else {
+                for (int i = 0; i < S - 1 && f_li < my_tiles; ++i) fetch_next();
+            }
+            int s = 0, prev_s = 0;
+            uint32_t ph = 0, prev_ph = 0;
+            bool first = true;
             for (int li = 0; li < my_tiles; ++li) {
                 const int buf = li & 1;
                 mbar_wait(bar_acce(buf), ((li >> 1) & 1) ^ 1);     // accumulator buffer drained by the epilogue
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-                for (int kc = 0; kc < nK; ++kc, ++it) {
-                    const int s = (int)(it % C::STAGES);
-                    const uint32_t ph = (uint32_t)((it / C::STAGES) & 1);
+                for (int kc = 0; kc < nK; ++kc) {
                     mbar_wait(bar_a(s), ph);
-                    mbar_wait(bar_b(s), ph);
+                    if (!resb) mbar_wait(bar_b(s), ph);
                     tc_fence_after();
-                    const uint32_t a_hi = base + s * C::STAGE_BYTES, a_lo = a_hi + A_HALF_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * A_HALF_BYTES, b_lo = b_hi + C::B_HALF_BYTES;
+                    const uint32_t a_hi = base + s * a_stride, a_lo = a_hi + A_HALF_BYTES;
+                    const uint32_t b_hi = base + b_region + (resb ? kc : s) * b_stride, b_lo = b_hi + C::B_HALF_BYTES;
 #pragma unroll
                     for (int k = 0; k < KC / 8; ++k) {
                         const uint32_t ko = k * 32;              // 8 tf32 = 32 bytes along the swizzled row
@@ -246,11 +282,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
                         umma_tf32(tmem_d, dah, dbh, idesc, 1);
                     }
                     umma_commit(bar_m(s));                       // frees stage s when these MMAs retire
-                    const long long nxt = it + C::STAGES - 1;
-                    if (nxt < my_chunks) {
-                        if (it >= 1) mbar_wait(bar_m((int)((it - 1) % C::STAGES)), (uint32_t)(((it - 1) / C::STAGES) & 1));
-                        issue_b(nxt);
+                    if (!resb && f_li < my_tiles) {
+                        // the stage to refill was last read by the PREVIOUS chunk's MMAs
+                        if (!first) mbar_wait(bar_m(prev_s), prev_ph);
+                        fetch_next();
                     }
+                    first = false;
+                    prev_s = s; prev_ph = ph;
+                    if (++s == S) { s = 0; ph ^= 1; }
                 }
                 umma_commit(bar_accf(buf));                      // accumulator complete -> epilogue
             }
@@ -258,86 +297,110 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
         __syncwarp();
     } else if (warp < PRODUCER_WARPS) {
         // ================= producer warps: A stage images =================
-        const int c = tid & 7;                       // 16-byte chunk of the 128-byte row
-        const int row0 = tid >> 3;                   // rows row0 + 16*ps
-        long long it = 0;
-        float4 cur[ROWS_PER_THREAD], nxt[ROWS_PER_THREAD];
+        // Thread -> 16-byte chunk c of rows row0 + ROW_STEP*ps.  One warp instruction covers 4 consecutive CSR slots,
+        // which mostly share P[tgt] (one coalesced line).  Raw operands of the NEXT chunk are in flight in registers
+        // while the current chunk is combined, split and stored: the relu(P+Q) combine is deferred to the store
+        // step so that issuing the loads never blocks.
+        const int c = tid & 7;
+        const int row0 = tid >> 3;
+        int s = 0;                                   // ring position, tracked incrementally
+        uint32_t wait_ph = 1;                        // parity of "stage s is free" (passes on a fresh barrier)
+        float4 pa[ROWS_PER_THREAD], qa[ROWS_PER_THREAD], pb[ROWS_PER_THREAD], qb[ROWS_PER_THREAD];
         const float *src0[ROWS_PER_THREAD];
         const float *src1[ROWS_PER_THREAD];
+        int ni[ROWS_PER_THREAD], nj[ROWS_PER_THREAD];    // gather indices of the NEXT tile, fetched a tile ahead
         uint32_t okmask = 0;
 
-        auto setup_rows = [&](const TileCoord &t) {
+        auto fetch_indices = [&](const TileCoord &t) {
+#pragma unroll
+            for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
+                const int r = t.m0 + row0 + ROW_STEP * ps;
+                ni[ps] = 0; nj[ps] = 0;
+                if (AMODE == AMODE_GATHER && r < M) { ni[ps] = p.tgt[r]; nj[ps] = p.col[r]; }
+            }
+        };
+        auto setup_rows = [&](const TileCoord &t) {      // consumes ni/nj of this tile
             okmask = 0;
 #pragma unroll
             for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
-                const int r = t.m0 + row0 + 16 * ps;
+                const int r = t.m0 + row0 + ROW_STEP * ps;
                 const bool ok = r < M;
                 okmask |= (ok ? 1u : 0u) << ps;
                 if (AMODE == AMODE_GATHER) {
-                    int i = 0, j = 0;
-                    if (ok) { i = p.tgt[r]; j = p.col[r]; }
                     const size_t fb = (size_t)t.frame * p.n_vtx_frame;
-                    src0[ps] = p.P + (fb + i) * (size_t)p.ldpq + 4 * c;
-                    src1[ps] = p.Q + (fb + j) * (size_t)p.ldpq + 4 * c;
+                    src0[ps] = p.P + (fb + ni[ps]) * (size_t)p.ldpq + 4 * c;
+                    src1[ps] = p.Q + (fb + nj[ps]) * (size_t)p.ldpq + 4 * c;
                 } else {
                     src0[ps] = p.A + (size_t)(ok ? r : 0) * p.lda + 4 * c;
                     src1[ps] = nullptr;
                 }
             }
         };
-        auto load_chunk = [&](int kc, float4 (&dst)[ROWS_PER_THREAD]) {
+        auto load_raw = [&](int kc, float4 (&pd)[ROWS_PER_THREAD], float4 (&qd)[ROWS_PER_THREAD]) {
             const int k = kc * KC + 4 * c;
 #pragma unroll
             for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                pd[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
+                qd[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (((okmask >> ps) & 1u) && k < p.K) {
-                    v = *reinterpret_cast<const float4 *>(src0[ps] + kc * KC);
-                    if (AMODE == AMODE_GATHER) {
-                        const float4 q = *reinterpret_cast<const float4 *>(src1[ps] + kc * KC);
-                        v.x = fmaxf(v.x + q.x, 0.f); v.y = fmaxf(v.y + q.y, 0.f);
-                        v.z = fmaxf(v.z + q.z, 0.f); v.w = fmaxf(v.w + q.w, 0.f);
-                    }
+                    pd[ps] = *reinterpret_cast<const float4 *>(src0[ps] + kc * KC);
+                    if (AMODE == AMODE_GATHER) qd[ps] = *reinterpret_cast<const float4 *>(src1[ps] + kc * KC);
                 }
-                dst[ps] = v;
             }
         };
-
-        int t = blockIdx.x;
-        if (t < total_tiles) {
-            setup_rows(decode(t));
-            load_chunk(0, cur);
-        }
-        for (; t < total_tiles; t += gridDim.x) {
-            for (int kc = 0; kc < nK; ++kc, ++it) {
-                const bool last = kc + 1 == nK;
-                const int tn = t + gridDim.x;
-                if (!last) {
-                    load_chunk(kc + 1, nxt);
-                } else if (tn < total_tiles) {       // cross the tile boundary: next tile's rows and first chunk
-                    setup_rows(decode(tn));
-                    load_chunk(0, nxt);
-                }
-                const int s = (int)(it % C::STAGES);
-                if (it >= C::STAGES) mbar_wait(bar_m(s), (uint32_t)(((it / C::STAGES) - 1) & 1));
-                uint8_t *a_hi = smem + s * C::STAGE_BYTES;
-                uint8_t *a_lo = a_hi + A_HALF_BYTES;
+        auto store_stage = [&](const float4 (&pd)[ROWS_PER_THREAD], const float4 (&qd)[ROWS_PER_THREAD]) {
+            mbar_wait(bar_m(s), wait_ph);            // MMAs that read this stage one ring turn ago have retired
+            uint8_t *a_hi = smem + s * a_stride;
+            uint8_t *a_lo = a_hi + A_HALF_BYTES;
 #pragma unroll
-                for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
-                    const int row = row0 + 16 * ps;
-                    const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
-                    const float4 v = cur[ps];
-                    float4 h, l;
-                    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-                    *reinterpret_cast<float4 *>(a_hi + off) = h;
-                    *reinterpret_cast<float4 *>(a_lo + off) = l;
+            for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
+                const int row = row0 + ROW_STEP * ps;
+                const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
+                float4 v = pd[ps];
+                if (AMODE == AMODE_GATHER) {
+                    v.x = fmaxf(v.x + qd[ps].x, 0.f); v.y = fmaxf(v.y + qd[ps].y, 0.f);
+                    v.z = fmaxf(v.z + qd[ps].z, 0.f); v.w = fmaxf(v.w + qd[ps].w, 0.f);
                 }
-                fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_a(s));
-#pragma unroll
-                for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) cur[ps] = nxt[ps];
+                float4 h, l;
+                h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+                l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+                *reinterpret_cast<float4 *>(a_hi + off) = h;
+                *reinterpret_cast<float4 *>(a_lo + off) = l;
             }
+            fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a(s));
+            if (++s == S) { s = 0; wait_ph ^= 1; }
+        };
+
+        int t = blockIdx.x, kc = 0;
+        bool in_a = true;                            // which register set holds the current chunk
+        if (t < total_tiles) {
+            const TileCoord t0 = decode(t);
+            fetch_indices(t0);
+            setup_rows(t0);
+            load_raw(0, pa, qa);
+            if (t + (int)gridDim.x < total_tiles) fetch_indices(decode(t + gridDim.x));
+        }
+        while (t < total_tiles) {
+            // coordinates of the next chunk of this CTA's stream
+            int kc_n = kc + 1, t_n = t;
+            if (kc_n == nK) { kc_n = 0; t_n = t + gridDim.x; }
+            const bool has_next = t_n < total_tiles;
+            if (has_next && kc_n == 0) {
+                setup_rows(decode(t_n));             // indices were fetched one tile ago
+                if (t_n + (int)gridDim.x < total_tiles) fetch_indices(decode(t_n + gridDim.x));
+            }
+            if (in_a) {
+                if (has_next) load_raw(kc_n, pb, qb);
+                store_stage(pa, qa);
+            } else {
+                if (has_next) load_raw(kc_n, pa, qa);
+                store_stage(pb, qb);
+            }
+            in_a = !in_a;
+            kc = kc_n;
+            t = t_n;
         }
     } else {
         // ================= epilogue warps =================
@@ -471,7 +534,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (warp == CONTROL_WARP) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 }  // namespace tc
