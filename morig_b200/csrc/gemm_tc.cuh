@@ -40,7 +40,7 @@ template <int BN> struct Cfg {
     static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
     static constexpr int STG_LD = 33;                                        // staging tile row stride (floats)
     static constexpr int STG_BYTES = EPILOGUE_WARPS * 32 * STG_LD * 4;       // 16.5 KB
-    static constexpr int AUX_BYTES = 512;                                    // barriers + tmem pointer
+    static constexpr int AUX_BYTES = 1024;                                   // barriers, tmem pointer, row keys
     static constexpr int SMEM_BYTES = PIPE_BYTES + STG_BYTES + AUX_BYTES + 1024;   // + slack for 1024B alignment
     static constexpr int TMEM_COLS = 2 * BN;                                 // two accumulator buffers
     static constexpr int A_STAGE_BYTES = 2 * A_HALF_BYTES;
@@ -404,125 +404,104 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
         }
     } else {
         // ================= epilogue warps =================
-        const int q = warp & 3;                      // TMEM lane quarter of this warp (warp 4..7 -> 0..3)
+        // tcgen05.ld hands every lane one accumulator ROW (32 consecutive columns).  Each 32x32 block is transposed
+        // through a 4 KB per-warp staging tile so that lanes become COLUMNS: the per-column epilogue constants then
+        // live in registers, the 32 rows of the column are processed from registers with compile-time indices, a
+        // running max is restarted at segment heads and flushed at segment tails (CSR target for the EdgeConv,
+        // graph id for pooling), and every global access is a coalesced 128-byte row segment.
+        const int q = warp & 3;                      // TMEM lane quarter of this warp (warps 8..11 -> 0..3)
         float *stg = stg_all + q * 32 * C::STG_LD;
+        int32_t *s_key = reinterpret_cast<int32_t *>(aux + 256) + q * 32;
         int li = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
             const TileCoord tcd = decode(t);
             const int buf = li & 1;
             const int n0 = tcd.n_tile * BN;
-            const int row = q * 32 + lane;
-            const int r = tcd.m0 + row;
+            const int rbase = tcd.m0 + q * 32;       // first row (CSR slot) of this warp
+            const int r = rbase + lane;
             const bool row_ok = r < M;
-            // per-row bookkeeping that does not depend on the accumulator: do it before waiting
-            int g = 0;
-            int tg = -1, d = 0;
-            bool is_tail = false, complete = false;
-            uint32_t tail_mask = 0;
-            if (EPI == EPI_STORE) {
-                if (p.batch && row_ok) g = (r / p.n_vtx) * p.n_graphs + p.batch[r % p.n_vtx];
-            } else {
-                tg = row_ok ? p.tgt[r] : -1;
-                const int up = __shfl_up_sync(0xffffffffu, tg, 1);
-                const int dn = __shfl_down_sync(0xffffffffu, tg, 1);
-                const bool is_head = (lane == 0) || (tg != up);
-                is_tail = (tg >= 0) && ((lane == 31) || (tg != dn));
-                const uint32_t head_mask = __ballot_sync(0xffffffffu, is_head);
-                tail_mask = __ballot_sync(0xffffffffu, is_tail);
-                const int my_head = 31 - __clz(head_mask & (0xffffffffu >> (31 - lane)));
-                d = lane - my_head;
-                if (is_tail) {
-                    const int e0w = tcd.m0 + q * 32;
-                    complete = p.rowptr[tg] >= e0w && p.rowptr[tg + 1] <= e0w + 32;
-                }
+            const int valid_rows = min(32, max(0, M - rbase));
+            // segment key of this lane's row (rows are sorted by it); independent of the accumulator
+            int key = -1;
+            if (row_ok) {
+                if (EPI == EPI_SEGMAX) key = p.tgt[r];
+                else key = p.batch ? (r / p.n_vtx) * p.n_graphs + p.batch[r % p.n_vtx] : 0;
             }
+            const int key_up = __shfl_up_sync(0xffffffffu, key, 1);
+            const int key_dn = __shfl_down_sync(0xffffffffu, key, 1);
+            const bool is_head = (lane == 0) || (key != key_up);
+            const bool is_tail = (key >= 0) && ((lane == 31) || (key != key_dn));
+            const uint32_t head_mask = __ballot_sync(0xffffffffu, is_head);
+            const uint32_t tail_mask = __ballot_sync(0xffffffffu, is_tail);
+            bool complete = false;                   // segment entirely inside this warp's 32 rows -> plain store
+            if (EPI == EPI_SEGMAX && is_tail) complete = p.rowptr[key] >= rbase && p.rowptr[key + 1] <= rbase + 32;
+            const uint32_t complete_mask = __ballot_sync(0xffffffffu, complete);
+            const size_t frame_base = (EPI == EPI_SEGMAX) ? (size_t)tcd.frame * p.n_vtx_frame : 0;
+            const bool one_group = (tail_mask & (tail_mask - 1)) == 0;      // at most one segment in these rows
+            const int key0 = __shfl_sync(0xffffffffu, key, 0);
+            __syncwarp();
+            s_key[lane] = key;
+            __syncwarp();
+
             mbar_wait(bar_accf(buf), (uint32_t)((li >> 1) & 1));
             tc_fence_after();
 #pragma unroll 1
             for (int cb = 0; cb < BN / 32; ++cb) {
                 const int col0 = cb * 32;
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + col0), v);
-                const int nl = n0 + col0 + lane;     // this lane's column when lanes index columns
+                float xr[32];
+                {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + col0), v);
+                    __syncwarp();                    // previous block's reads of the staging tile are done
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) stg[lane * C::STG_LD + j] = v[j];
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr) xr[rr] = stg[rr * C::STG_LD + lane];   // lane = column from here on
+                const int nl = n0 + col0 + lane;
                 const bool nl_ok = nl < p.N;
-                const float bias_l = (nl_ok && p.bias) ? p.bias[nl] : 0.f;
+                float bias_l = (nl_ok && p.bias) ? p.bias[nl] : 0.f;
                 const float scale_l = (nl_ok && p.scale) ? p.scale[nl] : 1.f;
                 const float shift_l = (nl_ok && p.shift) ? p.shift[nl] : 0.f;
+                const bool relu = (EPI == EPI_SEGMAX) || p.relu;
+                const bool rowbias_slow = (EPI == EPI_STORE) && p.rowbias && !one_group;
+                if (EPI == EPI_STORE && p.rowbias && one_group && nl_ok && key0 >= 0)
+                    bias_l += p.rowbias[(size_t)key0 * p.ldrb + nl];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = v[j] + __shfl_sync(0xffffffffu, bias_l, j);
-                    if (EPI == EPI_STORE && p.rowbias && row_ok && n0 + col0 + j < p.N)
-                        x += p.rowbias[(size_t)g * p.ldrb + n0 + col0 + j];
-                    if (EPI == EPI_SEGMAX || p.relu) x = fmaxf(x, 0.f);
-                    v[j] = fmaf(x, __shfl_sync(0xffffffffu, scale_l, j), __shfl_sync(0xffffffffu, shift_l, j));
+                for (int rr = 0; rr < 32; ++rr) {
+                    float x = xr[rr] + bias_l;
+                    if (rowbias_slow) {              // rows of several graphs in one warp: rare
+                        const int g = s_key[rr];
+                        if (g >= 0 && nl_ok) x += p.rowbias[(size_t)g * p.ldrb + nl];
+                    }
+                    if (relu) x = fmaxf(x, 0.f);
+                    xr[rr] = fmaf(x, scale_l, shift_l);              // BatchNorm affine BEFORE any max (scale may be < 0)
                 }
-                if (EPI == EPI_SEGMAX) {
-                    // inclusive segmented max scan over the rows (lanes) of this warp
+                if (EPI == EPI_STORE && p.C && nl_ok) {
+                    float *dst = p.C + (size_t)rbase * p.ldc + nl;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float x = v[j];
-#pragma unroll
-                        for (int off = 1; off < 32; off <<= 1) {
-                            const float o = __shfl_up_sync(0xffffffffu, x, off);
-                            if (d >= off) x = fmaxf(x, o);
-                        }
-                        v[j] = x;
+                    for (int rr = 0; rr < 32; ++rr) {
+                        if (rr < valid_rows) *dst = xr[rr];
+                        dst += p.ldc;
                     }
-                    // tails -> staging rows (by tail rank); then lanes become columns for coalesced row stores
-                    __syncwarp();
-                    if (is_tail) {
-                        const int rank = __popc(tail_mask & ((1u << lane) - 1u));
+                }
+                if (EPI == EPI_SEGMAX || p.pool) {
+                    float m = neg_inf();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) stg[rank * C::STG_LD + j] = v[j];
-                    }
-                    __syncwarp();
-                    uint32_t mleft = tail_mask;
-                    int rank = 0;
-                    while (mleft) {
-                        const int tl = __ffs(mleft) - 1;
-                        mleft &= mleft - 1;
-                        const int t_row = __shfl_sync(0xffffffffu, tg, tl);
-                        const bool t_complete = __shfl_sync(0xffffffffu, (int)complete, tl) != 0;
-                        const float x = stg[rank * C::STG_LD + lane];
-                        ++rank;
-                        if (nl_ok) {
-                            float *dst = p.C + ((size_t)tcd.frame * p.n_vtx_frame + t_row) * (size_t)p.ldc + nl;
-                            if (t_complete) *dst = x;
-                            else atomic_max_f32(dst, x);
-                        }
-                    }
-                } else {
-                    if (p.C) {
-                        // transpose through the per-warp staging tile: lanes become columns, so every row is
-                        // written as one coalesced 128-byte segment whatever the destination row stride
-                        __syncwarp();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) stg[lane * C::STG_LD + j] = v[j];
-                        __syncwarp();
-                        const int rows_here = min(32, M - (tcd.m0 + q * 32));
-                        float *dst = p.C + (size_t)(tcd.m0 + q * 32) * p.ldc + nl;
-                        if (nl_ok) {
-#pragma unroll 4
-                            for (int rr = 0; rr < rows_here; ++rr) dst[(size_t)rr * p.ldc] = stg[rr * C::STG_LD + lane];
-                        }
-                    }
-                    if (p.pool) {
-                        const int g0 = __shfl_sync(0xffffffffu, g, 0);
-                        const bool uniform = __all_sync(0xffffffffu, row_ok && g == g0);
-                        if (uniform) {
-                            float mine = neg_inf();
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                float m = v[j];
-#pragma unroll
-                                for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-                                if (lane == j) mine = m;
+                    for (int rr = 0; rr < 32; ++rr) {
+                        m = ((head_mask >> rr) & 1u) ? xr[rr] : fmaxf(m, xr[rr]);
+                        if ((tail_mask >> rr) & 1u) {                   // warp-uniform
+                            const int k_rr = s_key[rr];
+                            if (nl_ok) {
+                                if (EPI == EPI_SEGMAX) {
+                                    float *dst = p.C + (frame_base + k_rr) * (size_t)p.ldc + nl;
+                                    if ((complete_mask >> rr) & 1u) *dst = m;
+                                    else atomic_max_f32(dst, m);
+                                } else {
+                                    atomic_max_f32(p.pool + (size_t)k_rr * p.ldpool + nl, m);
+                                }
                             }
-                            if (nl_ok) atomic_max_f32(p.pool + (size_t)g0 * p.ldpool + nl, mine);
-                        } else if (row_ok) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (n0 + col0 + j < p.N) atomic_max_f32(p.pool + (size_t)g * p.ldpool + n0 + col0 + j, v[j]);
                         }
                     }
                 }
