@@ -65,10 +65,65 @@ static int launch_gemm(const GemmP &p, dim3 grid, cudaStream_t stream, const cha
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+static long long *g_trace = nullptr;      // debug timeline buffer (device), set by morig_debug_set_trace
+
+static bool env_flag(const char *name) {
+    const char *e = getenv(name);
+    return e && e[0] == '1';
+}
+
+// cta_group::2 variant (UMMA 256 x 256 on a 2-CTA cluster): halves the weight traffic per SM
+template <int AMODE, int EPI>
+static int launch_tc2(const GemmP &p, const float *blob, int frames, cudaStream_t stream, const char *name) {
+    auto kern = tc::tc2_gemm_kernel<AMODE, EPI>;
+    constexpr int smem = tc::SMEM_BYTES;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    MORIG_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        MORIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured_dev = dev;
+    }
+    tc::TcP tp;
+    tp.g = p;
+    tp.Bblob = blob;
+    tp.nK = ceil_div(p.K, tc::KC);
+    tp.ntn = ceil_div(p.N, tc::BN2);
+    tp.ntm = ceil_div(p.M, tc::BM);
+    tp.frames = frames;
+    tp.stages = tc::STAGES2;
+    tp.resident_b = 0;
+    tp.dbg = 0;
+    tp.trace = nullptr;
+    const long long pairs = (long long)tp.ntn * ceil_div(tp.ntm, 2) * frames;
+    const int clusters_max = sm_count() / 2;
+    const unsigned grid = 2u * (unsigned)(pairs < clusters_max ? pairs : clusters_max);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(tc::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MORIG_CUDA(cudaLaunchKernelEx(&cfg, kern, tp));
+    MORIG_LAUNCH_CHECK(name);
+    return 0;
+}
+
 template <int BN, int AMODE, int EPI>
 static int launch_tc(const GemmP &p, const float *blob, int frames, cudaStream_t stream, const char *name) {
+    if (BN == 256 && !env_flag("MORIG_NO_2CTA")) {
+        // enough pair-tiles to give every 2-CTA cluster of the machine at least one
+        const long long pairs = (long long)ceil_div(p.N, BN) * ceil_div(ceil_div(p.M, tc::BM), 2) * frames;
+        if (pairs >= sm_count() / 2) return launch_tc2<AMODE, EPI>(p, blob, frames, stream, name);
+    }
     auto kern = tc::tc_gemm_kernel<BN, AMODE, EPI>;
-    constexpr int smem = tc::Cfg<BN>::SMEM_BYTES;
+    constexpr int smem = tc::SMEM_BYTES;
     static thread_local int configured_dev = -1;
     int dev = 0;
     MORIG_CUDA(cudaGetDevice(&dev));
@@ -86,6 +141,8 @@ static int launch_tc(const GemmP &p, const float *blob, int frames, cudaStream_t
     using C = tc::Cfg<BN>;
     tp.resident_b = (tp.ntn == 1 && C::res_stages(tp.nK) >= 2) ? 1 : 0;
     tp.stages = tp.resident_b ? C::res_stages(tp.nK) : C::STAGES;
+    { const char *e = getenv("MORIG_TC_DBG"); tp.dbg = e ? atoi(e) : 0; }
+    tp.trace = g_trace;
     const long long tiles = (long long)tp.ntn * tp.ntm * frames;
     const int sms = sm_count();
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);     // persistent: one CTA per SM
@@ -106,6 +163,9 @@ static bool tc_disabled() {
 }  // namespace morig
 
 using namespace morig;
+
+// debug only (not declared in the public header): device buffer of 3 * 2048 * 2 int64 receiving the role timeline
+extern "C" MORIG_API void morig_debug_set_trace(long long *buf) { g_trace = buf; }
 
 extern "C" MORIG_API int morig_dense_fwd(const morig_dense_desc *d, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

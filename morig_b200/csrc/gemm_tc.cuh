@@ -1,22 +1,31 @@
 // tcgen05 tile engine (sm_100a): persistent, warp-specialised 3xTF32 GEMM with fp32 accumulation in TMEM.
 //
-//   D[128 x BN] (+)= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi        (kind::tf32, cta_group::1, M=128, N=BN, K=8)
+//   D[128 x BN] (+)= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi        (tcgen05.mma kind::tf32, K = 8 per instruction)
 //
 // fp32 inputs are split x = hi + lo with hi = rna_tf32(x); dropping lo*lo leaves fp32-class results (the 1e-4
 // absolute tolerance of the path rules out plain TF32/BF16).
 //
-// One CTA per SM walks tiles t = blockIdx.x, +gridDim.x, ... ; three roles run decoupled through mbarriers:
-//   warps 0-3  A producers: 32 k-columns per stage written straight into 128B-swizzled K-major shared memory;
-//              plain activation rows, or relu(P[tgt[e]] + Q[col[e]]) gathered per CSR slot (fused EdgeConv)
-//   warp  8    one elected lane: cp.async.bulk of the pre-split / pre-swizzled weight image of each
-//              (n-tile, k-chunk) (TMA engine, mbarrier complete_tx) and the 12 tcgen05.mma per stage;
-//              tcgen05.commit releases stages and publishes accumulators
-//   warps 4-7  epilogue: tcgen05.ld of one of the TWO accumulator buffers (so the next tile's MMAs overlap),
-//              bias (+ per-graph bias) -> ReLU -> BatchNorm affine, then
-//                 store rows / per-graph column max (warp shuffles + ordered atomics) /
-//                 segmented max over the CSR target: in-register segmented scan across the 32 rows of the warp,
-//                 segment tails transposed through a 4 KB per-warp staging tile for coalesced row stores;
-//                 segments crossing a warp's 32 rows merge with ordered-int atomic max (exact, deterministic)
+// One CTA per SM walks tiles; three roles run decoupled through mbarriers:
+//   warps 0-7   A producers: 32 k-columns per stage written straight into 128B-swizzled K-major shared memory;
+//               plain activation rows, or relu(P[tgt[e]] + Q[col[e]]) gathered per CSR slot (fused EdgeConv);
+//               the raw operands of the next chunk are in flight in registers while the current one is stored
+//   warp  12    one elected lane: cp.async.bulk of the pre-split / pre-swizzled weight image of each
+//               (n-tile, k-chunk) (TMA engine, mbarrier complete_tx) and the 12 tcgen05.mma per stage;
+//               tcgen05.commit releases stages and publishes accumulators
+//   warps 8-11  epilogue: tcgen05.ld of one of the TWO accumulator buffers (the next tile's MMAs overlap), 32x32
+//               blocks transposed through a 4 KB per-warp staging tile so that lanes become columns, then
+//               bias (+ per-graph bias) -> ReLU -> BatchNorm affine and
+//                 coalesced row stores / per-graph column max / segmented max over the CSR target
+//               (running max restarted at segment heads, flushed at tails; segments crossing a warp's 32 rows
+//                merge with ordered-int atomic max: exact and order independent, hence deterministic)
+//
+// Two kernels share the role code:
+//   tc_gemm_kernel<BN,...>   cta_group::1, UMMA 128 x BN; weight image streamed per stage or, when the CTA sees a
+//                            single n-tile and the image fits, kept resident in shared memory
+//   tc2_gemm_kernel<...>     cta_group::2 on a 2-CTA cluster, UMMA 256 x 256: each CTA produces its own 128 rows
+//                            of A and loads HALF of every weight chunk (the pair shares B through the tensor
+//                            core's cross-CTA operand path), which halves the L2 -> SM weight traffic that
+//                            bounds the streamed layers
 #pragma once
 #include "gemm_simt.cuh"
 
@@ -26,34 +35,41 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int KC = 32;                       // fp32 k-columns per stage = one 128-byte swizzle row
 constexpr int A_HALF_BYTES = BM * 128;       // 16 KB: hi (then lo) image of the A stage
-constexpr int PRODUCER_WARPS = 8;
-constexpr int EPILOGUE_WARPS = 4;
+constexpr int A_STAGE_BYTES = 2 * A_HALF_BYTES;
+constexpr int PRODUCER_WARPS = 4;
+constexpr int EPILOGUE_WARPS = 8;                                // two per TMEM lane quarter, alternating 32-column blocks
 constexpr int CONTROL_WARP = PRODUCER_WARPS + EPILOGUE_WARPS;
-constexpr int THREADS = 32 * (PRODUCER_WARPS + EPILOGUE_WARPS + 1);
-constexpr int ROWS_PER_THREAD = BM / (PRODUCER_WARPS * 4);       // 4 rows, one 16-byte chunk each
+constexpr int THREADS = 32 * (PRODUCER_WARPS + EPILOGUE_WARPS + 4);    // control warp + 3 idle warps: a full warpgroup
+// Register budget: 16 warps x 128 registers = the whole register file at launch; the roles then rebalance with
+// setmaxnreg (which works on whole warpgroups, hence the 3 idle warps next to the control warp): every scheduler
+// hosts 1 producer warp (208) + 2 epilogue warps (104) + 1 control-group warp (56) = 472 of its 512 registers/lane.
+constexpr int REGS_PRODUCER = 208, REGS_EPILOGUE = 104, REGS_CONTROL = 56;
+constexpr int ROWS_PER_THREAD = BM / (PRODUCER_WARPS * 4);       // 8 rows, one 16-byte chunk each
 constexpr int ROW_STEP = PRODUCER_WARPS * 4;                     // rows handled by one warp-wide instruction group
+constexpr int STG_LD = 33;                                       // staging tile row stride (floats)
+constexpr int STG_BYTES = EPILOGUE_WARPS * 32 * STG_LD * 4;      // 33 KB (the pad column of each tile holds the row keys)
+constexpr int AUX_BYTES = 1024;                                  // barriers, tmem pointer
+constexpr int PIPE_BYTES = 192 * 1024;                           // operand ring (every configuration)
+constexpr int SMEM_BYTES = PIPE_BYTES + STG_BYTES + AUX_BYTES + 1024;   // + slack for 1024 B alignment = 227 KB
 
 template <int BN> struct Cfg {
     static constexpr int B_HALF_BYTES = BN * 128;
-    static constexpr int STAGE_BYTES = 2 * A_HALF_BYTES + 2 * B_HALF_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
-    static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int STG_LD = 33;                                        // staging tile row stride (floats)
-    static constexpr int STG_BYTES = EPILOGUE_WARPS * 32 * STG_LD * 4;       // 16.5 KB
-    static constexpr int AUX_BYTES = 1024;                                   // barriers, tmem pointer, row keys
-    static constexpr int SMEM_BYTES = PIPE_BYTES + STG_BYTES + AUX_BYTES + 1024;   // + slack for 1024B alignment
-    static constexpr int TMEM_COLS = 2 * BN;                                 // two accumulator buffers
-    static constexpr int A_STAGE_BYTES = 2 * A_HALF_BYTES;
     static constexpr int B_CHUNK_BYTES = 2 * B_HALF_BYTES;
-    static constexpr int PIPE_BUDGET = PIPE_BYTES;                           // 192 KB for every BN
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_CHUNK_BYTES;
+    static constexpr int STAGES = PIPE_BYTES / STAGE_BYTES;                  // 2 / 3 / 4 for BN = 256 / 128 / 64
+    static constexpr int TMEM_COLS = 2 * BN;                                 // two accumulator buffers
     // resident-B mode (all k-chunks of the weight image stay in shared memory for the whole kernel):
     // possible when the CTA only ever sees one n-tile and the image leaves room for >= 2 A stages
     static constexpr int res_stages(int nK) {
-        const int left = PIPE_BUDGET - nK * B_CHUNK_BYTES;
+        const int left = PIPE_BYTES - nK * B_CHUNK_BYTES;
         const int s = left / A_STAGE_BYTES;
         return s > 4 ? 4 : s;
     }
 };
+
+// aux block layout (byte offsets): barriers are 8 bytes each
+constexpr uint32_t AUX_A_FULL = 0, AUX_B_FULL = 64, AUX_MMA_DONE = 128, AUX_ACC_FULL = 192, AUX_ACC_EMPTY = 208,
+                   AUX_TMEM_PTR = 224, AUX_B_PEER = 232, AUX_KEYS = 320;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -64,24 +80,44 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "}" ::"r"(bar), "r"(cta) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+template <bool CLUSTER>
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (CLUSTER) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
     return ok != 0;
 }
 // A pipeline bug must surface as a launch failure, never as a hung GPU: trap after ~2 s of waiting.
+template <bool CLUSTER = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
+    if (mbar_try_wait<CLUSTER>(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait<CLUSTER>(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
@@ -89,32 +125,66 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+template <int CTAS> __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    if (CTAS == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
 }
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+template <int CTAS> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    if (CTAS == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// commit: the mbarrier gets one arrival when all tcgen05.mma issued so far by this thread have retired.
+// cta_group::2 multicasts the arrival to the barrier at the same offset in both CTAs of the pair.
+template <int CTAS> __device__ __forceinline__ void umma_commit(uint32_t bar) {
+    if (CTAS == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    } else {
+        const uint16_t mask = 3;
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(bar), "h"(mask) : "memory");
+    }
 }
+template <int CTAS>
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    if (CTAS == 1) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    }
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// asynchronous TMEM -> register load of 32 lanes x 32 columns; the registers are valid after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -124,11 +194,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// the "+r" operands tie every later use of the registers to this wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                   "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
 }
 
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -146,9 +224,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return d;
 }
 
-// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=BN
-template <int BN> __device__ __forceinline__ uint32_t make_idesc() {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M x N
+__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct TcP {
@@ -158,10 +236,310 @@ struct TcP {
     int ntn, ntm, frames;    // tile grid (ntm is an upper bound in gather mode)
     int stages;              // A (and, when streaming, B) ring depth
     int resident_b;          // 1: the whole weight image is loaded once and kept in shared memory
+    long long *trace;        // debug timeline (CTA 0): [role 0..2][2048] (tag, clock64) pairs, or NULL
+    int dbg;                 // timing experiments only (MORIG_TC_DBG): 1 = one MMA per k-step, 2 = producers skip stores, 4 = no B refetch
 };
 
 struct TileCoord { int n_tile, m0, frame; };
 
+struct Tracer {
+    long long *buf; int n;
+    __device__ __forceinline__ void operator()(int tag) {
+        if (buf && n < 1024) { buf[2 * n] = tag; buf[2 * n + 1] = clock64(); ++n; }
+    }
+};
+
+// tile stream of one CTA: t = first, first + step, ... < total;  m0 = ((r % ntm) * mult + rank) * BM
+struct TileMap {
+    int ntn, ntm, total, first, step, mult, rank;
+    __device__ __forceinline__ TileCoord decode(int t) const {
+        TileCoord c;
+        c.n_tile = t % ntn;
+        const int r = t / ntn;
+        c.m0 = ((r % ntm) * mult + rank) * BM;
+        c.frame = r / ntm;
+        return c;
+    }
+    __device__ __forceinline__ int my_tiles() const { return total > first ? (total - 1 - first) / step + 1 : 0; }
+};
+
+// ================= producer warps: A stage images =================
+// Thread -> 16-byte chunk c of rows row0 + ROW_STEP*ps.  One warp instruction covers 4 consecutive CSR slots, which
+// mostly share P[tgt] (one coalesced line).  The relu(P+Q) combine is deferred to the store step so that issuing
+// the loads of the next chunk never blocks.  `arrive(s)` publishes stage s to the MMA issuer.
+template <int AMODE, class Arrive>
+__device__ __forceinline__ void producer_role(const GemmP &p, uint8_t *smem, uint32_t a_stride, uint32_t aux_addr, int S,
+                                              int nK, int M, const TileMap &tm, int tid, int lane, Arrive arrive,
+                                              int dbg = 0, long long *trace = nullptr) {
+    Tracer tr{(trace && blockIdx.x == 0 && tid == 0) ? trace : nullptr, 0};
+    const int c = tid & 7;
+    const int row0 = tid >> 3;
+    int s = 0;                                   // ring position, tracked incrementally
+    uint32_t wait_ph = 1;                        // parity of "stage s is free" (passes on a fresh barrier)
+    // register ring of raw operands: DEPTH chunks, DEPTH-1 of them in flight ahead of the one being stored.
+    // Memory latency (DRAM for activations, L2 for gathered rows) is ~1 us, a chunk's MMAs take ~0.8 us: one chunk
+    // of look-ahead leaves the tensor pipe waiting, so plain rows keep 3 chunks in flight and gathers 2.
+    constexpr int DEPTH = (AMODE == AMODE_GATHER) ? 2 : 4;
+    float4 pbuf[DEPTH][ROWS_PER_THREAD];
+    float4 qbuf[(AMODE == AMODE_GATHER) ? DEPTH : 1][ROWS_PER_THREAD];
+    const float *src0[ROWS_PER_THREAD];
+    const float *src1[ROWS_PER_THREAD];
+    int ni[ROWS_PER_THREAD], nj[ROWS_PER_THREAD];    // gather indices of the NEXT tile, fetched a tile ahead
+    uint32_t okmask = 0;
+
+    auto fetch_indices = [&](const TileCoord &t) {
+#pragma unroll
+        for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
+            const int r = t.m0 + row0 + ROW_STEP * ps;
+            ni[ps] = 0; nj[ps] = 0;
+            if (AMODE == AMODE_GATHER && r < M) { ni[ps] = p.tgt[r]; nj[ps] = p.col[r]; }
+        }
+    };
+    auto setup_rows = [&](const TileCoord &t) {      // consumes ni/nj of this tile
+        okmask = 0;
+#pragma unroll
+        for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
+            const int r = t.m0 + row0 + ROW_STEP * ps;
+            const bool ok = r < M;
+            okmask |= (ok ? 1u : 0u) << ps;
+            if (AMODE == AMODE_GATHER) {
+                const size_t fb = (size_t)t.frame * p.n_vtx_frame;
+                src0[ps] = p.P + (fb + ni[ps]) * (size_t)p.ldpq + 4 * c;
+                src1[ps] = p.Q + (fb + nj[ps]) * (size_t)p.ldpq + 4 * c;
+            } else {
+                src0[ps] = p.A + (size_t)(ok ? r : 0) * p.lda + 4 * c;
+                src1[ps] = nullptr;
+            }
+        }
+    };
+    auto load_raw = [&](int kc, float4 (&pd)[ROWS_PER_THREAD], float4 (&qd)[ROWS_PER_THREAD]) {
+        const int k = kc * KC + 4 * c;
+#pragma unroll
+        for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
+            pd[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (AMODE == AMODE_GATHER) qd[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (((okmask >> ps) & 1u) && k < p.K) {
+                pd[ps] = *reinterpret_cast<const float4 *>(src0[ps] + kc * KC);
+                if (AMODE == AMODE_GATHER) qd[ps] = *reinterpret_cast<const float4 *>(src1[ps] + kc * KC);
+            }
+        }
+    };
+    auto store_stage = [&](const float4 (&pd)[ROWS_PER_THREAD], const float4 (&qd)[ROWS_PER_THREAD]) {
+        tr(1);
+        mbar_wait(aux_addr + AUX_MMA_DONE + 8u * s, wait_ph);    // MMAs that read this stage one ring turn ago retired
+        tr(2);
+        uint8_t *a_hi = smem + s * a_stride;
+        uint8_t *a_lo = a_hi + A_HALF_BYTES;
+#pragma unroll
+        for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
+            const int row = row0 + ROW_STEP * ps;
+            const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
+            float4 v = pd[ps];
+            if (AMODE == AMODE_GATHER) {
+                v.x = fmaxf(v.x + qd[ps].x, 0.f); v.y = fmaxf(v.y + qd[ps].y, 0.f);
+                v.z = fmaxf(v.z + qd[ps].z, 0.f); v.w = fmaxf(v.w + qd[ps].w, 0.f);
+            }
+            // hi = x with the 13 low mantissa bits cleared (an exact TF32 value), lo = x - hi (exact in fp32; the
+            // tensor core reads its top 10 mantissa bits).  |lo| < 2^-10 |x|, so hi*hi + hi*lo + lo*hi is x*y to ~2^-20.
+            float4 h, l;
+            h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+            if (!(dbg & 2)) {
+                *reinterpret_cast<float4 *>(a_hi + off) = h;
+                *reinterpret_cast<float4 *>(a_lo + off) = l;
+            } else if (h.x == 12345.f && l.y == 54321.f) {
+                *reinterpret_cast<float4 *>(a_hi + off) = h;
+            }
+        }
+        fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) arrive(s);
+        tr(3);
+        if (++s == S) { s = 0; wait_ph ^= 1; }
+    };
+
+    // prefetch cursor (pt, pkc): next chunk of this CTA's stream whose loads have not been issued yet
+    int pt = tm.first, pkc = 0;
+    const int my_tiles = tm.my_tiles();
+    long long remaining = (long long)my_tiles * nK;      // chunks still to be stored
+    auto prefetch_into = [&](float4 (&pd)[ROWS_PER_THREAD], float4 (&qd)[ROWS_PER_THREAD]) {
+        if (pt >= tm.total) return;
+        if (pkc == 0) {
+            if (pt == tm.first) fetch_indices(tm.decode(pt));
+            setup_rows(tm.decode(pt));           // its indices were fetched one tile ago
+            if (pt + tm.step < tm.total) fetch_indices(tm.decode(pt + tm.step));
+        }
+        load_raw(pkc, pd, qd);
+        if (++pkc == nK) { pkc = 0; pt += tm.step; }
+    };
+#pragma unroll
+    for (int u = 0; u < DEPTH - 1; ++u) prefetch_into(pbuf[u], qbuf[(AMODE == AMODE_GATHER) ? u : 0]);
+    while (remaining > 0) {
+#pragma unroll
+        for (int u = 0; u < DEPTH; ++u) {
+            if (remaining > 0) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int w = (u + DEPTH - 1) % DEPTH;       // ring slot that becomes free for the next prefetch
+                prefetch_into(pbuf[w], qbuf[(AMODE == AMODE_GATHER) ? w : 0]);
+                store_stage(pbuf[u], qbuf[(AMODE == AMODE_GATHER) ? u : 0]);
+                --remaining;
+            }
+        }
+    }
+}
+
+// ================= epilogue warps =================
+// tcgen05.ld hands every lane one accumulator ROW (32 consecutive columns).  Each 32x32 block is transposed through a
+// 4 KB per-warp staging tile so that lanes become COLUMNS: the per-column constants then live in registers, the 32
+// rows of the column are processed from registers with compile-time indices, a running max is restarted at segment
+// heads and flushed at segment tails, and every global access is a coalesced 128-byte row segment.
+// `release(buf)` hands the accumulator buffer back to the MMA issuer.
+template <int BN, int EPI, class Release>
+__device__ __forceinline__ void epilogue_role(const GemmP &p, float *stg_all, uint8_t *aux, uint32_t aux_addr,
+                                              uint32_t tmem_base, int M, const TileMap &tm, int warp, int lane,
+                                              Release release, long long *trace = nullptr) {
+    constexpr int NB = BN / 32;                  // 32-column blocks per tile
+    constexpr int MYB = (NB + 1) / 2;            // blocks handled by this warp: cb = half, half + 2, ...
+    const int e = warp - PRODUCER_WARPS;         // epilogue warp 0..7
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read (hardware: warp id % 4)
+    const int half = e >> 2;
+    Tracer tr{(trace && blockIdx.x == 0 && e == 0 && lane == 0) ? trace + 2 * 2048 : nullptr, 0};
+    float *stg = stg_all + e * 32 * STG_LD;      // private 32 x 33 staging tile; column 32 of row r holds key[r]
+    (void)aux;
+
+    // Everything that does not depend on the accumulator is fetched ahead so that no global-memory latency sits
+    // between two tiles: the segment key of this lane's row two tiles ahead, the tail/complete flags one tile ahead.
+    auto load_key = [&](int t) -> int {
+        if (t >= tm.total) return -1;
+        const TileCoord c = tm.decode(t);
+        const int r = c.m0 + q * 32 + lane;
+        if (r >= M) return -1;
+        if (EPI == EPI_SEGMAX) return p.tgt[r];
+        return p.batch ? (r / p.n_vtx) * p.n_graphs + p.batch[r % p.n_vtx] : 0;
+    };
+    struct Flags { uint32_t tail_mask, complete_mask; };
+    auto make_flags = [&](int t, int key) -> Flags {
+        Flags f;
+        const int key_dn = __shfl_down_sync(0xffffffffu, key, 1);
+        const bool is_tail = (key >= 0) && ((lane == 31) || (key != key_dn));
+        f.tail_mask = __ballot_sync(0xffffffffu, is_tail);
+        bool complete = false;                   // segment entirely inside this warp's 32 rows -> plain store
+        if (EPI == EPI_SEGMAX && is_tail) {
+            const int rbase = tm.decode(t).m0 + q * 32;
+            complete = p.rowptr[key] >= rbase && p.rowptr[key + 1] <= rbase + 32;
+        }
+        f.complete_mask = __ballot_sync(0xffffffffu, complete);
+        return f;
+    };
+
+    int key_cur = load_key(tm.first);
+    int key_nxt = load_key(tm.first + tm.step);
+    Flags fl_cur = make_flags(tm.first, key_cur);
+    int cached_ntile = -1;
+    float bias_r[MYB], scale_r[MYB], shift_r[MYB];   // per-column constants of this lane's column in each of my blocks
+
+    int li = 0;
+    for (int t = tm.first; t < tm.total; t += tm.step, ++li) {
+        const TileCoord tcd = tm.decode(t);
+        const int buf = li & 1;
+        const int n0 = tcd.n_tile * BN;
+        const int rbase = tcd.m0 + q * 32;       // first row (CSR slot) of this warp
+        const int valid_rows = min(32, max(0, M - rbase));
+        const int key = key_cur;
+        const Flags fl = fl_cur;
+        // look-ahead: key two tiles ahead (load), flags one tile ahead (needs its key, loaded a tile ago)
+        const int key_nn = load_key(t + 2 * tm.step);
+        if (t + tm.step < tm.total) fl_cur = make_flags(t + tm.step, key_nxt);
+        key_cur = key_nxt;
+        key_nxt = key_nn;
+
+        const size_t frame_base = (EPI == EPI_SEGMAX) ? (size_t)tcd.frame * p.n_vtx_frame : 0;
+        __syncwarp();
+        stg[lane * STG_LD + 32] = __int_as_float(key);
+        if (tcd.n_tile != cached_ntile) {
+            cached_ntile = tcd.n_tile;
+#pragma unroll
+            for (int i = 0; i < MYB; ++i) {
+                const int nl = n0 + (half + 2 * i) * 32 + lane;
+                const bool ok = (half + 2 * i < NB) && nl < p.N;
+                bias_r[i] = (ok && p.bias) ? p.bias[nl] : 0.f;
+                scale_r[i] = (ok && p.scale) ? p.scale[nl] : 1.f;
+                shift_r[i] = (ok && p.shift) ? p.shift[nl] : 0.f;
+            }
+        }
+        const bool relu = (EPI == EPI_SEGMAX) || p.relu;
+
+        tr(10);
+        mbar_wait(aux_addr + AUX_ACC_FULL + 8u * buf, (uint32_t)((li >> 1) & 1));
+        tr(11);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+        uint32_t v[32];
+        if (half < NB) tmem_ld32_issue(tbase + (uint32_t)(half * 32), v);
+#pragma unroll
+        for (int i = 0; i < MYB; ++i) {
+            const int cb = half + 2 * i;
+            if (cb < NB) {                       // warp-uniform (only BN = 32 * odd would skip; kept for safety)
+                const int col0 = cb * 32;
+                tmem_ld_wait(v);
+                tr(13);
+                __syncwarp();                    // previous block's reads of the staging tile are done
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stg[lane * STG_LD + j] = __uint_as_float(v[j]);
+                __syncwarp();
+                tr(14);
+                if (cb + 2 < NB) tmem_ld32_issue(tbase + (uint32_t)(col0 + 64), v);   // overlaps this block's walk
+                // lane = column from here on: walk the rows of this column segment by segment (few segments per
+                // warp: one per CSR target / graph), reading the transposed block back from the staging tile
+                const int nl = n0 + col0 + lane;
+                const bool nl_ok = nl < p.N;
+                const float bias_l = bias_r[i], scale_l = scale_r[i], shift_l = shift_r[i];
+                float *crow = (EPI == EPI_STORE && p.C) ? p.C + (size_t)rbase * p.ldc + nl : nullptr;
+                uint32_t tails = fl.tail_mask;
+                int rr = 0;
+                while (rr < valid_rows) {
+                    const int seg_end = tails ? (__ffs(tails) - 1) : (valid_rows - 1);
+                    const int k_seg = __float_as_int(stg[seg_end * STG_LD + 32]);
+                    float b_seg = bias_l;
+                    if (EPI == EPI_STORE && p.rowbias && nl_ok && k_seg >= 0) b_seg += p.rowbias[(size_t)k_seg * p.ldrb + nl];
+                    float m = neg_inf();
+#pragma unroll 8
+                    for (; rr <= seg_end; ++rr) {
+                        float x = stg[rr * STG_LD + lane] + b_seg;
+                        if (relu) x = fmaxf(x, 0.f);
+                        const float z = fmaf(x, scale_l, shift_l);  // BatchNorm affine BEFORE any max (scale may be < 0)
+                        if (EPI == EPI_STORE && crow) {
+                            if (nl_ok) *crow = z;
+                            crow += p.ldc;
+                        }
+                        m = fmaxf(m, z);
+                    }
+                    if (nl_ok && tails) {
+                        if (EPI == EPI_SEGMAX) {
+                            float *dst = p.C + (frame_base + k_seg) * (size_t)p.ldc + nl;
+                            if ((fl.complete_mask >> seg_end) & 1u) *dst = m;
+                            else atomic_max_f32(dst, m);
+                        } else if (p.pool) {
+                            atomic_max_f32(p.pool + (size_t)k_seg * p.ldpool + nl, m);
+                        }
+                    }
+                    tails &= tails - 1;
+                }
+                tr(16);
+            }
+        }
+        tr(17);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) release(buf);             // buffer may be overwritten by tile li + 2
+        tr(12);
+    }
+}
+
+// =============================================================================================================
+// cta_group::1 kernel: UMMA 128 x BN
+// =============================================================================================================
 template <int BN, int AMODE, int EPI>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
     using C = Cfg<BN>;
@@ -173,20 +551,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
     const int nK = tp.nK;
     const int S = tp.stages;
     const bool resb = tp.resident_b != 0;
-    // stage s: A image at a_off(s); B image of the stage (streaming) or of k-chunk kc (resident) at b_off(.)
-    const uint32_t a_stride = resb ? (uint32_t)C::A_STAGE_BYTES : (uint32_t)C::STAGE_BYTES;
-    const uint32_t b_region = resb ? (uint32_t)(S * C::A_STAGE_BYTES) : (uint32_t)C::A_STAGE_BYTES;
+    // stage s: A image at s * a_stride; B image of the stage (streaming) or of k-chunk kc (resident)
+    const uint32_t a_stride = resb ? (uint32_t)A_STAGE_BYTES : (uint32_t)C::STAGE_BYTES;
+    const uint32_t b_region = resb ? (uint32_t)(S * A_STAGE_BYTES) : (uint32_t)A_STAGE_BYTES;
     const uint32_t b_stride = resb ? (uint32_t)C::B_CHUNK_BYTES : (uint32_t)C::STAGE_BYTES;
-    float *stg_all = reinterpret_cast<float *>(smem + C::PIPE_BYTES);
-    uint8_t *aux = smem + C::PIPE_BYTES + C::STG_BYTES;
-    const uint32_t aux_addr = base + C::PIPE_BYTES + C::STG_BYTES;
-    // aux: a_full[S] @0, b_full[S] @64, mma_done[S] @128, acc_full[2] @192, acc_empty[2] @208, tmem ptr @224
-    auto bar_a = [&](int s) { return aux_addr + 8u * s; };
-    auto bar_b = [&](int s) { return aux_addr + 64u + 8u * s; };
-    auto bar_m = [&](int s) { return aux_addr + 128u + 8u * s; };
-    auto bar_accf = [&](int b) { return aux_addr + 192u + 8u * b; };
-    auto bar_acce = [&](int b) { return aux_addr + 208u + 8u * b; };
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(aux + 224);
+    float *stg_all = reinterpret_cast<float *>(smem + PIPE_BYTES);
+    uint8_t *aux = smem + PIPE_BYTES + STG_BYTES;
+    const uint32_t aux_addr = base + PIPE_BYTES + STG_BYTES;
+    auto bar_a = [&](int s) { return aux_addr + AUX_A_FULL + 8u * s; };
+    auto bar_b = [&](int s) { return aux_addr + AUX_B_FULL + 8u * s; };
+    auto bar_m = [&](int s) { return aux_addr + AUX_MMA_DONE + 8u * s; };
+    auto bar_accf = [&](int b) { return aux_addr + AUX_ACC_FULL + 8u * b; };
+    auto bar_acce = [&](int b) { return aux_addr + AUX_ACC_EMPTY + 8u * b; };
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(aux + AUX_TMEM_PTR);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int M = p.M, ntm = tp.ntm;
@@ -194,15 +571,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
         M = p.rowptr[p.n_vtx_frame];                 // E' lives on the device only
         ntm = (M + BM - 1) / BM;
     }
-    const int total_tiles = tp.ntn * ntm * tp.frames;
-    auto decode = [&](int t) {
-        TileCoord c;
-        c.n_tile = t % tp.ntn;
-        const int r = t / tp.ntn;
-        c.m0 = (r % ntm) * BM;
-        c.frame = r / ntm;
-        return c;
-    };
+    TileMap tm;
+    tm.ntn = tp.ntn; tm.ntm = ntm; tm.total = tp.ntn * ntm * tp.frames;
+    tm.first = blockIdx.x; tm.step = gridDim.x; tm.mult = 1; tm.rank = 0;
 
     if (warp == CONTROL_WARP) {
         if (lane == 0) {
@@ -213,28 +584,30 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
             }
             for (int b = 0; b < 2; ++b) {
                 mbar_init(bar_accf(b), 1);
-                mbar_init(bar_acce(b), EPILOGUE_WARPS);
+                mbar_init(bar_acce(b), EPILOGUE_WARPS);      // every epilogue warp releases the buffer
             }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(aux_addr + 224u, C::TMEM_COLS);
+        tmem_alloc<1>(aux_addr + AUX_TMEM_PTR, C::TMEM_COLS);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == CONTROL_WARP) {
+    if (warp >= CONTROL_WARP) {
         // ================= control warp: B bulk copies + MMA issue (one elected lane) =================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc<BN>();
-            const uint32_t b_bytes = 2u * C::B_HALF_BYTES;
+        reg_dec<REGS_CONTROL>();
+        if (warp == CONTROL_WARP && lane == 0) {
+            Tracer tr{(tp.trace && blockIdx.x == 0) ? tp.trace + 2048 : nullptr, 0};
+            const uint32_t idesc = make_idesc(BM, BN);
+            const uint32_t b_bytes = (uint32_t)C::B_CHUNK_BYTES;
             const uint8_t *gB = reinterpret_cast<const uint8_t *>(tp.Bblob);
-            const int my_tiles = (total_tiles > (int)blockIdx.x) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+            const int my_tiles = tm.my_tiles();
             // All ring positions are tracked incrementally (no div/mod on this latency-critical thread).
             // fetch cursor: next (tile, k-chunk) whose weight image has to be requested, and its stage
-            int f_li = 0, f_kc = 0, f_s = 0, f_ntile = (my_tiles > 0) ? decode((int)blockIdx.x).n_tile : 0;
+            int f_li = 0, f_kc = 0, f_s = 0, f_ntile = (my_tiles > 0) ? tm.decode(tm.first).n_tile : 0;
             auto fetch_next = [&]() {                              // streaming mode only
                 const uint32_t dst = base + b_region + f_s * b_stride;
                 mbar_arrive_expect_tx(bar_b(f_s), b_bytes);
@@ -243,7 +616,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
                 if (++f_kc == nK) {
                     f_kc = 0;
                     ++f_li;
-                    if (f_li < my_tiles) f_ntile = decode((int)blockIdx.x + f_li * (int)gridDim.x).n_tile;
+                    if (f_li < my_tiles) f_ntile = tm.decode(tm.first + f_li * tm.step).n_tile;
                 }
             };
             if (resb) {
@@ -263,12 +636,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
             bool first = true;
             for (int li = 0; li < my_tiles; ++li) {
                 const int buf = li & 1;
+                tr(20);
                 mbar_wait(bar_acce(buf), ((li >> 1) & 1) ^ 1);     // accumulator buffer drained by the epilogue
+                tr(21);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
                 for (int kc = 0; kc < nK; ++kc) {
                     mbar_wait(bar_a(s), ph);
+                    tr(22);
                     if (!resb) mbar_wait(bar_b(s), ph);
+                    tr(23);
                     tc_fence_after();
                     const uint32_t a_hi = base + s * a_stride, a_lo = a_hi + A_HALF_BYTES;
                     const uint32_t b_hi = base + b_region + (resb ? kc : s) * b_stride, b_lo = b_hi + C::B_HALF_BYTES;
@@ -277,243 +654,194 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
                         const uint32_t ko = k * 32;              // 8 tf32 = 32 bytes along the swizzled row
                         const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
                         const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
-                        umma_tf32(tmem_d, dal, dbh, idesc, (kc | k) != 0);
-                        umma_tf32(tmem_d, dah, dbl, idesc, 1);
-                        umma_tf32(tmem_d, dah, dbh, idesc, 1);
+                        if (!(tp.dbg & 1)) {
+                            umma_tf32<1>(tmem_d, dal, dbh, idesc, (kc | k) != 0);
+                            umma_tf32<1>(tmem_d, dah, dbl, idesc, 1);
+                            umma_tf32<1>(tmem_d, dah, dbh, idesc, 1);
+                        } else {
+                            umma_tf32<1>(tmem_d, dah, dbh, idesc, (kc | k) != 0);
+                        }
                     }
-                    umma_commit(bar_m(s));                       // frees stage s when these MMAs retire
+                    umma_commit<1>(bar_m(s));                    // frees stage s when these MMAs retire
+                    tr(24);
                     if (!resb && f_li < my_tiles) {
                         // the stage to refill was last read by the PREVIOUS chunk's MMAs
                         if (!first) mbar_wait(bar_m(prev_s), prev_ph);
+                        tr(25);
+                        if ((tp.dbg & 4) && !first) {      // timing experiment: pretend the chunk landed
+                            mbar_arrive(bar_b(f_s));
+                            if (++f_s == S) f_s = 0;
+                            if (++f_kc == nK) { f_kc = 0; ++f_li; }
+                        } else {
+                            fetch_next();
+                        }
+                    }
+                    first = false;
+                    prev_s = s; prev_ph = ph;
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+                umma_commit<1>(bar_accf(buf));                   // accumulator complete -> epilogue
+            }
+        }
+        __syncwarp();
+    } else if (warp < PRODUCER_WARPS) {
+        reg_inc<REGS_PRODUCER>();
+        producer_role<AMODE>(p, smem, a_stride, aux_addr, S, nK, M, tm, tid, lane,
+                             [&](int s) { mbar_arrive(bar_a(s)); }, tp.dbg, tp.trace);
+    } else {
+        reg_dec<REGS_EPILOGUE>();
+        epilogue_role<BN, EPI>(p, stg_all, aux, aux_addr, tmem_base, M, tm, warp, lane,
+                               [&](int b) { mbar_arrive(bar_acce(b)); }, tp.trace);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == CONTROL_WARP) tmem_dealloc<1>(tmem_base, C::TMEM_COLS);
+}
+
+// =============================================================================================================
+// cta_group::2 kernel: 2-CTA cluster, UMMA 256 x 256.  CTA rank r of the pair owns rows (2*mp + r)*128.. of the
+// pair-tile and rows [r*128, r*128+128) of every weight chunk.  Only the leader (rank 0) issues MMAs; its barriers
+// collect the arrivals of both CTAs, and tcgen05.commit multicasts completions to both.
+// =============================================================================================================
+constexpr int BN2 = 256;
+constexpr int STAGE2_BYTES = A_STAGE_BYTES + 2 * (BN2 / 2) * 128;      // 32 KB A + 32 KB half weight chunk
+constexpr int STAGES2 = PIPE_BYTES / STAGE2_BYTES;                      // 3
+
+template <int AMODE, int EPI>
+__global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
+    const GemmP &p = tp.g;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (base - raw_addr);
+    const int nK = tp.nK;
+    constexpr int S = STAGES2;
+    constexpr uint32_t HALF_B = (BN2 / 2) * 128;                        // 16 KB: this CTA's rows of the hi (or lo) image
+    float *stg_all = reinterpret_cast<float *>(smem + PIPE_BYTES);
+    uint8_t *aux = smem + PIPE_BYTES + STG_BYTES;
+    const uint32_t aux_addr = base + PIPE_BYTES + STG_BYTES;
+    auto bar_a = [&](int s) { return aux_addr + AUX_A_FULL + 8u * s; };        // leader: 16 producer warps
+    auto bar_b = [&](int s) { return aux_addr + AUX_B_FULL + 8u * s; };        // local: this CTA's half chunk landed
+    auto bar_bp = [&](int s) { return aux_addr + AUX_B_PEER + 8u * s; };       // leader: the peer's half landed
+    auto bar_m = [&](int s) { return aux_addr + AUX_MMA_DONE + 8u * s; };      // local copy of the multicast commit
+    auto bar_accf = [&](int b) { return aux_addr + AUX_ACC_FULL + 8u * b; };   // local copy of the multicast commit
+    auto bar_acce = [&](int b) { return aux_addr + AUX_ACC_EMPTY + 8u * b; };  // leader: 8 epilogue warps
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(aux + AUX_TMEM_PTR);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    int M = p.M;
+    if (AMODE == AMODE_GATHER) M = p.rowptr[p.n_vtx_frame];
+    const int ntm = (M + BM - 1) / BM;
+    TileMap tm;
+    tm.ntn = tp.ntn; tm.ntm = (ntm + 1) / 2; tm.total = tp.ntn * tm.ntm * tp.frames;
+    tm.first = blockIdx.x >> 1; tm.step = gridDim.x >> 1; tm.mult = 2; tm.rank = (int)rank;
+
+    if (warp == CONTROL_WARP) {
+        if (lane == 0) {
+            for (int s = 0; s < S; ++s) {
+                mbar_init(bar_a(s), 2 * PRODUCER_WARPS);
+                mbar_init(bar_b(s), 1);
+                mbar_init(bar_bp(s), 1);
+                mbar_init(bar_m(s), 1);
+            }
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(bar_accf(b), 1);
+                mbar_init(bar_acce(b), 2 * EPILOGUE_WARPS);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<2>(aux_addr + AUX_TMEM_PTR, 2 * BN2);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                              // both CTAs' barriers exist before any remote arrival
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= CONTROL_WARP) {
+        reg_dec<REGS_CONTROL>();
+        if (warp == CONTROL_WARP && lane == 0) {
+            const uint8_t *gB = reinterpret_cast<const uint8_t *>(tp.Bblob);
+            const uint32_t chunk_bytes = 2u * BN2 * 128;           // full hi|lo image of one k-chunk in global memory
+            const int my_tiles = tm.my_tiles();
+            int f_li = 0, f_kc = 0, f_s = 0, f_ntile = (my_tiles > 0) ? tm.decode(tm.first).n_tile : 0;
+            auto fetch_next = [&]() {                              // this CTA's 128 rows of the hi and of the lo image
+                const uint32_t dst = base + f_s * STAGE2_BYTES + A_STAGE_BYTES;
+                const uint8_t *src = gB + ((size_t)f_ntile * nK + f_kc) * chunk_bytes + rank * HALF_B;
+                mbar_arrive_expect_tx(bar_b(f_s), 2 * HALF_B);
+                bulk_g2s(dst, src, HALF_B, bar_b(f_s));
+                bulk_g2s(dst + HALF_B, src + BN2 * 128, HALF_B, bar_b(f_s));
+                if (++f_s == S) f_s = 0;
+                if (++f_kc == nK) {
+                    f_kc = 0;
+                    ++f_li;
+                    if (f_li < my_tiles) f_ntile = tm.decode(tm.first + f_li * tm.step).n_tile;
+                }
+            };
+            for (int i = 0; i < S - 1 && f_li < my_tiles; ++i) fetch_next();
+            int s = 0, prev_s = 0;
+            uint32_t ph = 0, prev_ph = 0;
+            bool first = true;
+            const uint32_t idesc = make_idesc(2 * BM, BN2);
+            for (int li = 0; li < my_tiles; ++li) {
+                const int buf = li & 1;
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN2);
+                if (rank == 0) {
+                    mbar_wait<true>(bar_acce(buf), ((li >> 1) & 1) ^ 1);   // both CTAs drained this accumulator
+                    tc_fence_after();
+                }
+                for (int kc = 0; kc < nK; ++kc) {
+                    mbar_wait(bar_b(s), ph);                               // own half chunk landed
+                    if (rank == 0) {
+                        mbar_wait<true>(bar_bp(s), ph);                    // peer's half chunk landed
+                        mbar_wait<true>(bar_a(s), ph);                     // A images of both CTAs written
+                        tc_fence_after();
+                        const uint32_t a_hi = base + s * STAGE2_BYTES, a_lo = a_hi + A_HALF_BYTES;
+                        const uint32_t b_hi = a_hi + A_STAGE_BYTES, b_lo = b_hi + HALF_B;
+#pragma unroll
+                        for (int k = 0; k < KC / 8; ++k) {
+                            const uint32_t ko = k * 32;
+                            const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
+                            const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
+                            umma_tf32<2>(tmem_d, dal, dbh, idesc, (kc | k) != 0);
+                            umma_tf32<2>(tmem_d, dah, dbl, idesc, 1);
+                            umma_tf32<2>(tmem_d, dah, dbh, idesc, 1);
+                        }
+                        umma_commit<2>(bar_m(s));                          // both CTAs: stage s free when retired
+                    } else {
+                        mbar_arrive_cluster(bar_bp(s), 0);                 // tell the leader
+                    }
+                    if (f_li < my_tiles) {
+                        if (!first) mbar_wait(bar_m(prev_s), prev_ph);     // previous chunk's MMAs retired (multicast)
                         fetch_next();
                     }
                     first = false;
                     prev_s = s; prev_ph = ph;
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
-                umma_commit(bar_accf(buf));                      // accumulator complete -> epilogue
+                if (rank == 0) umma_commit<2>(bar_accf(buf));              // both CTAs: accumulator complete
             }
         }
         __syncwarp();
     } else if (warp < PRODUCER_WARPS) {
-        // ================= producer warps: A stage images =================
-        // Thread -> 16-byte chunk c of rows row0 + ROW_STEP*ps.  One warp instruction covers 4 consecutive CSR slots,
-        // which mostly share P[tgt] (one coalesced line).  Raw operands of the NEXT chunk are in flight in registers
-        // while the current chunk is combined, split and stored: the relu(P+Q) combine is deferred to the store
-        // step so that issuing the loads never blocks.
-        const int c = tid & 7;
-        const int row0 = tid >> 3;
-        int s = 0;                                   // ring position, tracked incrementally
-        uint32_t wait_ph = 1;                        // parity of "stage s is free" (passes on a fresh barrier)
-        float4 pa[ROWS_PER_THREAD], qa[ROWS_PER_THREAD], pb[ROWS_PER_THREAD], qb[ROWS_PER_THREAD];
-        const float *src0[ROWS_PER_THREAD];
-        const float *src1[ROWS_PER_THREAD];
-        int ni[ROWS_PER_THREAD], nj[ROWS_PER_THREAD];    // gather indices of the NEXT tile, fetched a tile ahead
-        uint32_t okmask = 0;
-
-        auto fetch_indices = [&](const TileCoord &t) {
-#pragma unroll
-            for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
-                const int r = t.m0 + row0 + ROW_STEP * ps;
-                ni[ps] = 0; nj[ps] = 0;
-                if (AMODE == AMODE_GATHER && r < M) { ni[ps] = p.tgt[r]; nj[ps] = p.col[r]; }
-            }
-        };
-        auto setup_rows = [&](const TileCoord &t) {      // consumes ni/nj of this tile
-            okmask = 0;
-#pragma unroll
-            for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
-                const int r = t.m0 + row0 + ROW_STEP * ps;
-                const bool ok = r < M;
-                okmask |= (ok ? 1u : 0u) << ps;
-                if (AMODE == AMODE_GATHER) {
-                    const size_t fb = (size_t)t.frame * p.n_vtx_frame;
-                    src0[ps] = p.P + (fb + ni[ps]) * (size_t)p.ldpq + 4 * c;
-                    src1[ps] = p.Q + (fb + nj[ps]) * (size_t)p.ldpq + 4 * c;
-                } else {
-                    src0[ps] = p.A + (size_t)(ok ? r : 0) * p.lda + 4 * c;
-                    src1[ps] = nullptr;
-                }
-            }
-        };
-        auto load_raw = [&](int kc, float4 (&pd)[ROWS_PER_THREAD], float4 (&qd)[ROWS_PER_THREAD]) {
-            const int k = kc * KC + 4 * c;
-#pragma unroll
-            for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
-                pd[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
-                qd[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (((okmask >> ps) & 1u) && k < p.K) {
-                    pd[ps] = *reinterpret_cast<const float4 *>(src0[ps] + kc * KC);
-                    if (AMODE == AMODE_GATHER) qd[ps] = *reinterpret_cast<const float4 *>(src1[ps] + kc * KC);
-                }
-            }
-        };
-        auto store_stage = [&](const float4 (&pd)[ROWS_PER_THREAD], const float4 (&qd)[ROWS_PER_THREAD]) {
-            mbar_wait(bar_m(s), wait_ph);            // MMAs that read this stage one ring turn ago have retired
-            uint8_t *a_hi = smem + s * a_stride;
-            uint8_t *a_lo = a_hi + A_HALF_BYTES;
-#pragma unroll
-            for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
-                const int row = row0 + ROW_STEP * ps;
-                const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
-                float4 v = pd[ps];
-                if (AMODE == AMODE_GATHER) {
-                    v.x = fmaxf(v.x + qd[ps].x, 0.f); v.y = fmaxf(v.y + qd[ps].y, 0.f);
-                    v.z = fmaxf(v.z + qd[ps].z, 0.f); v.w = fmaxf(v.w + qd[ps].w, 0.f);
-                }
-                float4 h, l;
-                h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-                *reinterpret_cast<float4 *>(a_hi + off) = h;
-                *reinterpret_cast<float4 *>(a_lo + off) = l;
-            }
-            fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_a(s));
-            if (++s == S) { s = 0; wait_ph ^= 1; }
-        };
-
-        int t = blockIdx.x, kc = 0;
-        bool in_a = true;                            // which register set holds the current chunk
-        if (t < total_tiles) {
-            const TileCoord t0 = decode(t);
-            fetch_indices(t0);
-            setup_rows(t0);
-            load_raw(0, pa, qa);
-            if (t + (int)gridDim.x < total_tiles) fetch_indices(decode(t + gridDim.x));
-        }
-        while (t < total_tiles) {
-            // coordinates of the next chunk of this CTA's stream
-            int kc_n = kc + 1, t_n = t;
-            if (kc_n == nK) { kc_n = 0; t_n = t + gridDim.x; }
-            const bool has_next = t_n < total_tiles;
-            if (has_next && kc_n == 0) {
-                setup_rows(decode(t_n));             // indices were fetched one tile ago
-                if (t_n + (int)gridDim.x < total_tiles) fetch_indices(decode(t_n + gridDim.x));
-            }
-            if (in_a) {
-                if (has_next) load_raw(kc_n, pb, qb);
-                store_stage(pa, qa);
-            } else {
-                if (has_next) load_raw(kc_n, pa, qa);
-                store_stage(pb, qb);
-            }
-            in_a = !in_a;
-            kc = kc_n;
-            t = t_n;
-        }
+        reg_inc<REGS_PRODUCER>();
+        producer_role<AMODE>(p, smem, (uint32_t)STAGE2_BYTES, aux_addr, S, nK, M, tm, tid, lane, [&](int s) {
+            if (rank == 0) mbar_arrive(bar_a(s));
+            else mbar_arrive_cluster(bar_a(s), 0);
+        });
     } else {
-        // ================= epilogue warps =================
-        // tcgen05.ld hands every lane one accumulator ROW (32 consecutive columns).  Each 32x32 block is transposed
-        // through a 4 KB per-warp staging tile so that lanes become COLUMNS: the per-column epilogue constants then
-        // live in registers, the 32 rows of the column are processed from registers with compile-time indices, a
-        // running max is restarted at segment heads and flushed at segment tails (CSR target for the EdgeConv,
-        // graph id for pooling), and every global access is a coalesced 128-byte row segment.
-        const int q = warp & 3;                      // TMEM lane quarter of this warp (warps 8..11 -> 0..3)
-        float *stg = stg_all + q * 32 * C::STG_LD;
-        int32_t *s_key = reinterpret_cast<int32_t *>(aux + 256) + q * 32;
-        int li = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
-            const TileCoord tcd = decode(t);
-            const int buf = li & 1;
-            const int n0 = tcd.n_tile * BN;
-            const int rbase = tcd.m0 + q * 32;       // first row (CSR slot) of this warp
-            const int r = rbase + lane;
-            const bool row_ok = r < M;
-            const int valid_rows = min(32, max(0, M - rbase));
-            // segment key of this lane's row (rows are sorted by it); independent of the accumulator
-            int key = -1;
-            if (row_ok) {
-                if (EPI == EPI_SEGMAX) key = p.tgt[r];
-                else key = p.batch ? (r / p.n_vtx) * p.n_graphs + p.batch[r % p.n_vtx] : 0;
-            }
-            const int key_up = __shfl_up_sync(0xffffffffu, key, 1);
-            const int key_dn = __shfl_down_sync(0xffffffffu, key, 1);
-            const bool is_head = (lane == 0) || (key != key_up);
-            const bool is_tail = (key >= 0) && ((lane == 31) || (key != key_dn));
-            const uint32_t head_mask = __ballot_sync(0xffffffffu, is_head);
-            const uint32_t tail_mask = __ballot_sync(0xffffffffu, is_tail);
-            bool complete = false;                   // segment entirely inside this warp's 32 rows -> plain store
-            if (EPI == EPI_SEGMAX && is_tail) complete = p.rowptr[key] >= rbase && p.rowptr[key + 1] <= rbase + 32;
-            const uint32_t complete_mask = __ballot_sync(0xffffffffu, complete);
-            const size_t frame_base = (EPI == EPI_SEGMAX) ? (size_t)tcd.frame * p.n_vtx_frame : 0;
-            const bool one_group = (tail_mask & (tail_mask - 1)) == 0;      // at most one segment in these rows
-            const int key0 = __shfl_sync(0xffffffffu, key, 0);
-            __syncwarp();
-            s_key[lane] = key;
-            __syncwarp();
-
-            mbar_wait(bar_accf(buf), (uint32_t)((li >> 1) & 1));
-            tc_fence_after();
-#pragma unroll 1
-            for (int cb = 0; cb < BN / 32; ++cb) {
-                const int col0 = cb * 32;
-                float xr[32];
-                {
-                    float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + col0), v);
-                    __syncwarp();                    // previous block's reads of the staging tile are done
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) stg[lane * C::STG_LD + j] = v[j];
-                    __syncwarp();
-                }
-#pragma unroll
-                for (int rr = 0; rr < 32; ++rr) xr[rr] = stg[rr * C::STG_LD + lane];   // lane = column from here on
-                const int nl = n0 + col0 + lane;
-                const bool nl_ok = nl < p.N;
-                float bias_l = (nl_ok && p.bias) ? p.bias[nl] : 0.f;
-                const float scale_l = (nl_ok && p.scale) ? p.scale[nl] : 1.f;
-                const float shift_l = (nl_ok && p.shift) ? p.shift[nl] : 0.f;
-                const bool relu = (EPI == EPI_SEGMAX) || p.relu;
-                const bool rowbias_slow = (EPI == EPI_STORE) && p.rowbias && !one_group;
-                if (EPI == EPI_STORE && p.rowbias && one_group && nl_ok && key0 >= 0)
-                    bias_l += p.rowbias[(size_t)key0 * p.ldrb + nl];
-#pragma unroll
-                for (int rr = 0; rr < 32; ++rr) {
-                    float x = xr[rr] + bias_l;
-                    if (rowbias_slow) {              // rows of several graphs in one warp: rare
-                        const int g = s_key[rr];
-                        if (g >= 0 && nl_ok) x += p.rowbias[(size_t)g * p.ldrb + nl];
-                    }
-                    if (relu) x = fmaxf(x, 0.f);
-                    xr[rr] = fmaf(x, scale_l, shift_l);              // BatchNorm affine BEFORE any max (scale may be < 0)
-                }
-                if (EPI == EPI_STORE && p.C && nl_ok) {
-                    float *dst = p.C + (size_t)rbase * p.ldc + nl;
-#pragma unroll
-                    for (int rr = 0; rr < 32; ++rr) {
-                        if (rr < valid_rows) *dst = xr[rr];
-                        dst += p.ldc;
-                    }
-                }
-                if (EPI == EPI_SEGMAX || p.pool) {
-                    float m = neg_inf();
-#pragma unroll
-                    for (int rr = 0; rr < 32; ++rr) {
-                        m = ((head_mask >> rr) & 1u) ? xr[rr] : fmaxf(m, xr[rr]);
-                        if ((tail_mask >> rr) & 1u) {                   // warp-uniform
-                            const int k_rr = s_key[rr];
-                            if (nl_ok) {
-                                if (EPI == EPI_SEGMAX) {
-                                    float *dst = p.C + (frame_base + k_rr) * (size_t)p.ldc + nl;
-                                    if ((complete_mask >> rr) & 1u) *dst = m;
-                                    else atomic_max_f32(dst, m);
-                                } else {
-                                    atomic_max_f32(p.pool + (size_t)k_rr * p.ldpool + nl, m);
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acce(buf));           // buffer may be overwritten by tile li + 2
-        }
+        reg_dec<REGS_EPILOGUE>();
+        epilogue_role<BN2, EPI>(p, stg_all, aux, aux_addr, tmem_base, M, tm, warp, lane, [&](int b) {
+            if (rank == 0) mbar_arrive(bar_acce(b));
+            else mbar_arrive_cluster(bar_acce(b), 0);
+        });
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == CONTROL_WARP) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    cluster_sync_all();                              // no CTA may exit while its pair can still signal it
+    if (warp == CONTROL_WARP) tmem_dealloc<2>(tmem_base, 2 * BN2);
 }
 
 }  // namespace tc
