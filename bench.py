@@ -149,6 +149,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("MORIG_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -241,7 +242,12 @@ def run_ours(args):
             outs = step_resident()
         d2h = sum(o.numel() * o.element_size() for o in outs)
         alg_flops_step = ALG_FLOP_PER_VERTEX * N_VTX * MESHES_PER_GPU
-        roof = engine.roofline_report(kstats, peaks, ms_total / args.steps, alg_flops_step)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+        if kstats and os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(kstats[0]["kernel"])      # ncu dram bytes per launch of the dominant kernel
+        roof = engine.roofline_report(kstats, peaks, ms_total / args.steps, alg_flops_step, traffic)
         cpu = cpu_reference_run(steps=3, warmup=1, n_meshes=1) if world == 1 else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
