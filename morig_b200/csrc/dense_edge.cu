@@ -73,9 +73,9 @@ static bool env_flag(const char *name) {
 }
 
 // cta_group::2 variant (UMMA 256 x 256 on a 2-CTA cluster): halves the weight traffic per SM
-template <int AMODE, int EPI>
+template <int BN, int AMODE, int EPI>
 static int launch_tc2(const GemmP &p, const float *blob, int frames, cudaStream_t stream, const char *name) {
-    auto kern = tc::tc2_gemm_kernel<AMODE, EPI>;
+    auto kern = tc::tc2_gemm_kernel<BN, AMODE, EPI>;
     constexpr int smem = tc::SMEM_BYTES;
     static thread_local int configured_dev = -1;
     int dev = 0;
@@ -88,12 +88,11 @@ static int launch_tc2(const GemmP &p, const float *blob, int frames, cudaStream_
     tp.g = p;
     tp.Bblob = blob;
     tp.nK = ceil_div(p.K, tc::KC);
-    tp.ntn = ceil_div(p.N, tc::BN2);
+    tp.ntn = ceil_div(p.N, BN);
     tp.ntm = ceil_div(p.M, tc::BM);
     tp.frames = frames;
-    tp.stages = tc::STAGES2;
+    tp.stages = tc::Cfg2<BN>::STAGES;
     tp.resident_b = 0;
-    tp.dbg = 0;
     tp.trace = nullptr;
     const long long pairs = (long long)tp.ntn * ceil_div(tp.ntm, 2) * frames;
     const int clusters_max = sm_count() / 2;
@@ -117,10 +116,12 @@ static int launch_tc2(const GemmP &p, const float *blob, int frames, cudaStream_
 
 template <int BN, int AMODE, int EPI>
 static int launch_tc(const GemmP &p, const float *blob, int frames, cudaStream_t stream, const char *name) {
-    if (BN == 256 && !env_flag("MORIG_NO_2CTA")) {
-        // enough pair-tiles to give every 2-CTA cluster of the machine at least one
-        const long long pairs = (long long)ceil_div(p.N, BN) * ceil_div(ceil_div(p.M, tc::BM), 2) * frames;
-        if (pairs >= sm_count() / 2) return launch_tc2<AMODE, EPI>(p, blob, frames, stream, name);
+    if constexpr (BN >= 128) {
+        if (!env_flag("MORIG_NO_2CTA")) {
+            // enough pair-tiles to give every 2-CTA cluster of the machine at least one
+            const long long pairs = (long long)ceil_div(p.N, BN) * ceil_div(ceil_div(p.M, tc::BM), 2) * frames;
+            if (pairs >= sm_count() / 2) return launch_tc2<BN, AMODE, EPI>(p, blob, frames, stream, name);
+        }
     }
     auto kern = tc::tc_gemm_kernel<BN, AMODE, EPI>;
     constexpr int smem = tc::SMEM_BYTES;
@@ -141,7 +142,6 @@ static int launch_tc(const GemmP &p, const float *blob, int frames, cudaStream_t
     using C = tc::Cfg<BN>;
     tp.resident_b = (tp.ntn == 1 && C::res_stages(tp.nK) >= 2) ? 1 : 0;
     tp.stages = tp.resident_b ? C::res_stages(tp.nK) : C::STAGES;
-    { const char *e = getenv("MORIG_TC_DBG"); tp.dbg = e ? atoi(e) : 0; }
     tp.trace = g_trace;
     const long long tiles = (long long)tp.ntn * tp.ntm * frames;
     const int sms = sm_count();

@@ -224,6 +224,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return d;
 }
 
+// the same descriptor split in its two 32-bit halves: only the low half depends on the address, and stepping 8 tf32
+// (32 bytes) along the swizzled row adds 2 to it
+constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; }
+
 // instruction descriptor: D=f32, A=B=tf32, both K-major, M x N
 __device__ __forceinline__ uint32_t make_idesc(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -237,7 +243,6 @@ struct TcP {
     int stages;              // A (and, when streaming, B) ring depth
     int resident_b;          // 1: the whole weight image is loaded once and kept in shared memory
     long long *trace;        // debug timeline (CTA 0): [role 0..2][2048] (tag, clock64) pairs, or NULL
-    int dbg;                 // timing experiments only (MORIG_TC_DBG): 1 = one MMA per k-step, 2 = producers skip stores, 4 = no B refetch
 };
 
 struct TileCoord { int n_tile, m0, frame; };
@@ -270,7 +275,7 @@ struct TileMap {
 template <int AMODE, class Arrive>
 __device__ __forceinline__ void producer_role(const GemmP &p, uint8_t *smem, uint32_t a_stride, uint32_t aux_addr, int S,
                                               int nK, int M, const TileMap &tm, int tid, int lane, Arrive arrive,
-                                              int dbg = 0, long long *trace = nullptr) {
+                                              long long *trace = nullptr) {
     Tracer tr{(trace && blockIdx.x == 0 && tid == 0) ? trace : nullptr, 0};
     const int c = tid & 7;
     const int row0 = tid >> 3;
@@ -344,12 +349,8 @@ __device__ __forceinline__ void producer_role(const GemmP &p, uint8_t *smem, uin
             float4 h, l;
             h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
             l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-            if (!(dbg & 2)) {
-                *reinterpret_cast<float4 *>(a_hi + off) = h;
-                *reinterpret_cast<float4 *>(a_lo + off) = l;
-            } else if (h.x == 12345.f && l.y == 54321.f) {
-                *reinterpret_cast<float4 *>(a_hi + off) = h;
-            }
+            *reinterpret_cast<float4 *>(a_hi + off) = h;
+            *reinterpret_cast<float4 *>(a_lo + off) = l;
         }
         fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
@@ -599,19 +600,24 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
     if (warp >= CONTROL_WARP) {
         // ================= control warp: B bulk copies + MMA issue (one elected lane) =================
         reg_dec<REGS_CONTROL>();
-        if (warp == CONTROL_WARP && lane == 0) {
-            Tracer tr{(tp.trace && blockIdx.x == 0) ? tp.trace + 2048 : nullptr, 0};
+        // The whole control warp runs the loop (uniform control flow keeps the address arithmetic on the uniform
+        // datapath); only the elected lane issues the asynchronous operations.
+        if (warp == CONTROL_WARP) {
+            const bool leader = lane == 0;
+            Tracer tr{(tp.trace && blockIdx.x == 0 && leader) ? tp.trace + 2048 : nullptr, 0};
             const uint32_t idesc = make_idesc(BM, BN);
             const uint32_t b_bytes = (uint32_t)C::B_CHUNK_BYTES;
             const uint8_t *gB = reinterpret_cast<const uint8_t *>(tp.Bblob);
             const int my_tiles = tm.my_tiles();
-            // All ring positions are tracked incrementally (no div/mod on this latency-critical thread).
+            // All ring positions are tracked incrementally (no div/mod on this latency-critical warp).
             // fetch cursor: next (tile, k-chunk) whose weight image has to be requested, and its stage
             int f_li = 0, f_kc = 0, f_s = 0, f_ntile = (my_tiles > 0) ? tm.decode(tm.first).n_tile : 0;
             auto fetch_next = [&]() {                              // streaming mode only
                 const uint32_t dst = base + b_region + f_s * b_stride;
-                mbar_arrive_expect_tx(bar_b(f_s), b_bytes);
-                bulk_g2s(dst, gB + ((size_t)f_ntile * nK + f_kc) * b_bytes, b_bytes, bar_b(f_s));
+                if (leader) {
+                    mbar_arrive_expect_tx(bar_b(f_s), b_bytes);
+                    bulk_g2s(dst, gB + ((size_t)f_ntile * nK + f_kc) * b_bytes, b_bytes, bar_b(f_s));
+                }
                 if (++f_s == S) f_s = 0;
                 if (++f_kc == nK) {
                     f_kc = 0;
@@ -622,10 +628,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
             if (resb) {
                 // one n-tile for the whole kernel: fetch every k-chunk of the image once
                 if (my_tiles > 0) {
-                    mbar_arrive_expect_tx(bar_b(0), b_bytes * (uint32_t)nK);
-                    for (int kc = 0; kc < nK; ++kc)
-                        bulk_g2s(base + b_region + kc * b_stride, gB + ((size_t)f_ntile * nK + kc) * b_bytes, b_bytes,
-                                 bar_b(0));
+                    if (leader) {
+                        mbar_arrive_expect_tx(bar_b(0), b_bytes * (uint32_t)nK);
+                        for (int kc = 0; kc < nK; ++kc)
+                            bulk_g2s(base + b_region + kc * b_stride, gB + ((size_t)f_ntile * nK + kc) * b_bytes, b_bytes,
+                                     bar_b(0));
+                    }
                     mbar_wait(bar_b(0), 0);
                 }
             } else {
@@ -647,47 +655,37 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
                     if (!resb) mbar_wait(bar_b(s), ph);
                     tr(23);
                     tc_fence_after();
-                    const uint32_t a_hi = base + s * a_stride, a_lo = a_hi + A_HALF_BYTES;
-                    const uint32_t b_hi = base + b_region + (resb ? kc : s) * b_stride, b_lo = b_hi + C::B_HALF_BYTES;
+                    const uint32_t a_hi = base + s * a_stride;
+                    const uint32_t b_hi = base + b_region + (resb ? kc : s) * b_stride;
+                    const uint32_t lah = desc_lo(a_hi), lal = desc_lo(a_hi + A_HALF_BYTES);
+                    const uint32_t lbh = desc_lo(b_hi), lbl = desc_lo(b_hi + C::B_HALF_BYTES);
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < KC / 8; ++k) {
-                        const uint32_t ko = k * 32;              // 8 tf32 = 32 bytes along the swizzled row
-                        const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
-                        const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
-                        if (!(tp.dbg & 1)) {
-                            umma_tf32<1>(tmem_d, dal, dbh, idesc, (kc | k) != 0);
-                            umma_tf32<1>(tmem_d, dah, dbl, idesc, 1);
-                            umma_tf32<1>(tmem_d, dah, dbh, idesc, 1);
-                        } else {
-                            umma_tf32<1>(tmem_d, dah, dbh, idesc, (kc | k) != 0);
+                        for (int k = 0; k < KC / 8; ++k) {           // 8 tf32 = 32 bytes along the swizzled row
+                            umma_tf32<1>(tmem_d, desc64(lal + 2 * k), desc64(lbh + 2 * k), idesc, (kc | k) != 0);
+                            umma_tf32<1>(tmem_d, desc64(lah + 2 * k), desc64(lbl + 2 * k), idesc, 1);
+                            umma_tf32<1>(tmem_d, desc64(lah + 2 * k), desc64(lbh + 2 * k), idesc, 1);
                         }
+                        umma_commit<1>(bar_m(s));                    // frees stage s when these MMAs retire
                     }
-                    umma_commit<1>(bar_m(s));                    // frees stage s when these MMAs retire
                     tr(24);
                     if (!resb && f_li < my_tiles) {
                         // the stage to refill was last read by the PREVIOUS chunk's MMAs
                         if (!first) mbar_wait(bar_m(prev_s), prev_ph);
                         tr(25);
-                        if ((tp.dbg & 4) && !first) {      // timing experiment: pretend the chunk landed
-                            mbar_arrive(bar_b(f_s));
-                            if (++f_s == S) f_s = 0;
-                            if (++f_kc == nK) { f_kc = 0; ++f_li; }
-                        } else {
-                            fetch_next();
-                        }
+                        fetch_next();
                     }
                     first = false;
                     prev_s = s; prev_ph = ph;
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
-                umma_commit<1>(bar_accf(buf));                   // accumulator complete -> epilogue
+                if (leader) umma_commit<1>(bar_accf(buf));       // accumulator complete -> epilogue
             }
         }
-        __syncwarp();
     } else if (warp < PRODUCER_WARPS) {
         reg_inc<REGS_PRODUCER>();
         producer_role<AMODE>(p, smem, a_stride, aux_addr, S, nK, M, tm, tid, lane,
-                             [&](int s) { mbar_arrive(bar_a(s)); }, tp.dbg, tp.trace);
+                             [&](int s) { mbar_arrive(bar_a(s)); }, tp.trace);
     } else {
         reg_dec<REGS_EPILOGUE>();
         epilogue_role<BN, EPI>(p, stg_all, aux, aux_addr, tmem_base, M, tm, warp, lane,
@@ -699,15 +697,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
 }
 
 // =============================================================================================================
-// cta_group::2 kernel: 2-CTA cluster, UMMA 256 x 256.  CTA rank r of the pair owns rows (2*mp + r)*128.. of the
+// cta_group::2 kernel: 2-CTA cluster, UMMA 256 x BN2 (BN2 = 256 or 128).  CTA rank r of the pair owns rows (2*mp + r)*128.. of the
 // pair-tile and rows [r*128, r*128+128) of every weight chunk.  Only the leader (rank 0) issues MMAs; its barriers
 // collect the arrivals of both CTAs, and tcgen05.commit multicasts completions to both.
 // =============================================================================================================
-constexpr int BN2 = 256;
-constexpr int STAGE2_BYTES = A_STAGE_BYTES + 2 * (BN2 / 2) * 128;      // 32 KB A + 32 KB half weight chunk
-constexpr int STAGES2 = PIPE_BYTES / STAGE2_BYTES;                      // 3
+template <int BN2> struct Cfg2 {
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + 2 * (BN2 / 2) * 128;    // 32 KB A + this CTA's half weight chunk
+    static constexpr int STAGES = (PIPE_BYTES / STAGE_BYTES) > 4 ? 4 : (PIPE_BYTES / STAGE_BYTES);   // 3 (BN 256) / 4 (BN 128)
+};
 
-template <int AMODE, int EPI>
+template <int BN2, int AMODE, int EPI>
 __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
     const GemmP &p = tp.g;
     extern __shared__ uint8_t smem_raw[];
@@ -715,7 +714,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (base - raw_addr);
     const int nK = tp.nK;
-    constexpr int S = STAGES2;
+    constexpr int S = Cfg2<BN2>::STAGES;
+    constexpr int STAGE2_BYTES = Cfg2<BN2>::STAGE_BYTES;
     constexpr uint32_t HALF_B = (BN2 / 2) * 128;                        // 16 KB: this CTA's rows of the hi (or lo) image
     float *stg_all = reinterpret_cast<float *>(smem + PIPE_BYTES);
     uint8_t *aux = smem + PIPE_BYTES + STG_BYTES;
@@ -762,7 +762,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
 
     if (warp >= CONTROL_WARP) {
         reg_dec<REGS_CONTROL>();
-        if (warp == CONTROL_WARP && lane == 0) {
+        if (warp == CONTROL_WARP) {
+            const bool leader = lane == 0;
             const uint8_t *gB = reinterpret_cast<const uint8_t *>(tp.Bblob);
             const uint32_t chunk_bytes = 2u * BN2 * 128;           // full hi|lo image of one k-chunk in global memory
             const int my_tiles = tm.my_tiles();
@@ -770,9 +771,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
             auto fetch_next = [&]() {                              // this CTA's 128 rows of the hi and of the lo image
                 const uint32_t dst = base + f_s * STAGE2_BYTES + A_STAGE_BYTES;
                 const uint8_t *src = gB + ((size_t)f_ntile * nK + f_kc) * chunk_bytes + rank * HALF_B;
-                mbar_arrive_expect_tx(bar_b(f_s), 2 * HALF_B);
-                bulk_g2s(dst, src, HALF_B, bar_b(f_s));
-                bulk_g2s(dst + HALF_B, src + BN2 * 128, HALF_B, bar_b(f_s));
+                if (leader) {
+                    mbar_arrive_expect_tx(bar_b(f_s), 2 * HALF_B);
+                    bulk_g2s(dst, src, HALF_B, bar_b(f_s));
+                    bulk_g2s(dst + HALF_B, src + BN2 * 128, HALF_B, bar_b(f_s));
+                }
                 if (++f_s == S) f_s = 0;
                 if (++f_kc == nK) {
                     f_kc = 0;
@@ -798,20 +801,21 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
                         mbar_wait<true>(bar_bp(s), ph);                    // peer's half chunk landed
                         mbar_wait<true>(bar_a(s), ph);                     // A images of both CTAs written
                         tc_fence_after();
-                        const uint32_t a_hi = base + s * STAGE2_BYTES, a_lo = a_hi + A_HALF_BYTES;
-                        const uint32_t b_hi = a_hi + A_STAGE_BYTES, b_lo = b_hi + HALF_B;
+                        const uint32_t a_hi = base + s * STAGE2_BYTES;
+                        const uint32_t b_hi = a_hi + A_STAGE_BYTES;
+                        const uint32_t lah = desc_lo(a_hi), lal = desc_lo(a_hi + A_HALF_BYTES);
+                        const uint32_t lbh = desc_lo(b_hi), lbl = desc_lo(b_hi + HALF_B);
+                        if (leader) {
 #pragma unroll
-                        for (int k = 0; k < KC / 8; ++k) {
-                            const uint32_t ko = k * 32;
-                            const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
-                            const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
-                            umma_tf32<2>(tmem_d, dal, dbh, idesc, (kc | k) != 0);
-                            umma_tf32<2>(tmem_d, dah, dbl, idesc, 1);
-                            umma_tf32<2>(tmem_d, dah, dbh, idesc, 1);
+                            for (int k = 0; k < KC / 8; ++k) {
+                                umma_tf32<2>(tmem_d, desc64(lal + 2 * k), desc64(lbh + 2 * k), idesc, (kc | k) != 0);
+                                umma_tf32<2>(tmem_d, desc64(lah + 2 * k), desc64(lbl + 2 * k), idesc, 1);
+                                umma_tf32<2>(tmem_d, desc64(lah + 2 * k), desc64(lbh + 2 * k), idesc, 1);
+                            }
+                            umma_commit<2>(bar_m(s));                      // both CTAs: stage s free when retired
                         }
-                        umma_commit<2>(bar_m(s));                          // both CTAs: stage s free when retired
-                    } else {
-                        mbar_arrive_cluster(bar_bp(s), 0);                 // tell the leader
+                    } else if (leader) {
+                        mbar_arrive_cluster(bar_bp(s), 0);                 // tell the leader CTA
                     }
                     if (f_li < my_tiles) {
                         if (!first) mbar_wait(bar_m(prev_s), prev_ph);     // previous chunk's MMAs retired (multicast)
@@ -821,10 +825,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
                     prev_s = s; prev_ph = ph;
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
-                if (rank == 0) umma_commit<2>(bar_accf(buf));              // both CTAs: accumulator complete
+                if (rank == 0 && leader) umma_commit<2>(bar_accf(buf));    // both CTAs: accumulator complete
             }
         }
-        __syncwarp();
     } else if (warp < PRODUCER_WARPS) {
         reg_inc<REGS_PRODUCER>();
         producer_role<AMODE>(p, smem, (uint32_t)STAGE2_BYTES, aux_addr, S, nK, M, tm, tid, lane, [&](int s) {

@@ -75,6 +75,7 @@ def knn_edges(pos: np.ndarray, k: int = 15) -> np.ndarray:
     """[2, kN] int64 rows (i, nbr): k nearest by fp32 ((a-b)^2).sum(), self excluded, ties -> lower index."""
     p = torch.from_numpy(pos)
     n = p.shape[0]
+    k = min(k, n - 1)                            # tiny meshes: every other vertex
     out = np.empty((n, k), dtype=np.int64)
     step = 1024
     for s in range(0, n, step):

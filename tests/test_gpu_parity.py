@@ -200,6 +200,65 @@ def test_models_match_oracle(arch, b, n):
         assert helpers.max_abs_diff(o, e) < helpers.TOL, k
 
 
+def _ragged_batch(sizes, seed, with_skin=False):
+    return synth.collate([synth.make_mesh(n, seed + i, with_skin) for i, n in enumerate(sizes)])
+
+
+@pytest.mark.parametrize("arch,sizes", [("jointnet_motion", (300, 1024, 177)), ("masknet_motion", (9, 130)),
+                                        ("skinnet_motion", (260, 64, 640))])
+def test_ragged_batches_match_oracle(arch, sizes):
+    """meshes of different sizes in one batch (vertex counts that are no multiple of any tile), incl. a 9-vertex mesh"""
+    kw = synth.ARCH_KWARGS[arch]
+    data = _ragged_batch(sizes, 300, with_skin=(arch == "skinnet_motion"))
+    model = helpers.build_model(arch, kw, 13, DEV)
+    expect = helpers.oracle_forward(arch, kw, model, data, data.pred_flow)
+    with torch.no_grad():
+        out = model(data.to(DEV), data.pred_flow.to(DEV))
+    for o, e, k in zip(out, expect, helpers.OUT_KEYS):
+        assert o.shape == e.shape
+        assert helpers.max_abs_diff(o, e) < helpers.TOL, k
+
+
+def test_degenerate_graphs_match_oracle():
+    """no edges at all (every vertex only gets its self loop), and a star graph whose hub has in-degree N-1"""
+    kw = synth.ARCH_KWARGS["jointnet_motion"]
+    model = helpers.build_model("jointnet_motion", kw, 17, DEV)
+    base = synth.make_batch(1, 400, seed=3)
+    n = base.pos.shape[0]
+    empty = torch.zeros(2, 0, dtype=torch.long)
+    star = torch.stack([torch.arange(1, n), torch.zeros(n - 1, dtype=torch.long)])
+    for tpl, geo in ((empty, empty), (star, base.geo_edge_index), (base.tpl_edge_index, star)):
+        data = synth.Batch(**base.__dict__)
+        data.tpl_edge_index, data.geo_edge_index = tpl.contiguous(), geo.contiguous()
+        expect = helpers.oracle_forward("jointnet_motion", kw, model, data, data.pred_flow)
+        with torch.no_grad():
+            out = model(data.to(DEV), data.pred_flow.to(DEV))
+        for o, e, k in zip(out, expect, helpers.OUT_KEYS):
+            assert helpers.max_abs_diff(o, e) < helpers.TOL, k
+
+
+@pytest.mark.parametrize("arch,b,n", [("masknet_motion", 8, 4096), ("skinnet_motion", 4, 8192)])
+def test_baseline_configs_3_and_4_run_and_are_deterministic(arch, b, n):
+    """BASELINE.json configs[2] / configs[3] sizes: finite outputs, unit-norm embeddings, run-to-run bit equality
+    (plain launches vs CUDA-graph replay), first mesh equal to the same mesh run alone"""
+    kw = synth.ARCH_KWARGS[arch]
+    skin = arch == "skinnet_motion"
+    model = helpers.build_model(arch, kw, 19, DEV)
+    data = synth.make_batch(b, n, seed=0, with_skin=skin).to(DEV)
+    with torch.no_grad():
+        a = [t.clone() for t in model(data, data.pred_flow)]
+        model(data, data.pred_flow)
+        c = model(data, data.pred_flow)                       # third call: graph replay
+        for x, y in zip(a, c):
+            assert torch.equal(x, y)
+        assert all(torch.isfinite(t).all() for t in a)
+        assert float((a[0].norm(dim=2) - 1).abs().max()) < 1e-5
+        one = synth.make_batch(1, n, seed=0, with_skin=skin).to(DEV)
+        solo = model(one, one.pred_flow)
+        for x, y in zip(solo, a):
+            assert helpers.max_abs_diff(x, y[: x.shape[0]]) < 1e-5
+
+
 def test_full_size_properties():
     """BASELINE.json configs[1] size (4 x 4096 vertices): properties that need no oracle —
     run-to-run bit equality, data-parallel shard concatenation == single batch, edge-order invariance."""
