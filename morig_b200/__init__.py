@@ -12,12 +12,12 @@ or, to swap the networks inside an unmodified reference checkout:
 """
 from __future__ import annotations
 
-from .basic_modules import MLP, EdgeConvMotion, GCUMotion
+from .basic_modules import GCU, MLP, EdgeConv, EdgeConvMotion, GCUMotion
 from .rignet import (GCNRig, JointNetMotion, MaskNetMotion, SkinMotion, SkinNet_inner, TemporalAttn,
                      jointnet_motion, masknet_motion, skinnet_motion)
 
 __all__ = ["jointnet_motion", "masknet_motion", "skinnet_motion", "JointNetMotion", "MaskNetMotion", "SkinMotion",
-           "SkinNet_inner", "GCNRig", "TemporalAttn", "GCUMotion", "EdgeConvMotion", "MLP", "install"]
+           "SkinNet_inner", "GCNRig", "TemporalAttn", "GCUMotion", "EdgeConvMotion", "GCU", "EdgeConv", "MLP", "install"]
 
 __version__ = "0.1.0"
 

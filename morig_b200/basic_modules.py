@@ -161,3 +161,67 @@ class GCUMotion(FusedModule):
         out = torch.empty(n, gp.out, device=dev, dtype=torch.float32)
         engine.run_gcu(self._ws, "gcu", gp, x, 0, x.shape[1], x.shape[1], pqpos, gt, gg, n, 1, out, 0, gp.out)
         return out
+
+
+class EdgeConv(FusedModule):
+    """`EdgeConv(nn_pos, aggr='max')` — models/basic_modules.py:142-162: the EdgeConvMotion kernel without a second
+    branch (`nn_pos` is the only MLP and is applied to x).  forward(x, edge_index) -> [N, H].
+    Not reached from models/rignet.py (only models/corrnet.py:17-20); provided because it is the C_p = 0 case of
+    the same fused kernel."""
+
+    def __init__(self, nn_pos: nn.Sequential, aggr: str = "max", **kwargs):
+        super().__init__()
+        if aggr != "max":
+            raise NotImplementedError("only aggr='max' is used by the reference networks")
+        self.nn_pos = nn_pos
+
+    def _pack(self):
+        wp, wq, b, br = packing._edge_mlp_parts(self._device_state(), "nn_pos")
+        w = torch.cat([wp, wq])
+        pq = packing.DenseLayer(W=packing._pack_wt(w), K=wp.shape[1], N=2 * br.H,
+                                bias=packing._vec(torch.cat([b, torch.zeros_like(b)]))).with_tc(w)
+        return pq, br
+
+    def run(self, x: torch.Tensor, g: engine.Graph, out: torch.Tensor, ldo: int, out_off: int) -> None:
+        pq, br = self._packed_for("edge", self._pack)
+        n = x.shape[0]
+        buf = self._ws.get("pq", (n, pq.N), x.device)
+        engine.dense(pq, x, 0, x.shape[1], n, C=buf, ldc=pq.N)
+        engine.edgeconv(br, buf, pq.N, 0, br.H, g, 1, out, ldo, out_off)
+
+    def forward(self, x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+        self._guard(x, edge_index)
+        x = _lib.require_cuda(x.unsqueeze(-1) if x.dim() == 1 else x, "x")
+        n = x.shape[0]
+        _, br = self._packed_for("edge", self._pack)
+        out = torch.empty(n, br.H, device=x.device, dtype=torch.float32)
+        engine.fill(out, engine.NEG_INF)
+        self.run(x, self._graphs.get(edge_index, n), out, br.H, 0)
+        return out
+
+
+class GCU(FusedModule):
+    """`GCU(in_channels, out_channels, aggr='max')` — models/basic_modules.py:165-177.
+    forward(pos, tpl_edge_index, geo_edge_index) -> [N, out_channels] (its `pos` argument is the feature)."""
+
+    def __init__(self, in_channels: int, out_channels: int, aggr: str = "max"):
+        super().__init__()
+        half = out_channels // 2
+        self.edge_conv_tpl = EdgeConv(nn_pos=MLP([in_channels * 2, half, half]), aggr=aggr)
+        self.edge_conv_geo = EdgeConv(nn_pos=MLP([in_channels * 2, half, half]), aggr=aggr)
+        self.mlp = MLP([out_channels, out_channels])
+
+    def forward(self, pos, tpl_edge_index, geo_edge_index) -> torch.Tensor:
+        self._guard(pos, tpl_edge_index, geo_edge_index)
+        x = _lib.require_cuda(pos.unsqueeze(-1) if pos.dim() == 1 else pos, "pos")
+        n, dev = x.shape[0], x.device
+        mlp = self._packed_for("gcu", lambda: packing.pack_mlp_layer(
+            {"m." + k: v for k, v in self.mlp.state_dict(keep_vars=True).items()}, "m.0"))
+        half = mlp.K // 2
+        ec = self._ws.get("ec", (n, 2 * half), dev)
+        engine.fill(ec, engine.NEG_INF)
+        self.edge_conv_tpl.run(x, self._graphs.get(tpl_edge_index, n), ec, 2 * half, 0)
+        self.edge_conv_geo.run(x, self._graphs.get(geo_edge_index, n), ec, 2 * half, half)
+        out = torch.empty(n, mlp.N, device=dev, dtype=torch.float32)
+        engine.dense(mlp, ec, 0, 2 * half, n, C=out, ldc=mlp.N)
+        return out

@@ -207,25 +207,11 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 }
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
-// shared-memory matrix descriptor: K-major, SWIZZLE_128B (8 rows x 128 B atoms, 1024 B apart)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address, 16-byte units
-    d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset: next 8-row group
-    d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
-    return d;
-}
-
-// the same descriptor split in its two 32-bit halves: only the low half depends on the address, and stepping 8 tf32
-// (32 bytes) along the swizzled row adds 2 to it
+// shared-memory matrix descriptor (K-major, SWIZZLE_128B: 8-row x 128 B atoms, 1024 B apart):
+//   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major), [32,46) stride
+//   byte offset >> 4 (next 8-row group), [46,48) version = 1 (Blackwell), [61,64) layout = 2 (SWIZZLE_128B).
+// Split in its two 32-bit halves: only the low half depends on the address, and stepping 8 tf32 (32 bytes) along the
+// swizzled row adds 2 to it.
 constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; }

@@ -79,6 +79,24 @@ def gcu_motion(sd, prefix: str, pos, x, tpl_ei, geo_ei) -> torch.Tensor:
     return _mlp(sd, prefix + ".mlp", torch.cat([a, b], dim=1))
 
 
+def edge_conv(sd, prefix: str, x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+    """`EdgeConv.forward/message/update` — models/basic_modules.py:148-159 (single MLP `nn_pos` applied to x)."""
+    if x.dim() == 1:
+        x = x.unsqueeze(-1)
+    n = x.shape[0]
+    ei = normalized_edges(edge_index, n)
+    j, i = ei[0], ei[1]
+    x_i, x_j = x.index_select(0, i), x.index_select(0, j)
+    return _segment_max(_mlp(sd, prefix + ".nn_pos", torch.cat([x_i, x_j - x_i], dim=1)), i, n)
+
+
+def gcu(sd, prefix: str, pos, tpl_ei, geo_ei) -> torch.Tensor:
+    """`GCU.forward` — models/basic_modules.py:172-177."""
+    a = edge_conv(sd, prefix + ".edge_conv_tpl", pos, tpl_ei)
+    b = edge_conv(sd, prefix + ".edge_conv_geo", pos, geo_ei)
+    return _mlp(sd, prefix + ".mlp", torch.cat([a, b], dim=1))
+
+
 def graph_max(x: torch.Tensor, batch: torch.Tensor) -> torch.Tensor:
     """`scatter_max(x, batch, dim=0)[0]` — models/rignet.py:63,176."""
     nb = int(batch.max()) + 1

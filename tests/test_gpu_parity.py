@@ -164,6 +164,21 @@ def test_edge_conv_motion_module(C_x, H, C_p, Dp):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("cin,cout", [(3, 32), (32, 64), (64, 256), (256, 512)])
+def test_gcu_module(cin, cout):
+    """GCU / EdgeConv (models/basic_modules.py:142-177) at the channel sizes models/corrnet.py:17-20 uses"""
+    import morig_b200
+    from oracle import rignet_port
+    data = synth.make_batch(2, 400, seed=8)
+    gcu = morig_b200.GCU(cin, cout).eval()
+    gcu.load_state_dict(synth.seeded_state_dict(gcu, cin))
+    x = torch.randn(800, cin, generator=torch.Generator().manual_seed(cin))
+    want = rignet_port.gcu({"g." + k: v for k, v in gcu.state_dict().items()}, "g", x, data.tpl_edge_index,
+                           data.geo_edge_index)
+    got = gcu.to(DEV)(x.to(DEV), data.tpl_edge_index.to(DEV), data.geo_edge_index.to(DEV))
+    assert helpers.max_abs_diff(got, want) < 2e-5
+
+
 def test_temporal_attn_module():
     import morig_b200
     from oracle import rignet_port

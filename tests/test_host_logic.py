@@ -56,6 +56,22 @@ def test_submodules_keep_reference_signatures(emulated):
     assert helpers.max_abs_diff(att(xs), want) < 5e-6
 
 
+def test_gcu_and_edge_conv_without_pos_branch(emulated):
+    """EdgeConv / GCU (models/basic_modules.py:142-177): the C_p = 0 case of the fused kernel"""
+    from oracle import rignet_port
+    import morig_b200
+    data = synth.make_batch(2, 100, seed=8)
+    for cin, cout in ((3, 32), (32, 64), (64, 256)):
+        gcu = morig_b200.GCU(cin, cout).eval()
+        gcu.load_state_dict(synth.seeded_state_dict(gcu, cin))
+        x = torch.randn(200, cin, generator=torch.Generator().manual_seed(cin))
+        sd = {"g." + k: v for k, v in gcu.state_dict().items()}
+        want = rignet_port.gcu(sd, "g", x, data.tpl_edge_index, data.geo_edge_index)
+        assert helpers.max_abs_diff(gcu(x, data.tpl_edge_index, data.geo_edge_index), want) < 5e-6
+        want = rignet_port.edge_conv(sd, "g.edge_conv_tpl", x, data.tpl_edge_index)
+        assert helpers.max_abs_diff(gcu.edge_conv_tpl(x, data.tpl_edge_index), want) < 5e-6
+
+
 def test_negative_bn_scale_is_not_commuted_through_max(emulated):
     """BN after ReLU with gamma < 0: max(s*h+t) != s*max(h)+t.  All second-layer BN scales negative."""
     from oracle import rignet_port

@@ -43,6 +43,21 @@ def test_port_is_bit_identical_to_unmodified_reference(arch):
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="/root/reference only exists in the build container")
+def test_gcu_port_is_bit_identical_to_unmodified_reference():
+    models = pyg_shim.import_reference_models()
+    from models.basic_modules import GCU          # the reference class, unmodified
+    ref = GCU(32, 64).eval()
+    ref.load_state_dict(synth.seeded_state_dict(ref, 3))
+    data = synth.make_batch(2, 100, seed=4)
+    x = torch.randn(200, 32, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        want = ref(x, data.tpl_edge_index, data.geo_edge_index)
+        got = rignet_port.gcu({"g." + k: v for k, v in ref.state_dict().items()}, "g", x, data.tpl_edge_index,
+                              data.geo_edge_index)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference only exists in the build container")
 def test_state_dict_keys_match_reference():
     import morig_b200
     models = pyg_shim.import_reference_models()
