@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MORIG_ABI_VERSION 1
+#define MORIG_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MORIG_API __attribute__((visibility("default")))
@@ -93,11 +93,19 @@ typedef struct morig_dense_desc {
     float         *pool;     int32_t ldpool;  /* [G, N] or NULL                                */
     int32_t        M, N, K;
     int32_t        relu;
-    /* optional tensor-core operand: W pre-split into tf32 hi|lo halves and pre-swizzled into the shared-
-     * memory image of each (n-tile of tc_bn rows, k-chunk of 32) -- see morig_b200/packing.py:pack_tc_blob.
+    /* optional tensor-core operand: W pre-split into hi|lo halves and pre-swizzled into the shared-memory
+     * image of each (n-tile of tc_bn rows, k-chunk) -- see morig_b200/packing.py:pack_tc_blob.
+     *   tc_kind 0: tf32 halves, k-chunks of 32;   tc_kind 1: fp16 halves of W * 2^j, k-chunks of 64,
+     *   tc_w_inv = 2^-j, and a_amax must point to a device float >= max|A| (see morig_absmax_f32).
      * When non-NULL (and A is 16-byte aligned with lda % 4 == 0, K % 4 == 0) the layer runs on the tcgen05
-     * 3xTF32 engine, otherwise on the fp32 CUDA-core engine using W. */
-    const float   *Wtc;      int32_t tc_bn;   /* tc_bn in {64, 128, 256}                        */
+     * split-precision engine (3 MMAs per product, fp32-class results), otherwise on the fp32 CUDA-core
+     * engine using W. */
+    const void    *Wtc;      int32_t tc_bn;   /* tc_bn in {64, 128, 256}                        */
+    int32_t        tc_kind;  float   tc_w_inv;
+    const float   *a_amax;                     /* device scalar, required for tc_kind 1          */
+    /* optional device scalar: atomically raised to max |C[r, n]| over everything this call stores
+     * (bit pattern of a non-negative float; zero it before the first producer of a buffer)          */
+    float         *c_amax;
 } morig_dense_desc;
 
 MORIG_API int morig_dense_fwd(const morig_dense_desc *d, void *stream);
@@ -118,6 +126,7 @@ MORIG_API int morig_dense_fwd(const morig_dense_desc *d, void *stream);
  *   blocks of `out` while reading PQ rows [0, N).
  *   out must be pre-filled with -inf where segments may straddle 128-edge tiles (use
  *   morig_fill_f32); tiles combine with ordered atomics, so results are deterministic.
+ *   (out_amax bounds the per-edge values z, hence also the stored maxima.)
  * ------------------------------------------------------------------------------------------- */
 typedef struct morig_edge_desc {
     const float   *PQ;     int32_t ldpq, p_off, q_off;
@@ -130,7 +139,10 @@ typedef struct morig_edge_desc {
     const float   *b1, *scale, *shift;        /* [H]                                 */
     float         *out;    int32_t ldo, out_off;
     int32_t        H;
-    const float   *W1tc;                      /* optional tcgen05 image of W1 (n-tile = H <= 256) */
+    const void    *W1tc;                      /* optional tcgen05 image of W1 (n-tile = H <= 256) */
+    int32_t        tc_kind;  float   tc_w_inv;/* as in morig_dense_desc                           */
+    const float   *pq_amax;                   /* device scalar >= max|PQ|, required for tc_kind 1 */
+    float         *out_amax;                  /* optional, raised to max |edge value| before the max */
 } morig_edge_desc;
 
 MORIG_API int morig_edgeconv_fwd(const morig_edge_desc *d, void *stream);
@@ -147,7 +159,7 @@ MORIG_API int morig_edgeconv_fwd(const morig_edge_desc *d, void *stream);
  * ------------------------------------------------------------------------------------------- */
 MORIG_API int morig_temporal_attn_fwd(const float *x, int32_t N, int32_t T, int32_t C, int32_t heads, int32_t D,
                             const float *u, const float *l0, const float *Mv, const float *c0,
-                            float *out, int32_t ldo, void *stream);
+                            float *out, int32_t ldo, float *out_amax, void *stream);
 
 /* x[r, 0:C] /= max(||x[r, 0:C]||_2, 1e-12)  — F.normalize(dim=1), models/rignet.py:87,98,120,131,199,203.
  * If dst2 != NULL the normalised row r = f*N + v is also written to dst2[v, f, 0:C]
@@ -165,9 +177,14 @@ MORIG_API int morig_frame_reduce(const float *x, int32_t N, int32_t T, int32_t C
  *   dst[r, dst_off + c] = src[(r % N), src_off + (r / N) * frame_stride + cols ? cols[c] : c]   */
 MORIG_API int morig_gather_cols(const float *src, int32_t lds, int32_t src_off, int32_t frame_stride,
                       const int32_t *cols, int32_t C, int32_t N, int32_t n_frames,
-                      float *dst, int32_t ldd, int32_t dst_off, void *stream);
+                      float *dst, int32_t ldd, int32_t dst_off, float *dst_amax, void *stream);
 
 MORIG_API int morig_fill_f32(float *dst, int64_t n, float value, void *stream);
+
+/* *amax = max(*amax, max |x[r, c]|) over r < R, c < C (row stride ldx): the operand range the fp16-split
+ * tensor-core layers need for inputs that were not produced by this library (out_amax / dst_amax /
+ * c_amax arguments above keep it up to date for everything that was). */
+MORIG_API int morig_absmax_f32(const float *x, int32_t ldx, int32_t R, int32_t C, float *amax, void *stream);
 
 #ifdef __cplusplus
 }

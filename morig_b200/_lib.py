@@ -31,6 +31,8 @@ class DenseDesc(C.Structure):
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
         ("relu", C.c_int32),
         ("Wtc", c_f32p), ("tc_bn", C.c_int32),
+        ("tc_kind", C.c_int32), ("tc_w_inv", C.c_float),
+        ("a_amax", c_f32p), ("c_amax", c_f32p),
     ]
 
 
@@ -45,6 +47,8 @@ class EdgeDesc(C.Structure):
         ("out", c_f32p), ("ldo", C.c_int32), ("out_off", C.c_int32),
         ("H", C.c_int32),
         ("W1tc", c_f32p),
+        ("tc_kind", C.c_int32), ("tc_w_inv", C.c_float),
+        ("pq_amax", c_f32p), ("out_amax", c_f32p),
     ]
 
 
@@ -59,17 +63,19 @@ _SIGNATURES = {
     "morig_dense_fwd": (C.c_int, [C.POINTER(DenseDesc), C.c_void_p]),
     "morig_edgeconv_fwd": (C.c_int, [C.POINTER(EdgeDesc), C.c_void_p]),
     "morig_temporal_attn_fwd": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                          c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_void_p]),
+                                          c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, c_f32p, C.c_void_p]),
     "morig_row_normalize": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_int32, C.c_int32,
                                       C.c_void_p]),
     "morig_frame_reduce": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_int32,
                                      C.c_void_p]),
     "morig_gather_cols": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_int32, C.c_int32,
-                                    C.c_int32, c_f32p, C.c_int32, C.c_int32, C.c_void_p]),
+                                    C.c_int32, c_f32p, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
     "morig_fill_f32": (C.c_int, [c_f32p, C.c_int64, C.c_float, C.c_void_p]),
+    "morig_absmax_f32": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
+ABI_VERSION = 2
 _lib = None
 
 
@@ -84,8 +90,8 @@ def load() -> C.CDLL:
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.morig_version() != 1:
-            raise ImportError(f"{LIB_PATH}: ABI version {lib.morig_version()} != 1; rebuild")
+        if lib.morig_version() != ABI_VERSION:
+            raise ImportError(f"{LIB_PATH}: ABI version {lib.morig_version()} != {ABI_VERSION}; rebuild")
         _lib = lib
     return _lib
 

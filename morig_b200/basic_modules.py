@@ -118,11 +118,12 @@ class EdgeConvMotion(FusedModule):
         g = self._graphs.get(edge_index, n)
         H, Dp = br_x.H, br_p.H
         out = torch.empty(n, H + Dp, device=dev, dtype=torch.float32)
-        engine.fill(out, engine.NEG_INF)
-        for layer, br, src, off in ((pq_x, br_x, x, 0), (pq_p, br_p, pos, H)):
-            buf = self._ws.get(f"pq{off}", (n, layer.N), dev)
-            engine.dense(layer, src, 0, src.shape[1], n, C=buf, ldc=layer.N)
-            engine.edgeconv(br, buf, layer.N, 0, br.H, g, 1, out, H + Dp, off)
+        with engine.forward_scope(self._ws, dev):
+            engine.fill(out, engine.NEG_INF)
+            for layer, br, src, off in ((pq_x, br_x, x, 0), (pq_p, br_p, pos, H)):
+                buf = self._ws.get(f"pq{off}", (n, layer.N), dev)
+                engine.dense(layer, src, 0, src.shape[1], n, C=buf, ldc=layer.N)
+                engine.edgeconv(br, buf, layer.N, 0, br.H, g, 1, out, H + Dp, off)
         return out
 
 
@@ -157,9 +158,10 @@ class GCUMotion(FusedModule):
         gt = self._graphs.get(tpl_edge_index, n)
         gg = self._graphs.get(geo_edge_index, n)
         pqpos = self._ws.get("pqpos", (n, pq_pos.N), dev)
-        engine.dense(pq_pos, pos, 0, pos.shape[1], n, C=pqpos, ldc=pq_pos.N)
         out = torch.empty(n, gp.out, device=dev, dtype=torch.float32)
-        engine.run_gcu(self._ws, "gcu", gp, x, 0, x.shape[1], x.shape[1], pqpos, gt, gg, n, 1, out, 0, gp.out)
+        with engine.forward_scope(self._ws, dev):
+            engine.dense(pq_pos, pos, 0, pos.shape[1], n, C=pqpos, ldc=pq_pos.N)
+            engine.run_gcu(self._ws, "gcu", gp, x, 0, x.shape[1], x.shape[1], pqpos, gt, gg, n, 1, out, 0, gp.out)
         return out
 
 
@@ -195,8 +197,9 @@ class EdgeConv(FusedModule):
         n = x.shape[0]
         _, br = self._packed_for("edge", self._pack)
         out = torch.empty(n, br.H, device=x.device, dtype=torch.float32)
-        engine.fill(out, engine.NEG_INF)
-        self.run(x, self._graphs.get(edge_index, n), out, br.H, 0)
+        with engine.forward_scope(self._ws, x.device):
+            engine.fill(out, engine.NEG_INF)
+            self.run(x, self._graphs.get(edge_index, n), out, br.H, 0)
         return out
 
 
@@ -219,9 +222,10 @@ class GCU(FusedModule):
             {"m." + k: v for k, v in self.mlp.state_dict(keep_vars=True).items()}, "m.0"))
         half = mlp.K // 2
         ec = self._ws.get("ec", (n, 2 * half), dev)
-        engine.fill(ec, engine.NEG_INF)
-        self.edge_conv_tpl.run(x, self._graphs.get(tpl_edge_index, n), ec, 2 * half, 0)
-        self.edge_conv_geo.run(x, self._graphs.get(geo_edge_index, n), ec, 2 * half, half)
         out = torch.empty(n, mlp.N, device=dev, dtype=torch.float32)
-        engine.dense(mlp, ec, 0, 2 * half, n, C=out, ldc=mlp.N)
+        with engine.forward_scope(self._ws, dev):
+            engine.fill(ec, engine.NEG_INF)
+            self.edge_conv_tpl.run(x, self._graphs.get(tpl_edge_index, n), ec, 2 * half, 0)
+            self.edge_conv_geo.run(x, self._graphs.get(geo_edge_index, n), ec, 2 * half, half)
+            engine.dense(mlp, ec, 0, 2 * half, n, C=out, ldc=mlp.N)
         return out

@@ -48,6 +48,15 @@ __device__ __forceinline__ void atomic_max_f32(float *addr, float v) {
 
 __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
 
+// |value| bookkeeping for the fp16-split tensor-core consumers: warp-wide max of the lanes' non-negative `v`, then one
+// integer atomic max per warp (bit patterns of non-negative floats order like the floats; exact, order independent).
+// Must be reached by all 32 lanes of the warp.
+__device__ __forceinline__ void amax_commit(float *amax, float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+    if (amax && (threadIdx.x & 31) == 0 && v > 0.f) atomicMax(reinterpret_cast<int *>(amax), __float_as_int(v));
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(256) edge_small_kernel(const morig_edge_desc d
     const int lane = threadIdx.x & 31;
     const int c = lane % H, sub = lane / H;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= (int64_t)d.N * d.n_frames) return;
+    if (w >= (int64_t)d.N * d.n_frames) return;      // whole warps leave together
     const int f = (int)(w / d.N), i = (int)(w % d.N);
     const size_t fb = (size_t)f * d.N;
 
@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(256) edge_small_kernel(const morig_edge_desc d
         for (int r = 0; r < d.out_repeat; ++r)
             d.out[((size_t)(f + r) * d.N + i) * (size_t)d.ldo + d.out_off + c] = m;
     }
+    amax_commit(d.out_amax, fabsf(m));
 }
 
 template <int BM, int BN, int AMODE, int EPI>
@@ -72,10 +73,20 @@ static bool env_flag(const char *name) {
     return e && e[0] == '1';
 }
 
-// cta_group::2 variant (UMMA 256 x 256 on a 2-CTA cluster): halves the weight traffic per SM
-template <int BN, int AMODE, int EPI>
-static int launch_tc2(const GemmP &p, const float *blob, int frames, cudaStream_t stream, const char *name) {
-    auto kern = tc::tc2_gemm_kernel<BN, AMODE, EPI>;
+template <int KIND> static void fill_tcp(tc::TcP &tp, const GemmP &p, const void *blob, int BN, int frames) {
+    tp.g = p;
+    tp.Bblob = reinterpret_cast<const float *>(blob);
+    tp.nK = ceil_div(p.K, tc::KindCfg<KIND>::KSTAGE);
+    tp.ntn = ceil_div(p.N, BN);
+    tp.ntm = ceil_div(p.M, tc::BM);
+    tp.frames = frames;
+    tp.trace = nullptr;
+}
+
+// cta_group::2 variant (UMMA 256 x BN on a 2-CTA cluster): halves the weight traffic and the MMA operand reads per SM
+template <int KIND, int BN, int AMODE, int EPI>
+static int launch_tc2(const GemmP &p, const void *blob, int frames, cudaStream_t stream, const char *name) {
+    auto kern = tc::tc2_gemm_kernel<KIND, BN, AMODE, EPI>;
     constexpr int smem = tc::SMEM_BYTES;
     static thread_local int configured_dev = -1;
     int dev = 0;
@@ -85,15 +96,11 @@ static int launch_tc2(const GemmP &p, const float *blob, int frames, cudaStream_
         configured_dev = dev;
     }
     tc::TcP tp;
-    tp.g = p;
-    tp.Bblob = blob;
-    tp.nK = ceil_div(p.K, tc::KC);
-    tp.ntn = ceil_div(p.N, BN);
-    tp.ntm = ceil_div(p.M, tc::BM);
-    tp.frames = frames;
-    tp.stages = tc::Cfg2<BN>::STAGES;
-    tp.resident_b = 0;
-    tp.trace = nullptr;
+    fill_tcp<KIND>(tp, p, blob, BN, frames);
+    using C2 = tc::Cfg2<BN>;
+    tp.resident_b = (tp.ntn == 1 && C2::res_stages(tp.nK) >= 2 && !env_flag("MORIG_NO_RESB")) ? 1 : 0;
+    tp.stages = tp.resident_b ? C2::res_stages(tp.nK) : C2::STAGES;
+    tp.trace = g_trace;
     const long long pairs = (long long)tp.ntn * ceil_div(tp.ntm, 2) * frames;
     const int clusters_max = sm_count() / 2;
     const unsigned grid = 2u * (unsigned)(pairs < clusters_max ? pairs : clusters_max);
@@ -114,16 +121,16 @@ static int launch_tc2(const GemmP &p, const float *blob, int frames, cudaStream_
     return 0;
 }
 
-template <int BN, int AMODE, int EPI>
-static int launch_tc(const GemmP &p, const float *blob, int frames, cudaStream_t stream, const char *name) {
+template <int KIND, int BN, int AMODE, int EPI>
+static int launch_tc(const GemmP &p, const void *blob, int frames, cudaStream_t stream, const char *name) {
     if constexpr (BN >= 128) {
         if (!env_flag("MORIG_NO_2CTA")) {
             // enough pair-tiles to give every 2-CTA cluster of the machine at least one
             const long long pairs = (long long)ceil_div(p.N, BN) * ceil_div(ceil_div(p.M, tc::BM), 2) * frames;
-            if (pairs >= sm_count() / 2) return launch_tc2<BN, AMODE, EPI>(p, blob, frames, stream, name);
+            if (pairs >= sm_count() / 2) return launch_tc2<KIND, BN, AMODE, EPI>(p, blob, frames, stream, name);
         }
     }
-    auto kern = tc::tc_gemm_kernel<BN, AMODE, EPI>;
+    auto kern = tc::tc_gemm_kernel<KIND, BN, AMODE, EPI>;
     constexpr int smem = tc::SMEM_BYTES;
     static thread_local int configured_dev = -1;
     int dev = 0;
@@ -133,14 +140,9 @@ static int launch_tc(const GemmP &p, const float *blob, int frames, cudaStream_t
         configured_dev = dev;
     }
     tc::TcP tp;
-    tp.g = p;
-    tp.Bblob = blob;
-    tp.nK = ceil_div(p.K, tc::KC);
-    tp.ntn = ceil_div(p.N, BN);
-    tp.ntm = ceil_div(p.M, tc::BM);
-    tp.frames = frames;
+    fill_tcp<KIND>(tp, p, blob, BN, frames);
     using C = tc::Cfg<BN>;
-    tp.resident_b = (tp.ntn == 1 && C::res_stages(tp.nK) >= 2) ? 1 : 0;
+    tp.resident_b = (tp.ntn == 1 && C::res_stages(tp.nK) >= 2 && !env_flag("MORIG_NO_RESB")) ? 1 : 0;
     tp.stages = tp.resident_b ? C::res_stages(tp.nK) : C::STAGES;
     tp.trace = g_trace;
     const long long tiles = (long long)tp.ntn * tp.ntm * frames;
@@ -149,6 +151,12 @@ static int launch_tc(const GemmP &p, const float *blob, int frames, cudaStream_t
     kern<<<grid, tc::THREADS, smem, stream>>>(tp);
     MORIG_LAUNCH_CHECK(name);
     return 0;
+}
+
+template <int BN, int AMODE, int EPI>
+static int launch_tc_kind(int kind, const GemmP &p, const void *blob, int frames, cudaStream_t stream, const char *name) {
+    if (kind == tc::KIND_F16) return launch_tc<tc::KIND_F16, BN, AMODE, EPI>(p, blob, frames, stream, name);
+    return launch_tc<tc::KIND_TF32, BN, AMODE, EPI>(p, blob, frames, stream, name);
 }
 
 static bool tc_disabled() {
@@ -187,13 +195,20 @@ extern "C" MORIG_API int morig_dense_fwd(const morig_dense_desc *d, void *stream
     p.c_vec = (d->C && d->ldc % 4 == 0 && aligned16(d->C)) ? 1 : 0;
     p.pool = d->pool; p.ldpool = d->ldpool;
     p.M = d->M; p.N = d->N; p.K = d->K; p.relu = d->relu;
+    p.amax_in = d->a_amax; p.amax_out = d->c_amax; p.w_inv = 1.f;
     if (d->Wtc && p.a_vec && !tc_disabled()) {
         MORIG_CHECK_ARG(aligned16(d->Wtc), "dense_fwd: Wtc must be 16B aligned");
         MORIG_CHECK_ARG(ceil_div(d->M, 128) <= 65535, "dense_fwd: M=%d too large for one launch", d->M);
+        MORIG_CHECK_ARG((uint64_t)d->M * (uint64_t)d->lda < (1ull << 32), "dense_fwd: M*lda exceeds 32-bit element offsets");
+        MORIG_CHECK_ARG(d->tc_kind == tc::KIND_TF32 || d->tc_kind == tc::KIND_F16, "dense_fwd: tc_kind=%d", d->tc_kind);
+        if (d->tc_kind == tc::KIND_F16) {
+            MORIG_CHECK_ARG(d->a_amax && d->tc_w_inv > 0.f, "dense_fwd: the fp16 kind needs a_amax and tc_w_inv");
+            p.w_inv = d->tc_w_inv;
+        }
         switch (d->tc_bn) {
-            case 64:  return launch_tc<64, AMODE_PLAIN, EPI_STORE>(p, d->Wtc, 1, stream, "tc_dense<64>");
-            case 128: return launch_tc<128, AMODE_PLAIN, EPI_STORE>(p, d->Wtc, 1, stream, "tc_dense<128>");
-            case 256: return launch_tc<256, AMODE_PLAIN, EPI_STORE>(p, d->Wtc, 1, stream, "tc_dense<256>");
+            case 64:  return launch_tc_kind<64, AMODE_PLAIN, EPI_STORE>(d->tc_kind, p, d->Wtc, 1, stream, "tc_dense<64>");
+            case 128: return launch_tc_kind<128, AMODE_PLAIN, EPI_STORE>(d->tc_kind, p, d->Wtc, 1, stream, "tc_dense<128>");
+            case 256: return launch_tc_kind<256, AMODE_PLAIN, EPI_STORE>(d->tc_kind, p, d->Wtc, 1, stream, "tc_dense<256>");
             default:  MORIG_CHECK_ARG(false, "dense_fwd: tc_bn=%d unsupported (64,128,256)", d->tc_bn);
         }
     }
@@ -232,12 +247,21 @@ extern "C" MORIG_API int morig_edgeconv_fwd(const morig_edge_desc *d, void *stre
     p.bias = d->b1; p.scale = d->scale; p.shift = d->shift;
     p.C = d->out + d->out_off; p.ldc = d->ldo;
     p.M = d->E_max; p.N = H; p.K = H; p.relu = 1;
+    p.amax_in = d->pq_amax; p.amax_out = d->out_amax; p.w_inv = 1.f;
     if (d->W1tc && !tc_disabled()) {
         MORIG_CHECK_ARG(aligned16(d->W1tc), "edgeconv_fwd: W1tc must be 16B aligned");
         MORIG_CHECK_ARG(ceil_div(d->E_max, 128) <= 65535, "edgeconv_fwd: E=%d too large for one launch", d->E_max);
-        if (H == 64)  return launch_tc<64, AMODE_GATHER, EPI_SEGMAX>(p, d->W1tc, d->n_frames, stream, "tc_edge<64>");
-        if (H == 128) return launch_tc<128, AMODE_GATHER, EPI_SEGMAX>(p, d->W1tc, d->n_frames, stream, "tc_edge<128>");
-        return launch_tc<256, AMODE_GATHER, EPI_SEGMAX>(p, d->W1tc, d->n_frames, stream, "tc_edge<256>");
+        MORIG_CHECK_ARG((uint64_t)d->N * (uint64_t)d->n_frames * (uint64_t)d->ldpq < (1ull << 32),
+                        "edgeconv_fwd: PQ exceeds 32-bit element offsets");
+        MORIG_CHECK_ARG(d->tc_kind == tc::KIND_TF32 || d->tc_kind == tc::KIND_F16, "edgeconv_fwd: tc_kind=%d", d->tc_kind);
+        if (d->tc_kind == tc::KIND_F16) {
+            MORIG_CHECK_ARG(d->pq_amax && d->tc_w_inv > 0.f, "edgeconv_fwd: the fp16 kind needs pq_amax and tc_w_inv");
+            p.w_inv = d->tc_w_inv;
+        }
+        const int kind = d->tc_kind;
+        if (H == 64)  return launch_tc_kind<64, AMODE_GATHER, EPI_SEGMAX>(kind, p, d->W1tc, d->n_frames, stream, "tc_edge<64>");
+        if (H == 128) return launch_tc_kind<128, AMODE_GATHER, EPI_SEGMAX>(kind, p, d->W1tc, d->n_frames, stream, "tc_edge<128>");
+        return launch_tc_kind<256, AMODE_GATHER, EPI_SEGMAX>(kind, p, d->W1tc, d->n_frames, stream, "tc_edge<256>");
     }
     if (H == 64) {
         dim3 grid(ceil_div(d->E_max, 128), 1, d->n_frames);

@@ -32,6 +32,10 @@ struct GemmP {
     float *C; int ldc; int c_vec;
     float *pool; int ldpool;
     int M, N, K, relu;
+    // dynamic range bookkeeping of the fp16-split tensor-core engine (gemm_tc.cuh): every kernel that stores
+    // activations max-reduces |value| into *amax_out; an fp16 consumer derives its operand scale from *amax_in
+    const float *amax_in; float *amax_out;
+    float w_inv;                // 1 / (power-of-two scale baked into the fp16 weight image)
 };
 
 constexpr int GEMM_THREADS = 256;
@@ -223,6 +227,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_simt_kernel(const GemmP 
         }
         const bool uniform = g_first == g_last;
         float cmax[TN];
+        float am = 0.f;
 #pragma unroll
         for (int j = 0; j < TN; ++j) cmax[j] = neg_inf();
 #pragma unroll
@@ -240,6 +245,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_simt_kernel(const GemmP 
                 if (p.relu) x = fmaxf(x, 0.f);
                 x = fmaf(x, cs[j], ct[j]);
                 v[j] = x;
+                if (n < p.N) am = fmaxf(am, fabsf(x));
                 if (pooling) {
                     if (uniform) cmax[j] = fmaxf(cmax[j], x);
                     else if (n < p.N) atomic_max_f32(p.pool + (size_t)g * p.ldpool + n, x);
@@ -260,6 +266,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_simt_kernel(const GemmP 
                 }
             }
         }
+        if (p.C) amax_commit(p.amax_out, am);
         if (pooling && uniform) {                    // CTA-wide column max, one atomic per column
             float *red = smem;                       // [16][BN], aliases the (drained) pipeline buffers
             __syncthreads();
@@ -279,6 +286,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_simt_kernel(const GemmP 
         int32_t *s_tgt = reinterpret_cast<int32_t *>(smem + (S::CS_FLOATS > S::PIPE_FLOATS ? S::CS_FLOATS : S::PIPE_FLOATS));
         __syncthreads();
         for (int r = tid; r < BM; r += GEMM_THREADS) s_tgt[r] = (m0 + r < M) ? p.tgt[m0 + r] : -1;
+        float am = 0.f;
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
             const int row = tile_row(i);
@@ -292,10 +300,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_simt_kernel(const GemmP 
                     float x = acc[i][j] + cb[j];
                     x = fmaxf(x, 0.f);               // second ReLU of the edge MLP
                     vv[q] = fmaf(x, cs[j], ct[j]);   // BatchNorm #2 BEFORE the max (scale may be < 0)
+                    if (m0 + row < M && n0 + tile_col(j) < p.N) am = fmaxf(am, fabsf(vv[q]));
                 }
                 *reinterpret_cast<float4 *>(Cs + row * S::CS_LD + tile_col(h * 4)) = v;
             }
         }
+        amax_commit(p.amax_out, am);
         __syncthreads();
         constexpr int PARTS = GEMM_THREADS / BN;
         constexpr int ROWS_PER = BM / PARTS;

@@ -1,9 +1,16 @@
-// tcgen05 tile engine (sm_100a): persistent, warp-specialised 3xTF32 GEMM with fp32 accumulation in TMEM.
+// tcgen05 tile engine (sm_100a): persistent, warp-specialised split-precision GEMM with fp32 accumulation in TMEM.
 //
-//   D[128 x BN] (+)= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi        (tcgen05.mma kind::tf32, K = 8 per instruction)
+//   D[128 x BN] (+)= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi
 //
-// fp32 inputs are split x = hi + lo with hi = rna_tf32(x); dropping lo*lo leaves fp32-class results (the 1e-4
-// absolute tolerance of the path rules out plain TF32/BF16).
+// fp32 inputs are split x = hi + lo; dropping lo*lo leaves fp32-class results (the 1e-4 absolute tolerance of the
+// path rules out plain TF32/BF16/FP16).  Two operand kinds share all of the code below:
+//   KIND_TF32  hi = x with 13 mantissa bits cleared, lo = x - hi          tcgen05.mma kind::tf32, K =  8 / instruction
+//   KIND_F16   hi = fp16(x*s) (11 significant bits), lo = fp16(x*s - hi)  tcgen05.mma kind::f16,  K = 16 / instruction
+//              -> the same 22 significant bits per operand at twice the MMA rate and half the shared-memory bytes.
+//              fp16 has a 5-bit exponent, so operands are scaled by powers of two: weights at pack time, activations
+//              by s = 2^(15 - ceil(log2(amax))) where amax is the running max |value| of the source buffer that every
+//              producing kernel maintains (GemmP::amax_in / amax_out); the epilogue multiplies by the exact inverse.
+//              Elements down to 2^-17 of the buffer's max keep all 22 bits (fp16 subnormals resolve 2^-24 * 2^-15).
 //
 // One CTA per SM walks tiles; three roles run decoupled through mbarriers:
 //   warps 0-7   A producers: 32 k-columns per stage written straight into 128B-swizzled K-major shared memory;
@@ -27,25 +34,36 @@
 //                            core's cross-CTA operand path), which halves the L2 -> SM weight traffic that
 //                            bounds the streamed layers
 #pragma once
+#include <cuda_fp16.h>
 #include "gemm_simt.cuh"
 
 namespace morig {
 namespace tc {
 
+enum { KIND_TF32 = 0, KIND_F16 = 1 };
+
 constexpr int BM = 128;
-constexpr int KC = 32;                       // fp32 k-columns per stage = one 128-byte swizzle row
+constexpr int KC = 32;                       // fp32 k-columns per producer ring unit
+// one stage = 128-byte swizzle rows: 32 tf32 (one ring unit) or 64 fp16 (two ring units)
+template <int KIND> struct KindCfg {
+    static constexpr int UPS = (KIND == KIND_F16) ? 2 : 1;      // ring units per stage
+    static constexpr int KSTAGE = KC * UPS;                     // k-columns per stage
+};
 constexpr int A_HALF_BYTES = BM * 128;       // 16 KB: hi (then lo) image of the A stage
 constexpr int A_STAGE_BYTES = 2 * A_HALF_BYTES;
-constexpr int PRODUCER_WARPS = 4;
+constexpr int PRODUCER_WARPS = 8;
 constexpr int EPILOGUE_WARPS = 8;                                // two per TMEM lane quarter, alternating 32-column blocks
 constexpr int CONTROL_WARP = PRODUCER_WARPS + EPILOGUE_WARPS;
 constexpr int THREADS = 32 * (PRODUCER_WARPS + EPILOGUE_WARPS + 4);    // control warp + 3 idle warps: a full warpgroup
-// Register budget: 16 warps x 128 registers = the whole register file at launch; the roles then rebalance with
-// setmaxnreg (which works on whole warpgroups, hence the 3 idle warps next to the control warp): every scheduler
-// hosts 1 producer warp (208) + 2 epilogue warps (104) + 1 control-group warp (56) = 472 of its 512 registers/lane.
-constexpr int REGS_PRODUCER = 208, REGS_EPILOGUE = 104, REGS_CONTROL = 56;
-constexpr int ROWS_PER_THREAD = BM / (PRODUCER_WARPS * 4);       // 8 rows, one 16-byte chunk each
-constexpr int ROW_STEP = PRODUCER_WARPS * 4;                     // rows handled by one warp-wide instruction group
+// Register budget: 20 warps x 96 registers at launch (640 threads cap the launch allocation at 61440 of the 65536
+// registers, and setmaxnreg can only redistribute what the CTA was given); the roles then rebalance with setmaxnreg
+// (which works on whole warpgroups, hence the 3 idle warps next to the control warp): every scheduler hosts
+// 2 producer warps (112) + 2 epilogue warps (104) + 1 control-group warp (48) = 480 = 5 x 96 registers/lane.  Both data roles are latency-bound
+// straight-line code, so two warps of each per scheduler (hiding each other's stalls) matter more than deep
+// per-thread register rings.
+constexpr int REGS_PRODUCER = 112, REGS_EPILOGUE = 104, REGS_CONTROL = 48;
+static_assert(2 * REGS_PRODUCER + 2 * REGS_EPILOGUE + REGS_CONTROL <= 5 * 96, "setmaxnreg budget exceeds the launch allocation");
+constexpr int ROWS_PER_THREAD = BM / (PRODUCER_WARPS * 4);       // 4 rows, one 16-byte fp32 chunk each
 constexpr int STG_LD = 33;                                       // staging tile row stride (floats)
 constexpr int STG_BYTES = EPILOGUE_WARPS * 32 * STG_LD * 4;      // 33 KB (the pad column of each tile holds the row keys)
 constexpr int AUX_BYTES = 1024;                                  // barriers, tmem pointer
@@ -165,24 +183,22 @@ template <int CTAS> __device__ __forceinline__ void umma_commit(uint32_t bar) {
                      ::"r"(bar), "h"(mask) : "memory");
     }
 }
-template <int CTAS>
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    if (CTAS == 1) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-            "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+#define MORIG_UMMA(GROUP, KINDSTR)                                                                   \
+    asm volatile(                                                                                   \
+        "{\n\t"                                                                                     \
+        ".reg .pred p;\n\t"                                                                         \
+        "setp.ne.b32 p, %4, 0;\n\t"                                                                 \
+        "tcgen05.mma.cta_group::" GROUP ".kind::" KINDSTR " [%0], %1, %2, %3, p;\n\t"               \
+        "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory")
+template <int KIND, int CTAS>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    if (KIND == KIND_TF32) {
+        if (CTAS == 1) MORIG_UMMA("1", "tf32"); else MORIG_UMMA("2", "tf32");
     } else {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-            "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+        if (CTAS == 1) MORIG_UMMA("1", "f16"); else MORIG_UMMA("2", "f16");
     }
 }
+#undef MORIG_UMMA
 // asynchronous TMEM -> register load of 32 lanes x 32 columns; the registers are valid after tmem_ld_wait()
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -216,9 +232,31 @@ constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; }
 
-// instruction descriptor: D=f32, A=B=tf32, both K-major, M x N
-__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// instruction descriptor: D = f32 (bits 4-5 = 1), A and B format (bits 7-9, 10-12: 0 = f16, 2 = tf32), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24
+template <int KIND> __device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+    const uint32_t fmt = (KIND == KIND_F16) ? 0u : 2u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// Activation scale of the fp16 kind: a power of two s with amax * s < 2^15 (gather mode: relu(P + Q) <= 2 amax), and
+// the factor that undoes it (and the weight image's scale) in the epilogue.  TF32 needs neither.
+template <int KIND>
+__device__ __forceinline__ void operand_scales(const GemmP &p, bool gather, float &a_scale, float &inv) {
+    a_scale = 1.f; inv = 1.f;
+    if (KIND == KIND_F16) {
+        const uint32_t bits = __float_as_uint(p.amax_in ? *p.amax_in : 1.f);
+        int e = (int)((bits >> 23) & 0xffu);            // amax < 2^(e - 126)
+        if (e == 0 || e == 255) e = 126;                // zero / denormal / non-finite source: no scaling
+        int sh = (gather ? 14 : 15) - (e - 126);
+        sh = sh < -100 ? -100 : (sh > 100 ? 100 : sh);
+        a_scale = __uint_as_float((uint32_t)(sh + 127) << 23);
+        inv = __uint_as_float((uint32_t)(127 - sh) << 23) * p.w_inv;
+    }
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo_k, float hi_k) {
+    const __half2 h = __floats2half2_rn(lo_k, hi_k);    // lower k in the low half (K-major, little endian)
+    return *reinterpret_cast<const uint32_t *>(&h);
 }
 
 struct TcP {
@@ -255,124 +293,147 @@ struct TileMap {
 };
 
 // ================= producer warps: A stage images =================
-// Thread -> 16-byte chunk c of rows row0 + ROW_STEP*ps.  One warp instruction covers 4 consecutive CSR slots, which
-// mostly share P[tgt] (one coalesced line).  The relu(P+Q) combine is deferred to the store step so that issuing
-// the loads of the next chunk never blocks.  `arrive(s)` publishes stage s to the MMA issuer.
-template <int AMODE, class Arrive>
-__device__ __forceinline__ void producer_role(const GemmP &p, uint8_t *smem, uint32_t a_stride, uint32_t aux_addr, int S,
-                                              int nK, int M, const TileMap &tm, int tid, int lane, Arrive arrive,
-                                              long long *trace = nullptr) {
+// The producers work in ring UNITS of 32 k-columns: thread -> 4 consecutive k-columns (one float4) of 4 rows.  A TF32
+// stage is one unit (16-byte hi and lo chunks), an FP16 stage two units (8-byte chunks).  Two register buffers rotate:
+// store unit u from one buffer, publish the stage, then refill the same buffer with the loads of unit u + 2 -- so
+// one to two units (16-32 KB per SM) are always in flight, and the proxy fence that precedes every publish never has
+// to drain loads younger than a full unit.  In gather mode the relu(P[tgt] + Q[col]) combine happens at store time;
+// gather indices are fetched one tile ahead.  Loads are unpredicated: rows past the end re-read the last valid row
+// (their accumulators are never looked at) and k-columns past K re-read columns 0-3 (the weight image is zero there).
+// `arrive(s)` publishes stage s to the MMA issuer.
+//
+// tile row of (role warp w, lane group g = lane >> 3, pass ps): rows {a, a+1, a+4, a+5}.  An 8-byte fp16 store covers
+// half a swizzled row and bit 2 of the row decides which half of the banks it lands in, so this mix keeps every
+// store instruction at its minimum of 2 (fp16) / 4 (tf32) wavefronts; adjacent rows mostly share their P[tgt] line.
+__device__ __forceinline__ int producer_row(int w, int g, int ps) {
+    const int b = w + PRODUCER_WARPS * ps;          // 32 blocks of 4 rows
+    return 8 * (b >> 1) + 2 * (b & 1) + (g & 1) + 4 * (g >> 1);
+}
+
+template <int KIND, int AMODE, class Arrive>
+__device__ __forceinline__ void producer_role(const GemmP &p, float a_scale, uint8_t *smem, uint32_t a_stride,
+                                              uint32_t aux_addr, int S, int nK, int M, const TileMap &tm, int tid,
+                                              int lane, Arrive arrive, long long *trace = nullptr) {
+    constexpr int UPS = KindCfg<KIND>::UPS;
+    constexpr int RPT = ROWS_PER_THREAD;
+    constexpr bool GATHER = (AMODE == AMODE_GATHER);
     Tracer tr{(trace && blockIdx.x == 0 && tid == 0) ? trace : nullptr, 0};
     const int c = tid & 7;
-    const int row0 = tid >> 3;
-    int s = 0;                                   // ring position, tracked incrementally
+    const int w = tid >> 5, g = (tid >> 3) & 3;
+    const int nU = nK * UPS;                     // ring units per tile
+    int s = 0;                                   // stage ring position
     uint32_t wait_ph = 1;                        // parity of "stage s is free" (passes on a fresh barrier)
-    // register ring of raw operands: DEPTH chunks, DEPTH-1 of them in flight ahead of the one being stored.
-    // Memory latency (DRAM for activations, L2 for gathered rows) is ~1 us, a chunk's MMAs take ~0.8 us: one chunk
-    // of look-ahead leaves the tensor pipe waiting, so plain rows keep 3 chunks in flight and gathers 2.
-    constexpr int DEPTH = (AMODE == AMODE_GATHER) ? 2 : 4;
-    float4 pbuf[DEPTH][ROWS_PER_THREAD];
-    float4 qbuf[(AMODE == AMODE_GATHER) ? DEPTH : 1][ROWS_PER_THREAD];
-    const float *src0[ROWS_PER_THREAD];
-    const float *src1[ROWS_PER_THREAD];
-    int ni[ROWS_PER_THREAD], nj[ROWS_PER_THREAD];    // gather indices of the NEXT tile, fetched a tile ahead
-    uint32_t okmask = 0;
 
-    auto fetch_indices = [&](const TileCoord &t) {
+    // shared-memory byte offset of this thread's chunk in each of its rows (unit 0 of a stage; unit 1 of an fp16
+    // stage is the other half of the swizzled row: offset ^ 64)
+    uint32_t soff[RPT];
 #pragma unroll
-        for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
-            const int r = t.m0 + row0 + ROW_STEP * ps;
-            ni[ps] = 0; nj[ps] = 0;
-            if (AMODE == AMODE_GATHER && r < M) { ni[ps] = p.tgt[r]; nj[ps] = p.col[r]; }
+    for (int ps = 0; ps < RPT; ++ps) {
+        const int row = producer_row(w, g, ps);
+        soff[ps] = (KIND == KIND_F16) ? (uint32_t)(row * 128 + (((c >> 1) ^ (row & 7)) << 4) + ((c & 1) << 3))
+                                      : (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4));
+    }
+
+    // load cursor: (tile, unit) whose loads are issued next, row pointers of that tile, indices of the following one
+    int lt = tm.first, lu = 0;
+    const float *rp[RPT];
+    const float *rq[GATHER ? RPT : 1];
+    int ni[GATHER ? RPT : 1], nj[GATHER ? RPT : 1];
+    const int last_row = M - 1;
+
+    auto fetch_idx = [&](int t) {
+        const int m0 = tm.decode(t).m0;
+#pragma unroll
+        for (int ps = 0; ps < RPT; ++ps) {
+            const int r = min(m0 + producer_row(w, g, ps), last_row);
+            ni[GATHER ? ps : 0] = p.tgt[r];
+            nj[GATHER ? ps : 0] = p.col[r];
         }
     };
-    auto setup_rows = [&](const TileCoord &t) {      // consumes ni/nj of this tile
-        okmask = 0;
+    auto issue = [&](float4 (&pd)[RPT], float4 (&qd)[GATHER ? RPT : 1]) {
+        if (lt >= tm.total) return;
+        if (lu == 0) {
+            const TileCoord tc_ = tm.decode(lt);
+            if (GATHER) {
+                if (lt == tm.first) fetch_idx(lt);
+                const size_t fb = (size_t)tc_.frame * p.n_vtx_frame;
 #pragma unroll
-        for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
-            const int r = t.m0 + row0 + ROW_STEP * ps;
-            const bool ok = r < M;
-            okmask |= (ok ? 1u : 0u) << ps;
-            if (AMODE == AMODE_GATHER) {
-                const size_t fb = (size_t)t.frame * p.n_vtx_frame;
-                src0[ps] = p.P + (fb + ni[ps]) * (size_t)p.ldpq + 4 * c;
-                src1[ps] = p.Q + (fb + nj[ps]) * (size_t)p.ldpq + 4 * c;
+                for (int ps = 0; ps < RPT; ++ps) {
+                    rp[ps] = p.P + (fb + ni[ps]) * (size_t)p.ldpq + 4 * c;
+                    rq[ps] = p.Q + (fb + nj[ps]) * (size_t)p.ldpq + 4 * c;
+                }
+                if (lt + tm.step < tm.total) fetch_idx(lt + tm.step);      // consumed a tile later
             } else {
-                src0[ps] = p.A + (size_t)(ok ? r : 0) * p.lda + 4 * c;
-                src1[ps] = nullptr;
-            }
-        }
-    };
-    auto load_raw = [&](int kc, float4 (&pd)[ROWS_PER_THREAD], float4 (&qd)[ROWS_PER_THREAD]) {
-        const int k = kc * KC + 4 * c;
 #pragma unroll
-        for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
-            pd[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (AMODE == AMODE_GATHER) qd[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (((okmask >> ps) & 1u) && k < p.K) {
-                pd[ps] = *reinterpret_cast<const float4 *>(src0[ps] + kc * KC);
-                if (AMODE == AMODE_GATHER) qd[ps] = *reinterpret_cast<const float4 *>(src1[ps] + kc * KC);
+                for (int ps = 0; ps < RPT; ++ps)
+                    rp[ps] = p.A + (size_t)min(tc_.m0 + producer_row(w, g, ps), last_row) * p.lda + 4 * c;
             }
         }
+        const int koff = (lu * KC + 4 * c < p.K) ? lu * KC : -4 * c;
+#pragma unroll
+        for (int ps = 0; ps < RPT; ++ps) {
+            pd[ps] = *reinterpret_cast<const float4 *>(rp[ps] + koff);
+            if (GATHER) qd[ps] = *reinterpret_cast<const float4 *>(rq[ps] + koff);
+        }
+        if (++lu == nU) { lu = 0; lt += tm.step; }
     };
-    auto store_stage = [&](const float4 (&pd)[ROWS_PER_THREAD], const float4 (&qd)[ROWS_PER_THREAD]) {
-        tr(1);
-        mbar_wait(aux_addr + AUX_MMA_DONE + 8u * s, wait_ph);    // MMAs that read this stage one ring turn ago retired
-        tr(2);
+    // US = unit inside the stage: with two rotating buffers and an even unit count per tile, buffer 0 always holds
+    // unit 0 and buffer 1 unit 1 of an fp16 stage, so it is a compile-time constant
+    // (a literal at both call sites: the lambda is inlined and `us` folds away)
+    auto store_unit = [&](const int us_arg, const float4 (&pd)[RPT], const float4 (&qd)[GATHER ? RPT : 1]) {
+        const int us = (KIND == KIND_F16) ? us_arg : 0;
+        if (us == 0) {
+            tr(1);
+            mbar_wait(aux_addr + AUX_MMA_DONE + 8u * s, wait_ph);    // MMAs that read this stage one ring turn ago retired
+            tr(2);
+        }
         uint8_t *a_hi = smem + s * a_stride;
         uint8_t *a_lo = a_hi + A_HALF_BYTES;
 #pragma unroll
-        for (int ps = 0; ps < ROWS_PER_THREAD; ++ps) {
-            const int row = row0 + ROW_STEP * ps;
-            const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
+        for (int ps = 0; ps < RPT; ++ps) {
             float4 v = pd[ps];
-            if (AMODE == AMODE_GATHER) {
+            if (GATHER) {
                 v.x = fmaxf(v.x + qd[ps].x, 0.f); v.y = fmaxf(v.y + qd[ps].y, 0.f);
                 v.z = fmaxf(v.z + qd[ps].z, 0.f); v.w = fmaxf(v.w + qd[ps].w, 0.f);
             }
-            // hi = x with the 13 low mantissa bits cleared (an exact TF32 value), lo = x - hi (exact in fp32; the
-            // tensor core reads its top 10 mantissa bits).  |lo| < 2^-10 |x|, so hi*hi + hi*lo + lo*hi is x*y to ~2^-20.
+            if (KIND == KIND_F16) { v.x *= a_scale; v.y *= a_scale; v.z *= a_scale; v.w *= a_scale; }
+            // hi = x with the 13 low mantissa bits cleared: 11 significant bits, exact both as TF32 and (inside the
+            // normal range the scale guarantees) as FP16; lo = x - hi is exact in fp32 and |lo| < 2^-10 |x|, so
+            // hi*hi + hi*lo + lo*hi reproduces x*y to ~2^-21.
             float4 h, l;
             h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
             l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-            *reinterpret_cast<float4 *>(a_hi + off) = h;
-            *reinterpret_cast<float4 *>(a_lo + off) = l;
-        }
-        fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) arrive(s);
-        tr(3);
-        if (++s == S) { s = 0; wait_ph ^= 1; }
-    };
-
-    // prefetch cursor (pt, pkc): next chunk of this CTA's stream whose loads have not been issued yet
-    int pt = tm.first, pkc = 0;
-    const int my_tiles = tm.my_tiles();
-    long long remaining = (long long)my_tiles * nK;      // chunks still to be stored
-    auto prefetch_into = [&](float4 (&pd)[ROWS_PER_THREAD], float4 (&qd)[ROWS_PER_THREAD]) {
-        if (pt >= tm.total) return;
-        if (pkc == 0) {
-            if (pt == tm.first) fetch_indices(tm.decode(pt));
-            setup_rows(tm.decode(pt));           // its indices were fetched one tile ago
-            if (pt + tm.step < tm.total) fetch_indices(tm.decode(pt + tm.step));
-        }
-        load_raw(pkc, pd, qd);
-        if (++pkc == nK) { pkc = 0; pt += tm.step; }
-    };
-#pragma unroll
-    for (int u = 0; u < DEPTH - 1; ++u) prefetch_into(pbuf[u], qbuf[(AMODE == AMODE_GATHER) ? u : 0]);
-    while (remaining > 0) {
-#pragma unroll
-        for (int u = 0; u < DEPTH; ++u) {
-            if (remaining > 0) {
-                constexpr int dummy = 0;
-                (void)dummy;
-                const int w = (u + DEPTH - 1) % DEPTH;       // ring slot that becomes free for the next prefetch
-                prefetch_into(pbuf[w], qbuf[(AMODE == AMODE_GATHER) ? w : 0]);
-                store_stage(pbuf[u], qbuf[(AMODE == AMODE_GATHER) ? u : 0]);
-                --remaining;
+            if (KIND == KIND_F16) {
+                const uint32_t off = soff[ps] ^ (us ? 64u : 0u);     // unit 1 = the other half of the swizzled row
+                *reinterpret_cast<uint2 *>(a_hi + off) = make_uint2(pack_h2(h.x, h.y), pack_h2(h.z, h.w));
+                *reinterpret_cast<uint2 *>(a_lo + off) = make_uint2(pack_h2(l.x, l.y), pack_h2(l.z, l.w));
+            } else {
+                *reinterpret_cast<float4 *>(a_hi + soff[ps]) = h;
+                *reinterpret_cast<float4 *>(a_lo + soff[ps]) = l;
             }
         }
+        if (us == UPS - 1) {
+            fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) arrive(s);
+            tr(3);
+            if (++s == S) { s = 0; wait_ph ^= 1; }
+        }
+    };
+
+    float4 pb0[RPT], pb1[RPT];
+    float4 qb0[GATHER ? RPT : 1], qb1[GATHER ? RPT : 1];
+    long long remaining = (long long)tm.my_tiles() * nU;      // units still to be stored
+    issue(pb0, qb0);
+    issue(pb1, qb1);
+    while (remaining > 0) {
+        store_unit(0, pb0, qb0);
+        issue(pb0, qb0);
+        if (remaining > 1) {
+            store_unit(1, pb1, qb1);
+            issue(pb1, qb1);
+        }
+        remaining -= 2;
     }
 }
 
@@ -383,11 +444,11 @@ __device__ __forceinline__ void producer_role(const GemmP &p, uint8_t *smem, uin
 // heads and flushed at segment tails, and every global access is a coalesced 128-byte row segment.
 // `release(buf)` hands the accumulator buffer back to the MMA issuer.
 template <int BN, int EPI, class Release>
-__device__ __forceinline__ void epilogue_role(const GemmP &p, float *stg_all, uint8_t *aux, uint32_t aux_addr,
+__device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, float *stg_all, uint8_t *aux, uint32_t aux_addr,
                                               uint32_t tmem_base, int M, const TileMap &tm, int warp, int lane,
                                               Release release, long long *trace = nullptr) {
     constexpr int NB = BN / 32;                  // 32-column blocks per tile
-    constexpr int MYB = (NB + 1) / 2;            // blocks handled by this warp: cb = half, half + 2, ...
+    static_assert(NB >= 2, "two epilogue warps share every TMEM lane quarter");   // this warp: cb = half, half + 2, ...
     const int e = warp - PRODUCER_WARPS;         // epilogue warp 0..7
     const int q = warp & 3;                      // TMEM lane quarter this warp may read (hardware: warp id % 4)
     const int half = e >> 2;
@@ -423,8 +484,7 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float *stg_all, ui
     int key_cur = load_key(tm.first);
     int key_nxt = load_key(tm.first + tm.step);
     Flags fl_cur = make_flags(tm.first, key_cur);
-    int cached_ntile = -1;
-    float bias_r[MYB], scale_r[MYB], shift_r[MYB];   // per-column constants of this lane's column in each of my blocks
+    float amax_l = 0.f;                              // max |stored value| seen by this lane (GemmP::amax_out)
 
     int li = 0;
     for (int t = tm.first; t < tm.total; t += tm.step, ++li) {
@@ -444,18 +504,12 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float *stg_all, ui
         const size_t frame_base = (EPI == EPI_SEGMAX) ? (size_t)tcd.frame * p.n_vtx_frame : 0;
         __syncwarp();
         stg[lane * STG_LD + 32] = __int_as_float(key);
-        if (tcd.n_tile != cached_ntile) {
-            cached_ntile = tcd.n_tile;
-#pragma unroll
-            for (int i = 0; i < MYB; ++i) {
-                const int nl = n0 + (half + 2 * i) * 32 + lane;
-                const bool ok = (half + 2 * i < NB) && nl < p.N;
-                bias_r[i] = (ok && p.bias) ? p.bias[nl] : 0.f;
-                scale_r[i] = (ok && p.scale) ? p.scale[nl] : 1.f;
-                shift_r[i] = (ok && p.shift) ? p.shift[nl] : 0.f;
-            }
-        }
-        const bool relu = (EPI == EPI_SEGMAX) || p.relu;
+        const float relu_floor = ((EPI == EPI_SEGMAX) || p.relu) ? 0.f : neg_inf();
+        const bool has_rb = (EPI == EPI_STORE) && p.rowbias != nullptr;
+        const uint32_t tails = fl.tail_mask;
+        // fast path: a full 32-row block (all but the last tile) and, for the dense epilogue, a single segment
+        // (tiles that straddle two graphs of the batch take the general path)
+        const bool fast = valid_rows == 32 && (EPI == EPI_SEGMAX || tails == 0x80000000u);
 
         tr(10);
         mbar_wait(aux_addr + AUX_ACC_FULL + 8u * buf, (uint32_t)((li >> 1) & 1));
@@ -463,58 +517,105 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float *stg_all, ui
         tc_fence_after();
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
         uint32_t v[32];
-        if (half < NB) tmem_ld32_issue(tbase + (uint32_t)(half * 32), v);
+        tmem_ld32_issue(tbase + (uint32_t)(half * 32), v);
+        // The block loop is deliberately NOT unrolled: the walk below is ~400 instructions of straight-line code and
+        // sixteen warps of two roles share the instruction cache.
+#pragma unroll 1
+        for (int cb = half; cb < NB; cb += 2) {
+            const int col0 = cb * 32;
+            const int nl = n0 + col0 + lane;
+            const bool nl_ok = nl < p.N;
+            // per-column constants (L1/L2 hits; their latency hides behind the accumulator load and the transposition)
+            const float bias_l = (nl_ok && p.bias) ? p.bias[nl] : 0.f;
+            const float scale_l = (nl_ok && p.scale) ? p.scale[nl] : 1.f;
+            const float shift_l = (nl_ok && p.shift) ? p.shift[nl] : 0.f;
+            tmem_ld_wait(v);
+            tr(13);
+            __syncwarp();                        // previous block's reads of the staging tile are done
 #pragma unroll
-        for (int i = 0; i < MYB; ++i) {
-            const int cb = half + 2 * i;
-            if (cb < NB) {                       // warp-uniform (only BN = 32 * odd would skip; kept for safety)
-                const int col0 = cb * 32;
-                tmem_ld_wait(v);
-                tr(13);
-                __syncwarp();                    // previous block's reads of the staging tile are done
+            for (int j = 0; j < 32; ++j) stg[lane * STG_LD + j] = __uint_as_float(v[j]);
+            __syncwarp();
+            tr(14);
+            if (cb + 2 < NB) tmem_ld32_issue(tbase + (uint32_t)(col0 + 64), v);   // overlaps this block's walk
+            // lane = column from here on; rows of this column are read back from the staging tile
+            float *crow = (EPI == EPI_STORE && p.C) ? p.C + (size_t)rbase * p.ldc + nl : nullptr;
+            auto seg_key = [&](int r) { return __float_as_int(stg[r * STG_LD + 32]); };
+            auto flush = [&](int r, float m) {              // the segment ending at row r is complete (warp-uniform call)
+                if (!nl_ok) return;
+                const int k_seg = seg_key(r);
+                if (EPI == EPI_SEGMAX) {
+                    float *dst = p.C + (frame_base + k_seg) * (size_t)p.ldc + nl;
+                    if ((fl.complete_mask >> r) & 1u) *dst = m;
+                    else atomic_max_f32(dst, m);
+                } else if (p.pool) {
+                    atomic_max_f32(p.pool + (size_t)k_seg * p.ldpool + nl, m);
+                }
+            };
+            if (fast) {
+                // Branch-free straight-line code over the 32 rows.  Segment boundaries are warp-uniform bit masks
+                // (every lane walks the same rows): the running max restarts at heads, its value after every row goes
+                // back to the staging tile (this lane's own column), and a short loop over the tails flushes results.
+                const uint32_t heads = (tails << 1) | 1u;
+                float b_cur = bias_l;
+                if (has_rb && nl_ok) {
+                    const int k_seg = seg_key(31);
+                    if (k_seg >= 0) b_cur += p.rowbias[(size_t)k_seg * p.ldrb + nl];
+                }
+                float m = neg_inf();
+                float am_blk = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) stg[lane * STG_LD + j] = __uint_as_float(v[j]);
-                __syncwarp();
-                tr(14);
-                if (cb + 2 < NB) tmem_ld32_issue(tbase + (uint32_t)(col0 + 64), v);   // overlaps this block's walk
-                // lane = column from here on: walk the rows of this column segment by segment (few segments per
-                // warp: one per CSR target / graph), reading the transposed block back from the staging tile
-                const int nl = n0 + col0 + lane;
-                const bool nl_ok = nl < p.N;
-                const float bias_l = bias_r[i], scale_l = scale_r[i], shift_l = shift_r[i];
-                float *crow = (EPI == EPI_STORE && p.C) ? p.C + (size_t)rbase * p.ldc + nl : nullptr;
-                uint32_t tails = fl.tail_mask;
+                for (int hb = 0; hb < 2; ++hb) {
+                    float xr[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) xr[j] = stg[(hb * 16 + j) * STG_LD + lane];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int r = hb * 16 + j;
+                        const float x = fmaxf(fmaf(xr[j], inv, b_cur), relu_floor);   // inv undoes the fp16 operand scales
+                        const float z = fmaf(x, scale_l, shift_l);       // BatchNorm affine BEFORE any max (scale may be < 0)
+                        am_blk = fmaxf(am_blk, fabsf(z));
+                        if (EPI == EPI_STORE) {
+                            if (crow && nl_ok) crow[(size_t)r * p.ldc] = z;
+                            m = fmaxf(m, z);
+                        } else {
+                            m = fmaxf(((heads >> r) & 1u) ? neg_inf() : m, z);
+                            stg[r * STG_LD + lane] = m;
+                        }
+                    }
+                }
+                if (nl_ok) amax_l = fmaxf(amax_l, am_blk);
+                if (EPI == EPI_STORE) {
+                    flush(31, m);
+                } else {
+                    uint32_t tl = tails;
+                    while (tl) {
+                        const int r = __ffs(tl) - 1;
+                        flush(r, stg[r * STG_LD + lane]);
+                        tl &= tl - 1;
+                    }
+                }
+            } else {
+                // general path (ragged last tile, tiles that straddle graphs): walk segment by segment
+                uint32_t tl = tails;
                 int rr = 0;
                 while (rr < valid_rows) {
-                    const int seg_end = tails ? (__ffs(tails) - 1) : (valid_rows - 1);
-                    const int k_seg = __float_as_int(stg[seg_end * STG_LD + 32]);
+                    const int seg_end = tl ? (__ffs(tl) - 1) : (valid_rows - 1);
+                    const int k_seg = seg_key(seg_end);
                     float b_seg = bias_l;
-                    if (EPI == EPI_STORE && p.rowbias && nl_ok && k_seg >= 0) b_seg += p.rowbias[(size_t)k_seg * p.ldrb + nl];
+                    if (has_rb && nl_ok && k_seg >= 0) b_seg += p.rowbias[(size_t)k_seg * p.ldrb + nl];
                     float m = neg_inf();
-#pragma unroll 8
                     for (; rr <= seg_end; ++rr) {
-                        float x = stg[rr * STG_LD + lane] + b_seg;
-                        if (relu) x = fmaxf(x, 0.f);
-                        const float z = fmaf(x, scale_l, shift_l);  // BatchNorm affine BEFORE any max (scale may be < 0)
-                        if (EPI == EPI_STORE && crow) {
-                            if (nl_ok) *crow = z;
-                            crow += p.ldc;
-                        }
+                        const float x = fmaxf(fmaf(stg[rr * STG_LD + lane], inv, b_seg), relu_floor);
+                        const float z = fmaf(x, scale_l, shift_l);
+                        if (nl_ok) amax_l = fmaxf(amax_l, fabsf(z));
+                        if (EPI == EPI_STORE && crow && nl_ok) crow[(size_t)rr * p.ldc] = z;
                         m = fmaxf(m, z);
                     }
-                    if (nl_ok && tails) {
-                        if (EPI == EPI_SEGMAX) {
-                            float *dst = p.C + (frame_base + k_seg) * (size_t)p.ldc + nl;
-                            if ((fl.complete_mask >> seg_end) & 1u) *dst = m;
-                            else atomic_max_f32(dst, m);
-                        } else if (p.pool) {
-                            atomic_max_f32(p.pool + (size_t)k_seg * p.ldpool + nl, m);
-                        }
-                    }
-                    tails &= tails - 1;
+                    if (tl) flush(seg_end, m);
+                    tl &= tl - 1;
                 }
-                tr(16);
             }
+            tr(16);
         }
         tr(17);
         tc_fence_before();
@@ -522,12 +623,13 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float *stg_all, ui
         if (lane == 0) release(buf);             // buffer may be overwritten by tile li + 2
         tr(12);
     }
+    if (EPI == EPI_SEGMAX || p.C) amax_commit(p.amax_out, amax_l);
 }
 
 // =============================================================================================================
 // cta_group::1 kernel: UMMA 128 x BN
 // =============================================================================================================
-template <int BN, int AMODE, int EPI>
+template <int KIND, int BN, int AMODE, int EPI>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
     using C = Cfg<BN>;
     const GemmP &p = tp.g;
@@ -561,6 +663,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
     TileMap tm;
     tm.ntn = tp.ntn; tm.ntm = ntm; tm.total = tp.ntn * ntm * tp.frames;
     tm.first = blockIdx.x; tm.step = gridDim.x; tm.mult = 1; tm.rank = 0;
+    float a_scale, inv;
+    operand_scales<KIND>(p, AMODE == AMODE_GATHER, a_scale, inv);
 
     if (warp == CONTROL_WARP) {
         if (lane == 0) {
@@ -591,7 +695,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
         if (warp == CONTROL_WARP) {
             const bool leader = lane == 0;
             Tracer tr{(tp.trace && blockIdx.x == 0 && leader) ? tp.trace + 2048 : nullptr, 0};
-            const uint32_t idesc = make_idesc(BM, BN);
+            const uint32_t idesc = make_idesc<KIND>(BM, BN);
             const uint32_t b_bytes = (uint32_t)C::B_CHUNK_BYTES;
             const uint8_t *gB = reinterpret_cast<const uint8_t *>(tp.Bblob);
             const int my_tiles = tm.my_tiles();
@@ -647,10 +751,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
                     const uint32_t lbh = desc_lo(b_hi), lbl = desc_lo(b_hi + C::B_HALF_BYTES);
                     if (leader) {
 #pragma unroll
-                        for (int k = 0; k < KC / 8; ++k) {           // 8 tf32 = 32 bytes along the swizzled row
-                            umma_tf32<1>(tmem_d, desc64(lal + 2 * k), desc64(lbh + 2 * k), idesc, (kc | k) != 0);
-                            umma_tf32<1>(tmem_d, desc64(lah + 2 * k), desc64(lbl + 2 * k), idesc, 1);
-                            umma_tf32<1>(tmem_d, desc64(lah + 2 * k), desc64(lbh + 2 * k), idesc, 1);
+                        for (int k = 0; k < 4; ++k) {                // 8 tf32 / 16 fp16 = 32 bytes along the swizzled row
+                            umma<KIND, 1>(tmem_d, desc64(lal + 2 * k), desc64(lbh + 2 * k), idesc, (kc | k) != 0);
+                            umma<KIND, 1>(tmem_d, desc64(lah + 2 * k), desc64(lbl + 2 * k), idesc, 1);
+                            umma<KIND, 1>(tmem_d, desc64(lah + 2 * k), desc64(lbh + 2 * k), idesc, 1);
                         }
                         umma_commit<1>(bar_m(s));                    // frees stage s when these MMAs retire
                     }
@@ -670,11 +774,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
         }
     } else if (warp < PRODUCER_WARPS) {
         reg_inc<REGS_PRODUCER>();
-        producer_role<AMODE>(p, smem, a_stride, aux_addr, S, nK, M, tm, tid, lane,
-                             [&](int s) { mbar_arrive(bar_a(s)); }, tp.trace);
+        producer_role<KIND, AMODE>(p, a_scale, smem, a_stride, aux_addr, S, nK, M, tm, tid, lane,
+                                   [&](int s) { mbar_arrive(bar_a(s)); }, tp.trace);
     } else {
-        reg_dec<REGS_EPILOGUE>();
-        epilogue_role<BN, EPI>(p, stg_all, aux, aux_addr, tmem_base, M, tm, warp, lane,
+        reg_inc<REGS_EPILOGUE>();
+        epilogue_role<BN, EPI>(p, inv, stg_all, aux, aux_addr, tmem_base, M, tm, warp, lane,
                                [&](int b) { mbar_arrive(bar_acce(b)); }, tp.trace);
     }
     tc_fence_before();
@@ -688,30 +792,44 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
 // collect the arrivals of both CTAs, and tcgen05.commit multicasts completions to both.
 // =============================================================================================================
 template <int BN2> struct Cfg2 {
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + 2 * (BN2 / 2) * 128;    // 32 KB A + this CTA's half weight chunk
+    static constexpr int HALF_B = (BN2 / 2) * 128;                              // this CTA's rows of the hi (or lo) image
+    static constexpr int B_BYTES = 2 * HALF_B;                                  // this CTA's share of one weight chunk
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_BYTES;                 // 32 KB A + half weight chunk
     static constexpr int STAGES = (PIPE_BYTES / STAGE_BYTES) > 4 ? 4 : (PIPE_BYTES / STAGE_BYTES);   // 3 (BN 256) / 4 (BN 128)
+    // resident-B mode: the pair sees one n-tile for the whole kernel and each CTA keeps its half of all k-chunks
+    static constexpr int res_stages(int nK) {
+        const int left = PIPE_BYTES - nK * B_BYTES;
+        const int s = left / A_STAGE_BYTES;
+        return s > 4 ? 4 : s;
+    }
 };
 
-template <int BN2, int AMODE, int EPI>
+template <int KIND, int BN2, int AMODE, int EPI>
 __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
+    using C2 = Cfg2<BN2>;
     const GemmP &p = tp.g;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (base - raw_addr);
     const int nK = tp.nK;
-    constexpr int S = Cfg2<BN2>::STAGES;
-    constexpr int STAGE2_BYTES = Cfg2<BN2>::STAGE_BYTES;
-    constexpr uint32_t HALF_B = (BN2 / 2) * 128;                        // 16 KB: this CTA's rows of the hi (or lo) image
+    const int S = tp.stages;
+    const bool resb = tp.resident_b != 0;
+    constexpr uint32_t HALF_B = C2::HALF_B;
+    // stage s: A image at s * a_stride; this CTA's half weight chunk behind it (streaming) or, resident, chunk kc
+    // at b_region + kc * B_BYTES
+    const uint32_t a_stride = resb ? (uint32_t)A_STAGE_BYTES : (uint32_t)C2::STAGE_BYTES;
+    const uint32_t b_region = resb ? (uint32_t)(S * A_STAGE_BYTES) : (uint32_t)A_STAGE_BYTES;
+    const uint32_t b_stride = resb ? (uint32_t)C2::B_BYTES : (uint32_t)C2::STAGE_BYTES;
     float *stg_all = reinterpret_cast<float *>(smem + PIPE_BYTES);
     uint8_t *aux = smem + PIPE_BYTES + STG_BYTES;
     const uint32_t aux_addr = base + PIPE_BYTES + STG_BYTES;
-    auto bar_a = [&](int s) { return aux_addr + AUX_A_FULL + 8u * s; };        // leader: 16 producer warps
+    auto bar_a = [&](int s) { return aux_addr + AUX_A_FULL + 8u * s; };        // leader: 8 producer warps of the pair
     auto bar_b = [&](int s) { return aux_addr + AUX_B_FULL + 8u * s; };        // local: this CTA's half chunk landed
     auto bar_bp = [&](int s) { return aux_addr + AUX_B_PEER + 8u * s; };       // leader: the peer's half landed
     auto bar_m = [&](int s) { return aux_addr + AUX_MMA_DONE + 8u * s; };      // local copy of the multicast commit
     auto bar_accf = [&](int b) { return aux_addr + AUX_ACC_FULL + 8u * b; };   // local copy of the multicast commit
-    auto bar_acce = [&](int b) { return aux_addr + AUX_ACC_EMPTY + 8u * b; };  // leader: 8 epilogue warps
+    auto bar_acce = [&](int b) { return aux_addr + AUX_ACC_EMPTY + 8u * b; };  // leader: 16 epilogue warps of the pair
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(aux + AUX_TMEM_PTR);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -722,10 +840,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
     TileMap tm;
     tm.ntn = tp.ntn; tm.ntm = (ntm + 1) / 2; tm.total = tp.ntn * tm.ntm * tp.frames;
     tm.first = blockIdx.x >> 1; tm.step = gridDim.x >> 1; tm.mult = 2; tm.rank = (int)rank;
+    float a_scale, inv;
+    operand_scales<KIND>(p, AMODE == AMODE_GATHER, a_scale, inv);
 
     if (warp == CONTROL_WARP) {
         if (lane == 0) {
-            for (int s = 0; s < S; ++s) {
+            for (int s = 0; s < 4; ++s) {
                 mbar_init(bar_a(s), 2 * PRODUCER_WARPS);
                 mbar_init(bar_b(s), 1);
                 mbar_init(bar_bp(s), 1);
@@ -754,13 +874,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
             const uint32_t chunk_bytes = 2u * BN2 * 128;           // full hi|lo image of one k-chunk in global memory
             const int my_tiles = tm.my_tiles();
             int f_li = 0, f_kc = 0, f_s = 0, f_ntile = (my_tiles > 0) ? tm.decode(tm.first).n_tile : 0;
-            auto fetch_next = [&]() {                              // this CTA's 128 rows of the hi and of the lo image
-                const uint32_t dst = base + f_s * STAGE2_BYTES + A_STAGE_BYTES;
-                const uint8_t *src = gB + ((size_t)f_ntile * nK + f_kc) * chunk_bytes + rank * HALF_B;
+            // this CTA's 128 (64) rows of the hi and of the lo image of chunk (n_tile, kc) -> dst
+            auto fetch_chunk = [&](uint32_t dst, int n_tile, int kc, uint32_t bar) {
+                const uint8_t *src = gB + ((size_t)n_tile * nK + kc) * chunk_bytes + rank * HALF_B;
+                bulk_g2s(dst, src, HALF_B, bar);
+                bulk_g2s(dst + HALF_B, src + BN2 * 128, HALF_B, bar);
+            };
+            auto fetch_next = [&]() {                              // streaming mode only
                 if (leader) {
                     mbar_arrive_expect_tx(bar_b(f_s), 2 * HALF_B);
-                    bulk_g2s(dst, src, HALF_B, bar_b(f_s));
-                    bulk_g2s(dst + HALF_B, src + BN2 * 128, HALF_B, bar_b(f_s));
+                    fetch_chunk(base + b_region + f_s * b_stride, f_ntile, f_kc, bar_b(f_s));
                 }
                 if (++f_s == S) f_s = 0;
                 if (++f_kc == nK) {
@@ -769,63 +892,83 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
                     if (f_li < my_tiles) f_ntile = tm.decode(tm.first + f_li * tm.step).n_tile;
                 }
             };
-            for (int i = 0; i < S - 1 && f_li < my_tiles; ++i) fetch_next();
+            if (resb) {
+                if (my_tiles > 0) {
+                    if (leader) {
+                        mbar_arrive_expect_tx(bar_b(0), 2 * HALF_B * (uint32_t)nK);
+                        for (int kc = 0; kc < nK; ++kc) fetch_chunk(base + b_region + kc * b_stride, f_ntile, kc, bar_b(0));
+                    }
+                    mbar_wait(bar_b(0), 0);
+                    if (rank == 0) mbar_wait<true>(bar_bp(0), 0);          // the peer's half image landed too
+                    else if (leader) mbar_arrive_cluster(bar_bp(0), 0);
+                }
+            } else {
+                for (int i = 0; i < S - 1 && f_li < my_tiles; ++i) fetch_next();
+            }
             int s = 0, prev_s = 0;
             uint32_t ph = 0, prev_ph = 0;
             bool first = true;
-            const uint32_t idesc = make_idesc(2 * BM, BN2);
-            for (int li = 0; li < my_tiles; ++li) {
-                const int buf = li & 1;
-                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN2);
-                if (rank == 0) {
-                    mbar_wait<true>(bar_acce(buf), ((li >> 1) & 1) ^ 1);   // both CTAs drained this accumulator
-                    tc_fence_after();
-                }
-                for (int kc = 0; kc < nK; ++kc) {
-                    mbar_wait(bar_b(s), ph);                               // own half chunk landed
+            const uint32_t idesc = make_idesc<KIND>(2 * BM, BN2);
+            Tracer tr{(tp.trace && blockIdx.x == 0 && leader) ? tp.trace + 2048 : nullptr, 0};
+            if (!(resb && rank != 0)) {                            // resident mode: the peer's control warp is done
+                for (int li = 0; li < my_tiles; ++li) {
+                    const int buf = li & 1;
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN2);
                     if (rank == 0) {
-                        mbar_wait<true>(bar_bp(s), ph);                    // peer's half chunk landed
-                        mbar_wait<true>(bar_a(s), ph);                     // A images of both CTAs written
+                        tr(20);
+                        mbar_wait<true>(bar_acce(buf), ((li >> 1) & 1) ^ 1);   // both CTAs drained this accumulator
+                        tr(21);
                         tc_fence_after();
-                        const uint32_t a_hi = base + s * STAGE2_BYTES;
-                        const uint32_t b_hi = a_hi + A_STAGE_BYTES;
-                        const uint32_t lah = desc_lo(a_hi), lal = desc_lo(a_hi + A_HALF_BYTES);
-                        const uint32_t lbh = desc_lo(b_hi), lbl = desc_lo(b_hi + HALF_B);
-                        if (leader) {
+                    }
+                    for (int kc = 0; kc < nK; ++kc) {
+                        if (!resb) mbar_wait(bar_b(s), ph);                    // own half chunk landed
+                        if (rank == 0) {
+                            if (!resb) mbar_wait<true>(bar_bp(s), ph);         // peer's half chunk landed
+                            tr(23);
+                            mbar_wait<true>(bar_a(s), ph);                     // A images of both CTAs written
+                            tr(22);
+                            tc_fence_after();
+                            const uint32_t a_hi = base + s * a_stride;
+                            const uint32_t b_hi = base + b_region + (resb ? kc : s) * b_stride;
+                            const uint32_t lah = desc_lo(a_hi), lal = desc_lo(a_hi + A_HALF_BYTES);
+                            const uint32_t lbh = desc_lo(b_hi), lbl = desc_lo(b_hi + HALF_B);
+                            if (leader) {
 #pragma unroll
-                            for (int k = 0; k < KC / 8; ++k) {
-                                umma_tf32<2>(tmem_d, desc64(lal + 2 * k), desc64(lbh + 2 * k), idesc, (kc | k) != 0);
-                                umma_tf32<2>(tmem_d, desc64(lah + 2 * k), desc64(lbl + 2 * k), idesc, 1);
-                                umma_tf32<2>(tmem_d, desc64(lah + 2 * k), desc64(lbh + 2 * k), idesc, 1);
+                                for (int k = 0; k < 4; ++k) {
+                                    umma<KIND, 2>(tmem_d, desc64(lal + 2 * k), desc64(lbh + 2 * k), idesc, (kc | k) != 0);
+                                    umma<KIND, 2>(tmem_d, desc64(lah + 2 * k), desc64(lbl + 2 * k), idesc, 1);
+                                    umma<KIND, 2>(tmem_d, desc64(lah + 2 * k), desc64(lbh + 2 * k), idesc, 1);
+                                }
+                                umma_commit<2>(bar_m(s));                      // both CTAs: stage s free when retired
                             }
-                            umma_commit<2>(bar_m(s));                      // both CTAs: stage s free when retired
+                            tr(24);
+                        } else if (leader) {
+                            mbar_arrive_cluster(bar_bp(s), 0);                 // tell the leader CTA
                         }
-                    } else if (leader) {
-                        mbar_arrive_cluster(bar_bp(s), 0);                 // tell the leader CTA
+                        if (!resb && f_li < my_tiles) {
+                            if (!first) mbar_wait(bar_m(prev_s), prev_ph);     // previous chunk's MMAs retired (multicast)
+                            fetch_next();
+                        }
+                        first = false;
+                        prev_s = s; prev_ph = ph;
+                        if (++s == S) { s = 0; ph ^= 1; }
                     }
-                    if (f_li < my_tiles) {
-                        if (!first) mbar_wait(bar_m(prev_s), prev_ph);     // previous chunk's MMAs retired (multicast)
-                        fetch_next();
-                    }
-                    first = false;
-                    prev_s = s; prev_ph = ph;
-                    if (++s == S) { s = 0; ph ^= 1; }
+                    if (rank == 0 && leader) umma_commit<2>(bar_accf(buf));    // both CTAs: accumulator complete
                 }
-                if (rank == 0 && leader) umma_commit<2>(bar_accf(buf));    // both CTAs: accumulator complete
             }
         }
     } else if (warp < PRODUCER_WARPS) {
         reg_inc<REGS_PRODUCER>();
-        producer_role<AMODE>(p, smem, (uint32_t)STAGE2_BYTES, aux_addr, S, nK, M, tm, tid, lane, [&](int s) {
+        producer_role<KIND, AMODE>(p, a_scale, smem, a_stride, aux_addr, S, nK, M, tm, tid, lane, [&](int s) {
             if (rank == 0) mbar_arrive(bar_a(s));
             else mbar_arrive_cluster(bar_a(s), 0);
-        });
+        }, tp.trace);
     } else {
-        reg_dec<REGS_EPILOGUE>();
-        epilogue_role<BN2, EPI>(p, stg_all, aux, aux_addr, tmem_base, M, tm, warp, lane, [&](int b) {
+        reg_inc<REGS_EPILOGUE>();
+        epilogue_role<BN2, EPI>(p, inv, stg_all, aux, aux_addr, tmem_base, M, tm, warp, lane, [&](int b) {
             if (rank == 0) mbar_arrive(bar_acce(b));
             else mbar_arrive_cluster(bar_acce(b), 0);
-        });
+        }, tp.trace);
     }
     tc_fence_before();
     __syncthreads();

@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float *__restr
                                                             int D, const float *__restrict__ u,
                                                             const float *__restrict__ l0, const float *__restrict__ Mv,
                                                             const float *__restrict__ c0, float *__restrict__ out,
-                                                            int ldo) {
+                                                            int ldo, float *out_amax) {
     extern __shared__ float s_mv[];                 // [heads][C][D]  (transposed for lane-contiguous reads)
     for (int idx = threadIdx.x; idx < heads * C * D; idx += blockDim.x) {
         const int h = idx / (C * D), rem = idx % (C * D), cc = rem / D, dd = rem % D;
@@ -26,7 +26,8 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float *__restr
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (n >= N) return;
+    if (n >= N) return;                             // whole warps leave together
+    float am = 0.f;
     float xt[ATT_MAX_T];
 #pragma unroll
     for (int t = 0; t < ATT_MAX_T; ++t) xt[t] = (t < T && lane < C) ? x[((size_t)n * T + t) * C + lane] : 0.f;
@@ -72,7 +73,9 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float *__restr
                 o = fmaf(__shfl_sync(0xffffffffu, y[h], cc), s_mv[(h * C + cc) * D + d], o);
         }
         out[(size_t)n * ldo + d] = o;
+        am = fmaxf(am, fabsf(o));
     }
+    amax_commit(out_amax, am);
 }
 
 // ---- F.normalize(dim=1): warp per row ------------------------------------------------------------
@@ -108,14 +111,27 @@ __global__ void frame_reduce_kernel(const float *__restrict__ x, int N, int T, i
 
 __global__ void gather_cols_kernel(const float *__restrict__ src, int lds, int src_off, int frame_stride,
                                    const int32_t *__restrict__ cols, int C, int N, int n_frames, float *dst, int ldd,
-                                   int dst_off) {
+                                   int dst_off, float *dst_amax) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)N * n_frames * C) return;
-    const int c = (int)(idx % C);
-    const int64_t r = idx / C;
-    const int f = (int)(r / N), v = (int)(r % N);
-    const int sc = src_off + f * frame_stride + (cols ? cols[c] : c);
-    dst[(size_t)r * ldd + dst_off + c] = src[(size_t)v * lds + sc];
+    float val = 0.f;
+    if (idx < (int64_t)N * n_frames * C) {
+        const int c = (int)(idx % C);
+        const int64_t r = idx / C;
+        const int f = (int)(r / N), v = (int)(r % N);
+        const int sc = src_off + f * frame_stride + (cols ? cols[c] : c);
+        val = src[(size_t)v * lds + sc];
+        dst[(size_t)r * ldd + dst_off + c] = val;
+    }
+    amax_commit(dst_amax, fabsf(val));
+}
+
+// grid-stride max |x| of a strided [R, C] block
+__global__ void __launch_bounds__(256) absmax_kernel(const float *__restrict__ x, int ldx, int R, int C, float *amax) {
+    const int64_t total = (int64_t)R * C;
+    float am = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        am = fmaxf(am, fabsf(x[(size_t)(i / C) * ldx + (i % C)]));
+    amax_commit(amax, am);
 }
 
 __global__ void fill_kernel(float *dst, int64_t n, float value) {
@@ -130,7 +146,7 @@ using namespace morig;
 
 extern "C" MORIG_API int morig_temporal_attn_fwd(const float *x, int32_t N, int32_t T, int32_t C, int32_t heads, int32_t D,
                                        const float *u, const float *l0, const float *Mv, const float *c0, float *out,
-                                       int32_t ldo, void *stream_) {
+                                       int32_t ldo, float *out_amax, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MORIG_CHECK_ARG(x && u && l0 && Mv && c0 && out && N > 0, "temporal_attn_fwd: null operand");
     MORIG_CHECK_ARG(T >= 1 && T <= ATT_MAX_T, "temporal_attn_fwd: T=%d unsupported (1..%d key-frames)", T, ATT_MAX_T);
@@ -140,7 +156,7 @@ extern "C" MORIG_API int morig_temporal_attn_fwd(const float *x, int32_t N, int3
                     "temporal_attn_fwd: D=%d unsupported (multiple of 32)", D);
     const int T_ = 256;
     temporal_attn_kernel<<<ceil_div(N * 32, T_), T_, (size_t)heads * C * D * sizeof(float), stream>>>(
-        x, N, T, C, heads, D, u, l0, Mv, c0, out, ldo);
+        x, N, T, C, heads, D, u, l0, Mv, c0, out, ldo, out_amax);
     MORIG_LAUNCH_CHECK("temporal_attn_kernel");
     return 0;
 }
@@ -166,13 +182,22 @@ extern "C" MORIG_API int morig_frame_reduce(const float *x, int32_t N, int32_t T
 
 extern "C" MORIG_API int morig_gather_cols(const float *src, int32_t lds, int32_t src_off, int32_t frame_stride,
                                  const int32_t *cols, int32_t C, int32_t N, int32_t n_frames, float *dst, int32_t ldd,
-                                 int32_t dst_off, void *stream_) {
+                                 int32_t dst_off, float *dst_amax, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MORIG_CHECK_ARG(src && dst && C > 0 && N > 0 && n_frames > 0, "gather_cols: bad argument");
     const int64_t total = (int64_t)N * n_frames * C;
     gather_cols_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(src, lds, src_off, frame_stride, cols, C, N,
-                                                                            n_frames, dst, ldd, dst_off);
+                                                                            n_frames, dst, ldd, dst_off, dst_amax);
     MORIG_LAUNCH_CHECK("gather_cols_kernel");
+    return 0;
+}
+
+extern "C" MORIG_API int morig_absmax_f32(const float *x, int32_t ldx, int32_t R, int32_t C, float *amax, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MORIG_CHECK_ARG(x && amax && R > 0 && C > 0 && ldx >= C, "absmax_f32: bad argument");
+    const int64_t blocks = ceil_div64((int64_t)R * C, 256 * 8);
+    absmax_kernel<<<(unsigned)(blocks > 148 * 8 ? 148 * 8 : blocks), 256, 0, stream>>>(x, ldx, R, C, amax);
+    MORIG_LAUNCH_CHECK("absmax_kernel");
     return 0;
 }
 

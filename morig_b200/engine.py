@@ -23,7 +23,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import _lib
-from .packing import AttnPack, DenseLayer, EdgeBranch, GCNRigPack, GCUPack, SkinPack
+from .packing import KIND_F16, AttnPack, DenseLayer, EdgeBranch, GCNRigPack, GCUPack, SkinPack
 
 NEG_INF = float("-inf")
 
@@ -33,6 +33,7 @@ class Workspace:
 
     def __init__(self):
         self._bufs: Dict[Tuple, torch.Tensor] = {}
+        self.tracker = AmaxTracker()
 
     def get(self, name: str, shape, device, dtype=torch.float32, zero: bool = False) -> torch.Tensor:
         key = (name, tuple(shape), dtype, str(device))
@@ -47,6 +48,121 @@ class Workspace:
 
     def clear(self):
         self._bufs.clear()
+
+
+class AmaxTracker:
+    """Range bookkeeping for the fp16-split tensor-core layers (csrc/gemm_tc.cuh): one device float per buffer
+    holding max |value| of everything written to it during the current forward.  Kernels of this library raise
+    it while they store (`c_amax` / `out_amax` / `dst_amax` of the C-ABI); for tensors that came from outside
+    (or were last written by a kernel that does not track) `morig_absmax_f32` computes it on demand.  All slots
+    are zeroed by one fill at the start of every forward (`begin`), so results do not depend on history."""
+
+    SLOTS = 256
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+        self.slots: Dict[int, int] = {}
+        self.valid: set = set()
+
+    def begin(self, device) -> None:
+        if self.buf is None or self.buf.device != torch.device(device):
+            self.buf = torch.zeros(self.SLOTS, dtype=torch.float32, device=device)
+            self.slots = {}
+        elif len(self.slots) >= self.SLOTS - 8:
+            self.slots = {}
+        fill(self.buf, 0.0)
+        self.valid = set()
+
+    def _slot(self, t: torch.Tensor) -> int:
+        key = t.untyped_storage().data_ptr()
+        idx = self.slots.get(key)
+        if idx is None:
+            idx = len(self.slots)
+            if idx >= self.SLOTS - 1:
+                raise RuntimeError("morig_b200: out of amax slots")
+            self.slots[key] = idx
+        return idx
+
+    def out_ptr(self, t: torch.Tensor) -> int:
+        """slot address for a kernel that is about to write (part of) `t` and tracks what it stores"""
+        idx = self._slot(t)
+        self.valid.add(idx)
+        return self.buf.data_ptr() + 4 * idx
+
+    def invalidate(self, t: torch.Tensor) -> None:
+        """`t` was written by a kernel that does not track: its next fp16 consumer recomputes the range"""
+        idx = self.slots.get(t.untyped_storage().data_ptr())
+        if idx is not None and idx in self.valid:
+            self.valid.discard(idx)
+            _absmax_reset(self.buf, idx)
+
+    def in_ptr(self, t: torch.Tensor, off: int, ld: int, rows: int, cols: int) -> int:
+        """slot address holding max|t| for an fp16 consumer of the [rows, cols] block at element offset `off`"""
+        idx = self._slot(t)
+        if idx not in self.valid:
+            _absmax(t, off, ld, rows, cols, self.buf, idx)
+            self.valid.add(idx)
+        return self.buf.data_ptr() + 4 * idx
+
+
+_tracker: Optional[AmaxTracker] = None       # set for the duration of one forward (`forward_scope`)
+_scratch: Dict[str, torch.Tensor] = {}       # per-device one-float scratch for calls outside a forward scope
+
+
+class forward_scope:
+    """`with forward_scope(ws, device):` around one top-level forward: activates the workspace's AmaxTracker.
+    Nested scopes (a module's forward called from another module's forward) are no-ops."""
+
+    def __init__(self, ws: "Workspace", device):
+        self.ws, self.device, self.outer = ws, device, False
+
+    def __enter__(self):
+        global _tracker
+        if _tracker is None:
+            self.outer = True
+            _tracker = self.ws.tracker
+            _tracker.begin(self.device)
+        return self
+
+    def __exit__(self, *exc):
+        global _tracker
+        if self.outer:
+            _tracker = None
+        return False
+
+
+def _absmax_reset(buf: torch.Tensor, idx: int) -> None:
+    _lib.check(_lib.load().morig_fill_f32(buf.data_ptr() + 4 * idx, 1, 0.0, _lib.stream_ptr()), "morig_fill_f32")
+    if _counter is not None:
+        _counter.count += 1
+
+
+def _absmax(t: torch.Tensor, off: int, ld: int, rows: int, cols: int, buf: torch.Tensor, idx: int) -> None:
+    tok = _begin("absmax", 1, 0.0, 4.0 * rows * cols) if (_counter is not None or _timer is not None) else None
+    _lib.check(_lib.load().morig_absmax_f32(t.data_ptr() + 4 * off, ld, rows, cols, buf.data_ptr() + 4 * idx,
+                                            _lib.stream_ptr()), "morig_absmax_f32")
+    _end(tok)
+
+
+def _amax_in(t: torch.Tensor, off: int, ld: int, rows: int, cols: int) -> int:
+    if _tracker is not None:
+        return _tracker.in_ptr(t, off, ld, rows, cols)
+    key = str(t.device)                              # direct helper call (tests, micro-benchmarks): always recompute
+    buf = _scratch.get(key)
+    if buf is None:
+        buf = _scratch[key] = torch.zeros(1, dtype=torch.float32, device=t.device)
+    _absmax_reset(buf, 0)
+    _absmax(t, off, ld, rows, cols, buf, 0)
+    return buf.data_ptr()
+
+
+def _amax_out(t: Optional[torch.Tensor]) -> int:
+    return _tracker.out_ptr(t) if (_tracker is not None and t is not None) else 0
+
+
+def _untracked(t: Optional[torch.Tensor]) -> None:
+    if _tracker is not None and t is not None:
+        _tracker.invalidate(t)
 
 
 @dataclass
@@ -241,7 +357,10 @@ def dense(layer: DenseLayer, A: torch.Tensor, a_off: int, lda: int, M: int, *, K
     d.M, d.N, d.K = M, layer.N, (layer.K if K is None else K)
     d.relu = 1 if layer.relu else 0
     if layer.Wtc is not None and d.K == layer.K:
-        d.Wtc, d.tc_bn = layer.Wtc.data_ptr(), layer.tc_bn
+        d.Wtc, d.tc_bn, d.tc_kind, d.tc_w_inv = layer.Wtc.data_ptr(), layer.tc_bn, layer.tc_kind, layer.tc_w_inv
+        if layer.tc_kind == KIND_F16:
+            d.a_amax = _amax_in(A, a_off, lda, M, d.K)
+    d.c_amax = _amax_out(C)
     tok = None
     if _counter is not None or _timer is not None:
         kk = d.K
@@ -262,7 +381,10 @@ def edgeconv(br: EdgeBranch, pq: torch.Tensor, ldpq: int, p_off: int, q_off: int
     d.b1, d.scale, d.shift = br.b1.data_ptr(), br.scale.data_ptr(), br.shift.data_ptr()
     d.out, d.ldo, d.out_off = out.data_ptr(), ldo, out_off
     d.H = br.H
-    d.W1tc = _lib.ptr(br.W1tc)
+    d.W1tc, d.tc_kind, d.tc_w_inv = _lib.ptr(br.W1tc), br.tc_kind, br.tc_w_inv
+    if br.W1tc is not None and br.tc_kind == KIND_F16:
+        d.pq_amax = _amax_in(pq, 0, ldpq, g.n * n_frames, ldpq)
+    d.out_amax = _amax_out(out)
     tok = None
     if _counter is not None or _timer is not None:
         H, e = br.H, g.e_max
@@ -282,8 +404,8 @@ def gather_cols(src: torch.Tensor, lds: int, src_off: int, frame_stride: int, co
                 n: int, n_frames: int, dst: torch.Tensor, ldd: int, dst_off: int) -> None:
     tok = _begin("gather_cols", 1, 0.0, 8.0 * n * n_frames * c) if (_counter is not None or _timer is not None) else None
     _lib.check(_lib.load().morig_gather_cols(src.data_ptr(), lds, src_off, frame_stride, _lib.ptr(cols), c, n,
-                                             n_frames, dst.data_ptr(), ldd, dst_off, _lib.stream_ptr()),
-               "morig_gather_cols")
+                                             n_frames, dst.data_ptr(), ldd, dst_off, _amax_out(dst),
+                                             _lib.stream_ptr()), "morig_gather_cols")
     _end(tok)
 
 
@@ -293,6 +415,8 @@ def row_normalize(x: torch.Tensor, ldx: int, rows: int, c: int, dst2: Optional[t
     _lib.check(_lib.load().morig_row_normalize(x.data_ptr(), ldx, rows, c, _lib.ptr(dst2), n, n_frames,
                                                _lib.stream_ptr()), "morig_row_normalize")
     _end(tok)
+    _untracked(x)
+    _untracked(dst2)
 
 
 # ---- layer sequences -------------------------------------------------------------------------------
@@ -363,7 +487,7 @@ def temporal_attn(pk: AttnPack, x: torch.Tensor, out: torch.Tensor) -> None:
     tok = _begin("temporal_attn", 1, 0.0, 4.0 * n * (t * c + pk.D)) if (_counter is not None or _timer is not None) else None
     _lib.check(_lib.load().morig_temporal_attn_fwd(x.data_ptr(), n, t, c, pk.heads, pk.D, pk.u.data_ptr(),
                                                    pk.l0.data_ptr(), pk.Mv.data_ptr(), pk.c0.data_ptr(),
-                                                   out.data_ptr(), out.shape[1], _lib.stream_ptr()),
+                                                   out.data_ptr(), out.shape[1], _amax_out(out), _lib.stream_ptr()),
                "morig_temporal_attn_fwd")
     _end(tok)
 
@@ -372,6 +496,7 @@ def frame_reduce(x: torch.Tensor, mode: str, out: torch.Tensor) -> None:
     n, t, c = x.shape
     _lib.check(_lib.load().morig_frame_reduce(x.data_ptr(), n, t, c, 0 if mode == "mean" else 1, out.data_ptr(),
                                               out.shape[1], _lib.stream_ptr()), "morig_frame_reduce")
+    _untracked(out)
 
 
 def run_temporal_attn(ws: Workspace, tag: str, pk: AttnPack, x: torch.Tensor, out: torch.Tensor) -> None:

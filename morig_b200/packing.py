@@ -22,6 +22,7 @@ All packed weights are stored transposed, [K, ldw] row-major with ldw a multiple
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -69,28 +70,57 @@ def tc_tile_n(n: int) -> int:
     return 64 if n <= 64 else (128 if n <= 128 else 256)
 
 
-def pack_tc_blob(w_out_in: torch.Tensor, k: int, bn: int) -> torch.Tensor:
-    """Tensor-core image of a Linear weight [N, K'] (fp64): split into TF32 hi + lo (W ~ hi + lo, 3xTF32
-    compensation) and laid out as the byte image of the kernel's shared-memory B stage:
+KIND_TF32, KIND_F16 = 0, 1
 
-        blob[n_tile][k_chunk][half = hi|lo][row n (bn)][16-byte chunk c ^ (n % 8)][4 floats]
 
-    i.e. K-major rows of 32 fp32 (128 bytes) with the SWIZZLE_128B pattern already applied, so that one
-    cp.async.bulk per (n_tile, k_chunk) fills the stage (csrc/gemm_tc.cuh).  K is zero-padded to a multiple
-    of 32 (`k` = the K the kernel will be launched with), N to a multiple of bn."""
+def tc_kind() -> int:
+    """operand kind of the tcgen05 engine: fp16 split (default) or tf32 split (`MORIG_TC_KIND=tf32`)"""
+    v = os.environ.get("MORIG_TC_KIND", "f16").lower()
+    if v not in ("f16", "tf32"):
+        raise ValueError(f"MORIG_TC_KIND={v!r}: expected 'f16' or 'tf32'")
+    return KIND_F16 if v == "f16" else KIND_TF32
+
+
+def pack_tc_blob(w_out_in: torch.Tensor, k: int, bn: int, kind: int = KIND_TF32):
+    """Tensor-core image of a Linear weight [N, K'] (fp64): split W ~ hi + lo (the kernel issues
+    A_lo*B_hi + A_hi*B_lo + A_hi*B_hi) and laid out as the byte image of the kernel's shared-memory B stage:
+
+        blob[n_tile][k_chunk][half = hi|lo][row n (bn)][16-byte chunk c ^ (n % 8)][4 tf32 | 8 fp16]
+
+    i.e. K-major rows of 128 bytes (32 tf32 / 64 fp16) with the SWIZZLE_128B pattern already applied, so that one
+    cp.async.bulk per (n_tile, k_chunk) fills the stage (csrc/gemm_tc.cuh).  K is zero-padded to a multiple of
+    the chunk (`k` = the K the kernel will be launched with), N to a multiple of bn.
+
+    kind TF32: hi = rna_tf32(W), lo = rna_tf32(W - hi).
+    kind F16:  fp16 has a 5-bit exponent, so the image holds W * 2^j with j chosen such that max|W| * 2^j lies in
+               [2^14, 2^15); hi = fp16(W 2^j), lo = fp16(W 2^j - hi).  Elements down to 2^-17 of max|W| keep 22
+               significant bits.  Returns (blob, 2^-j); the kernel's epilogue multiplies by it.
+    Returns (blob, w_inv) with w_inv = 1.0 for TF32."""
     n, kin = w_out_in.shape
-    nk = (k + 31) // 32
+    kc = 64 if kind == KIND_F16 else 32
+    per = kc // 8                                                     # elements per 16-byte chunk
+    nk = (k + kc - 1) // kc
     nt = (n + bn - 1) // bn
-    wp = torch.zeros(nt * bn, nk * 32, dtype=torch.float64, device=w_out_in.device)
+    wp = torch.zeros(nt * bn, nk * kc, dtype=torch.float64, device=w_out_in.device)
     wp[:n, :kin] = w_out_in
-    hi = tf32_rna(wp.to(torch.float32))
-    lo = tf32_rna((wp - hi.to(torch.float64)).to(torch.float32))
-    both = torch.stack([hi, lo], dim=0)                               # [2, nt*bn, nk*32]
-    both = both.reshape(2, nt, bn, nk, 8, 4).permute(1, 3, 0, 2, 4, 5)  # [nt, nk, 2, bn, chunk, 4]
+    w_inv = 1.0
+    if kind == KIND_F16:
+        amax = float(wp.abs().max())
+        j = 14 - math.floor(math.log2(amax)) if amax > 0.0 and math.isfinite(amax) else 0
+        j = max(-100, min(100, j))
+        ws = wp * (2.0 ** j)
+        hi = ws.to(torch.float16)
+        lo = (ws - hi.to(torch.float64)).to(torch.float16)
+        w_inv = 2.0 ** (-j)
+    else:
+        hi = tf32_rna(wp.to(torch.float32))
+        lo = tf32_rna((wp - hi.to(torch.float64)).to(torch.float32))
+    both = torch.stack([hi, lo], dim=0)                               # [2, nt*bn, nk*kc]
+    both = both.reshape(2, nt, bn, nk, 8, per).permute(1, 3, 0, 2, 4, 5)  # [nt, nk, 2, bn, chunk, per]
     rows = torch.arange(bn, device=wp.device)
     src_chunk = torch.arange(8, device=wp.device).unsqueeze(0) ^ (rows % 8).unsqueeze(1)   # dst chunk d holds src d^(n%8)
-    idx = src_chunk.view(1, 1, 1, bn, 8, 1).expand(nt, nk, 2, bn, 8, 4)
-    return torch.gather(both, 4, idx).contiguous().reshape(-1)
+    idx = src_chunk.view(1, 1, 1, bn, 8, 1).expand(nt, nk, 2, bn, 8, per)
+    return torch.gather(both, 4, idx).contiguous().reshape(-1), w_inv
 
 
 @dataclass
@@ -105,16 +135,19 @@ class DenseLayer:
     relu: bool = False
     Wtc: Optional[torch.Tensor] = None     # tcgen05 image (pack_tc_blob) or None -> CUDA-core engine
     tc_bn: int = 0
+    tc_kind: int = KIND_TF32
+    tc_w_inv: float = 1.0
 
     @property
     def ldw(self) -> int:
         return self.W.shape[1]
 
-    def with_tc(self, w_out_in: torch.Tensor) -> "DenseLayer":
+    def with_tc(self, w_out_in: torch.Tensor, kind: Optional[int] = None) -> "DenseLayer":
         """attach the tensor-core image when the layer is large enough to benefit (K >= 32, N >= 48)"""
         if self.K >= 32 and self.K % 4 == 0 and self.N >= 48:
             self.tc_bn = tc_tile_n(self.N)
-            self.Wtc = pack_tc_blob(w_out_in, self.K, self.tc_bn)
+            self.tc_kind = tc_kind() if kind is None else kind
+            self.Wtc, self.tc_w_inv = pack_tc_blob(w_out_in, self.K, self.tc_bn, self.tc_kind)
         return self
 
 
@@ -144,6 +177,8 @@ class EdgeBranch:
     shift: torch.Tensor
     H: int
     W1tc: Optional[torch.Tensor] = None    # tcgen05 image of W1 (H >= 64)
+    tc_kind: int = KIND_TF32
+    tc_w_inv: float = 1.0
 
 
 def _edge_mlp_parts(sd, prefix: str):
@@ -161,7 +196,8 @@ def _edge_mlp_parts(sd, prefix: str):
     b1f = b1 + w1 @ t0
     br = EdgeBranch(W1=_pack_wt(w1f), b1=_vec(b1f), scale=_vec(s1), shift=_vec(t1), H=w1.shape[0])
     if br.H in (64, 128, 256):
-        br.W1tc = pack_tc_blob(w1f, br.H, br.H)
+        br.tc_kind = tc_kind()
+        br.W1tc, br.tc_w_inv = pack_tc_blob(w1f, br.H, br.H, br.tc_kind)
     return wa - wb, wb, b0, br
 
 

@@ -42,7 +42,8 @@ class TemporalAttn(FusedModule):
         x = _lib.require_cuda(x, "x")
         pk = self._packed_for("attn", self.pack)
         out = torch.empty(x.shape[0], pk.ff1.N, device=x.device, dtype=torch.float32)
-        engine.run_temporal_attn(self._ws, "attn", pk, x, out)
+        with engine.forward_scope(self._ws, x.device):
+            engine.run_temporal_attn(self._ws, "attn", pk, x, out)
         return out
 
 
@@ -76,7 +77,8 @@ class GCNRig(FusedModule):
         gt = self._graphs.get(tpl_edge_index, n)
         gg = self._graphs.get(geo_edge_index, n)
         binfo = self._batches.get(batch)
-        out = self.run(self._ws, "rig", pos, feature, feature.shape[1], 0, gt, gg, binfo, 1)
+        with engine.forward_scope(self._ws, pos.device):
+            out = self.run(self._ws, "rig", pos, feature, feature.shape[1], 0, gt, gg, binfo, 1)
         return out.clone()
 
 
@@ -224,10 +226,11 @@ class _JointMaskBase(_MotionNet):
 
     def _forward_impl(self, data, input_flow, ws, graphs, batches):
         pos, flow, n, gt, gg, binfo = self._inputs(data, input_flow, graphs, batches)
-        motion_all = self._encode(ws, pos, flow, n, gt, gg, binfo, 32)
-        motion_aggr = self._aggregate(ws, motion_all, self.aggr_method, 64)
-        head = getattr(self, self._head_name)
-        pred = head.run(ws, "head", pos, motion_aggr, motion_aggr.shape[1], 0, gt, gg, binfo, 1)
+        with engine.forward_scope(ws, pos.device):
+            motion_all = self._encode(ws, pos, flow, n, gt, gg, binfo, 32)
+            motion_aggr = self._aggregate(ws, motion_all, self.aggr_method, 64)
+            head = getattr(self, self._head_name)
+            pred = head.run(ws, "head", pos, motion_aggr, motion_aggr.shape[1], 0, gt, gg, binfo, 1)
         return motion_all, motion_aggr, pred.clone()
 
 
@@ -277,7 +280,8 @@ class SkinNet_inner(FusedModule):
         gt = self._graphs.get(data.tpl_edge_index, n)
         gg = self._graphs.get(data.geo_edge_index, n)
         binfo = self._batches.get(data.batch, data)
-        return self.run(self._ws, "skin", data, pos, motion, gt, gg, binfo).clone()
+        with engine.forward_scope(self._ws, pos.device):
+            return self.run(self._ws, "skin", data, pos, motion, gt, gg, binfo).clone()
 
 
 class SkinMotion(_MotionNet):
@@ -297,9 +301,10 @@ class SkinMotion(_MotionNet):
 
     def _forward_impl(self, data, input_flow, ws, graphs, batches):
         pos, flow, n, gt, gg, binfo = self._inputs(data, input_flow, graphs, batches)
-        motion_all = self._encode(ws, pos, flow, n, gt, gg, binfo, self.motion_dim)
-        motion_aggr = self._aggregate(ws, motion_all, "attn", self.motion_dim)
-        pred = self.skinNet.run(ws, "skin", data, pos, motion_aggr, gt, gg, binfo)
+        with engine.forward_scope(ws, pos.device):
+            motion_all = self._encode(ws, pos, flow, n, gt, gg, binfo, self.motion_dim)
+            motion_aggr = self._aggregate(ws, motion_all, "attn", self.motion_dim)
+            pred = self.skinNet.run(ws, "skin", data, pos, motion_aggr, gt, gg, binfo)
         return motion_all, motion_aggr, pred.clone()
 
 

@@ -31,17 +31,20 @@ def dense_case(M, K, N):
     W = torch.randn(N, K, generator=g, dtype=torch.float64) / K ** 0.5
     b = torch.randn(N, generator=g).to(DEV)
     simt = packing.DenseLayer(W=packing._pack_wt(W).to(DEV), K=K, N=N, bias=b, relu=True)
-    tc = packing.DenseLayer(W=simt.W, K=K, N=N, bias=b, relu=True).with_tc(W)
-    tc.Wtc = tc.Wtc.to(DEV)
-    C1 = torch.empty(M, N, device=DEV)
-    C2 = torch.empty(M, N, device=DEV)
-    t_simt = timeit(lambda: engine.dense(simt, A, 0, K, M, C=C1, ldc=N))
-    t_tc = timeit(lambda: engine.dense(tc, A, 0, K, M, C=C2, ldc=N))
     ref = torch.relu(A[:2048].double() @ W.to(DEV).t() + b.double())
     fl = 2.0 * M * N * K
-    print(f"dense M={M} K={K} N={N}: simt {t_simt:.3f} ms {fl / t_simt / 1e9:.1f} TF/s | tc {t_tc:.3f} ms "
-          f"{fl / t_tc / 1e9:.1f} TF/s | err simt {float((C1[:2048] - ref).abs().max()):.2e} "
-          f"tc {float((C2[:2048] - ref).abs().max()):.2e}", flush=True)
+    line = f"dense M={M} K={K} N={N}:"
+    for name, kind in (("simt", None), ("tf32", packing.KIND_TF32), ("f16", packing.KIND_F16)):
+        layer = simt
+        if kind is not None:
+            layer = packing.DenseLayer(W=simt.W, K=K, N=N, bias=b, relu=True).with_tc(W, kind)
+            layer.Wtc = layer.Wtc.to(DEV)
+        C = torch.empty(M, N, device=DEV)
+        with engine.forward_scope(WS, DEV):          # operand range computed once, outside the timed launches
+            engine.dense(layer, A, 0, K, M, C=C, ldc=N)
+            t = timeit(lambda: engine.dense(layer, A, 0, K, M, C=C, ldc=N))
+        line += f" {name} {t:.3f} ms {fl / t / 1e9:.1f} TF/s err {float((C[:2048] - ref).abs().max()):.2e} |"
+    print(line, flush=True)
 
 
 def edge_case(H, frames):
@@ -53,20 +56,29 @@ def edge_case(H, frames):
     W1 = torch.randn(H, H, generator=gen, dtype=torch.float64) / H ** 0.5
     vec = lambda: torch.randn(H, generator=gen).to(DEV)
     br = packing.EdgeBranch(W1=packing._pack_wt(W1).to(DEV), b1=vec(), scale=vec(), shift=vec(), H=H)
-    br_tc = packing.EdgeBranch(W1=br.W1, b1=br.b1, scale=br.scale, shift=br.shift, H=H,
-                               W1tc=packing.pack_tc_blob(W1, H, H).to(DEV))
-    o1 = torch.empty(n * frames, H, device=DEV)
-    o2 = torch.empty(n * frames, H, device=DEV)
-
-    def run(b, o):
-        engine.fill(o, float("-inf"))
-        engine.edgeconv(b, pq, 2 * H, 0, H, g, frames, o, H, 0)
-    t1 = timeit(lambda: run(br, o1))
-    t2 = timeit(lambda: run(br_tc, o2))
     fl = 2.0 * g.e_max * H * H * frames
-    print(f"edge H={H} frames={frames} E={g.e_max}: simt {t1:.3f} ms {fl / t1 / 1e9:.1f} TF/s | tc {t2:.3f} ms "
-          f"{fl / t2 / 1e9:.1f} TF/s | max|simt-tc| {float((o1 - o2).abs().max()):.2e}", flush=True)
+    line = f"edge H={H} frames={frames} E={g.e_max}:"
+    o_ref = None
+    for name, kind in (("simt", None), ("tf32", packing.KIND_TF32), ("f16", packing.KIND_F16)):
+        b = br
+        if kind is not None:
+            blob, w_inv = packing.pack_tc_blob(W1, H, H, kind)
+            b = packing.EdgeBranch(W1=br.W1, b1=br.b1, scale=br.scale, shift=br.shift, H=H, W1tc=blob.to(DEV),
+                                   tc_kind=kind, tc_w_inv=w_inv)
+        o = torch.empty(n * frames, H, device=DEV)
 
+        def run():
+            engine.fill(o, float("-inf"))
+            engine.edgeconv(b, pq, 2 * H, 0, H, g, frames, o, H, 0)
+        with engine.forward_scope(WS, DEV):
+            run()
+            t = timeit(run)
+        o_ref = o if o_ref is None else o_ref
+        line += f" {name} {t:.3f} ms {fl / t / 1e9:.1f} TF/s d {float((o - o_ref).abs().max()):.2e} |"
+    print(line, flush=True)
+
+
+WS = engine.Workspace()
 
 if __name__ == "__main__":
     R = 81920

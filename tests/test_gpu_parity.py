@@ -13,7 +13,7 @@ DEV = "cuda:0"
 
 def test_library_loaded_is_in_tree():
     lib = _lib.load()
-    assert lib.morig_version() == 1
+    assert lib.morig_version() == _lib.ABI_VERSION
     assert lib.morig_sm_count() > 0
 
 
@@ -73,18 +73,23 @@ def test_dense_fwd(M, K, N):
     assert helpers.max_abs_diff(C, ref) < 2e-5
 
 
+KINDS = [pytest.param(packing.KIND_TF32, id="tf32"), pytest.param(packing.KIND_F16, id="f16")]
+
+
+@pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("M,K,N", [(128, 32, 64), (300, 96, 64), (1000, 64, 128), (257, 288, 256), (4099, 544, 512),
-                                   (640, 840, 1024), (20, 1024, 1024), (513, 36, 768)])
-def test_dense_fwd_tensor_core(M, K, N):
-    """tcgen05 3xTF32 engine against an fp64 reference: fp32-class accuracy is required (tolerance of the path
-    is 1e-4 absolute after ~20 chained layers, so a single layer must stay near fp32 rounding)"""
+                                   (640, 840, 1024), (20, 1024, 1024), (513, 36, 768), (40000, 256, 256)])
+def test_dense_fwd_tensor_core(M, K, N, kind):
+    """tcgen05 split-precision engine (both operand kinds) against an fp64 reference: fp32-class accuracy is
+    required (tolerance of the path is 1e-4 absolute after ~20 chained layers, so a single layer must stay near
+    fp32 rounding)"""
     g = torch.Generator().manual_seed(M + K + N)
     A = torch.randn(M, K, generator=g)
     W = torch.randn(N, K, generator=g) / K ** 0.5
     b, s, t = torch.randn(N, generator=g), torch.randn(N, generator=g), torch.randn(N, generator=g)
     layer = packing.DenseLayer(W=packing._pack_wt(W.double()).to(DEV), K=K, N=N, bias=b.to(DEV), scale=s.to(DEV),
-                               shift=t.to(DEV), relu=True).with_tc(W.double())
-    assert layer.Wtc is not None
+                               shift=t.to(DEV), relu=True).with_tc(W.double(), kind)
+    assert layer.Wtc is not None and layer.tc_kind == kind
     layer.Wtc = layer.Wtc.to(DEV)
     C = torch.full((M, N), float("nan"), device=DEV)
     engine.dense(layer, A.to(DEV), 0, K, M, C=C, ldc=N)
@@ -92,6 +97,55 @@ def test_dense_fwd_tensor_core(M, K, N):
     # 3xTF32 keeps ~21 mantissa bits per product but the tensor core accumulates K/8 partial sums with
     # truncation: allow 1e-5 of the output range (plain TF32 would be ~1e-3, fp32 FFMA ~1e-6)
     assert helpers.max_abs_diff(C, ref) < 1e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("a_mag,w_mag", [(3.0e4, 1.0), (1.0e-6, 1.0), (1.0, 2.0e3), (250.0, 1.0e-4), (1.0e6, 1.0e-5)])
+def test_dense_fp16_kind_dynamic_range(a_mag, w_mag):
+    """fp16 operand kind: activations and weights far outside fp16's exponent range must be handled by the
+    power-of-two operand scales (derived on the device from the tracked max |A|), and columns whose magnitudes
+    differ by 2^12 inside one tensor must all keep fp32-class accuracy"""
+    M, K, N = 1500, 320, 192
+    g = torch.Generator().manual_seed(5)
+    col_scale = torch.ones(K)
+    col_scale[::3] = 2.0 ** -12
+    A = torch.randn(M, K, generator=g) * col_scale * a_mag
+    W = torch.randn(N, K, generator=g) / K ** 0.5 * w_mag
+    W = W / col_scale.clamp(min=2.0 ** -6)                       # small activation columns meet larger weights
+    layer = packing.DenseLayer(W=packing._pack_wt(W.double()).to(DEV), K=K, N=N).with_tc(W.double(), packing.KIND_F16)
+    layer.Wtc = layer.Wtc.to(DEV)
+    C = torch.full((M, N), float("nan"), device=DEV)
+    engine.dense(layer, A.to(DEV), 0, K, M, C=C, ldc=N)
+    ref = A.double() @ W.double().t()
+    assert torch.isfinite(C).all()
+    assert helpers.max_abs_diff(C, ref) < 1e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("H,frames,mag", [(64, 1, 1.0), (128, 2, 300.0), (256, 1, 1.0e-3), (256, 3, 40.0)])
+def test_edgeconv_tensor_core_kinds(H, frames, mag, kind):
+    """fused EdgeConv branch on the tcgen05 engine, both operand kinds, against an fp64 evaluation of
+    max_e relu(relu(P[i] + Q[j]) W1 + b1) * s + t on a ragged graph (heavy target, isolated vertices)"""
+    n = 1500
+    g = torch.Generator().manual_seed(H + frames)
+    ei = torch.randint(0, n - 10, (2, 12000), generator=g)
+    ei[1, :900] = 7
+    gr = engine.graph_prep(ei.to(DEV), n)
+    pq = torch.randn(n * frames, 2 * H, generator=g) * mag
+    W1 = torch.randn(H, H, generator=g, dtype=torch.float64) / H ** 0.5
+    b1, sc, sh = (torch.randn(H, generator=g) * mag for _ in range(3))
+    sc = sc / mag
+    blob, w_inv = packing.pack_tc_blob(W1, H, H, kind)
+    br = packing.EdgeBranch(W1=packing._pack_wt(W1).to(DEV), b1=b1.to(DEV), scale=sc.to(DEV), shift=sh.to(DEV), H=H,
+                            W1tc=blob.to(DEV), tc_kind=kind, tc_w_inv=w_inv)
+    out = torch.full((n * frames, H), float("-inf"), device=DEV)
+    engine.edgeconv(br, pq.to(DEV), 2 * H, 0, H, gr, frames, out, H, 0)
+    e_real = int(gr.rowptr[n])
+    i, j = gr.tgt[:e_real].long().cpu(), gr.col[:e_real].long().cpu()
+    for f in range(frames):
+        P, Q = pq[f * n:(f + 1) * n, :H].double(), pq[f * n:(f + 1) * n, H:].double()
+        z = torch.relu(torch.relu(P[i] + Q[j]) @ W1.t() + b1.double()) * sc.double() + sh.double()
+        ref = torch.full((n, H), float("-inf"), dtype=torch.float64).scatter_reduce(0, i[:, None].expand_as(z), z, "amax")
+        assert helpers.max_abs_diff(out[f * n:(f + 1) * n], ref) < 1e-5 * max(1.0, float(ref.abs().max()))
 
 
 def test_dense_tensor_core_pool_and_rowbias():

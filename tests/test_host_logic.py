@@ -10,7 +10,7 @@ import pytest
 import torch
 
 import helpers
-from morig_b200 import _lib, synth
+from morig_b200 import _lib, engine, synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -158,7 +158,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(_lib.EXPORTS) == declared                      # the ctypes table covers the whole header
-    assert _lib.load().morig_version() == 1
+    assert _lib.load().morig_version() == _lib.ABI_VERSION == 2
 
 
 def test_tensor_core_weight_image_layout():
@@ -169,7 +169,9 @@ def test_tensor_core_weight_image_layout():
     g = torch.Generator().manual_seed(0)
     n, k, bn = 300, 70, 256
     w = torch.randn(n, k, generator=g, dtype=torch.float64)
-    blob = packing.pack_tc_blob(w, 72, bn).numpy()
+    blob, w_inv = packing.pack_tc_blob(w, 72, bn)
+    blob = blob.numpy()
+    assert w_inv == 1.0
     nk, nt = 3, 2
     assert blob.size == nt * nk * 2 * bn * 32
     img = blob.reshape(nt, nk, 2, bn * 32)
@@ -189,6 +191,65 @@ def test_tensor_core_weight_image_layout():
     err = np.abs(hi.astype(np.float64) + lo.astype(np.float64) - full)
     assert err.max() <= 2.0 ** -21 * np.abs(full).max()
     assert np.abs(hi - full).max() <= 2.0 ** -11 * np.abs(full).max()
+
+
+def test_tensor_core_weight_image_layout_fp16():
+    """pack_tc_blob(kind=F16): power-of-two scaled fp16 hi/lo split in the same SWIZZLE_128B stage image, rows of
+    64 halfs; hi + lo must reproduce W * 2^j to 2^-22 of the largest weight and nothing may overflow fp16"""
+    import numpy as np
+    from morig_b200 import packing
+    g = torch.Generator().manual_seed(1)
+    n, k, bn = 130, 100, 128
+    w = torch.randn(n, k, generator=g, dtype=torch.float64) * 37.5
+    blob, w_inv = packing.pack_tc_blob(w, 100, bn, packing.KIND_F16)
+    blob = blob.numpy()
+    nk, nt = 2, 2
+    assert blob.dtype == np.float16 and blob.size == nt * nk * 2 * bn * 64
+    img = blob.reshape(nt, nk, 2, bn * 64)
+    rec = np.zeros((2, nt * bn, nk * 64), dtype=np.float64)
+    for t in range(nt):
+        for kc in range(nk):
+            for half in range(2):
+                flat = img[t, kc, half]
+                for row in range(bn):
+                    for c in range(8):
+                        off = (row * 128 + ((c ^ (row % 8)) * 16)) // 2
+                        rec[half, t * bn + row, kc * 64 + 8 * c: kc * 64 + 8 * c + 8] = flat[off:off + 8]
+    assert np.isfinite(rec).all()
+    full = np.zeros((nt * bn, nk * 64))
+    full[:n, :k] = w.numpy()
+    scaled_max = np.abs(full).max() / w_inv
+    assert 2.0 ** 14 <= scaled_max < 2.0 ** 15
+    assert np.log2(w_inv) == round(np.log2(w_inv))
+    err = np.abs((rec[0] + rec[1]) * w_inv - full)
+    assert err.max() <= 2.0 ** -22 * np.abs(full).max()
+
+
+def test_amax_tracker_bookkeeping(emulated, monkeypatch):
+    """AmaxTracker: slots are per storage, zeroed at the start of a forward, recomputed on demand for tensors
+    this library did not write and after untracked in-place writes"""
+    calls = []
+    monkeypatch.setattr(engine, "_absmax", lambda t, off, ld, rows, cols, buf, idx: calls.append(("absmax", idx)))
+    monkeypatch.setattr(engine, "_absmax_reset", lambda buf, idx: calls.append(("reset", idx)))
+    ws = engine.Workspace()
+    a, b = torch.zeros(4, 8), torch.zeros(4, 8)
+    with engine.forward_scope(ws, "cpu"):
+        tr = engine._tracker
+        assert tr is ws.tracker
+        p_a = engine._amax_in(a, 0, 8, 4, 8)                  # foreign tensor: computed on demand, once
+        assert engine._amax_in(a[1:], 8, 8, 3, 8) == p_a      # a view shares the storage slot
+        assert calls == [("absmax", 0)]
+        p_b = engine._amax_out(b)                             # tracked producer: no absmax launch needed
+        assert p_b == p_a + 4 and engine._amax_in(b, 0, 8, 4, 8) == p_b and len(calls) == 1
+        engine._untracked(b)                                  # e.g. row_normalize in place
+        assert calls[-1] == ("reset", 1)
+        engine._amax_in(b, 0, 8, 4, 8)
+        assert calls[-1] == ("absmax", 1)
+        with engine.forward_scope(ws, "cpu"):                 # nested scope: no reset
+            assert engine._tracker is tr and 0 in tr.valid
+    assert engine._tracker is None
+    with engine.forward_scope(ws, "cpu"):
+        assert not ws.tracker.valid                           # new forward: everything recomputed / re-tracked
 
 
 def test_c_abi_argument_validation_without_gpu():
