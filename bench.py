@@ -11,8 +11,10 @@ feeds a new Batch every iteration, training/train_rig.py:206-223).  Prints ONE J
 
   value   meshes/s, inputs resident in HBM, each step timed with CUDA events on the launch stream,
           an L2 flush (256 MiB write) between steps, max over ranks
-  e2e     the same metric through the public nn.Module call with HOST (pinned) inputs: H2D copy of the
-          batch + forward + D2H copy of the three outputs inside the timed region
+  e2e     the same metric through the public API with HOST (pinned) inputs and HOST results: every step's H2D copy
+          of the batch, forward and D2H copy of the three outputs are inside the timed region.  Steps go through
+          `morig_b200.HostPipeline` (copy-in / forward / copy-out of consecutive batches on three streams);
+          `e2e.serial` is the strictly sequential `model(data.to(dev), flow)` + `.to("cpu")` loop of the reference
   roofline / cpu_baseline: see DESIGN.md "Measurement"
 """
 from __future__ import annotations
@@ -218,7 +220,33 @@ def run_ours(args):
     # preparation included) as one CUDA graph on static input buffers, so warm-up >= 3 covers the capture
     ms_total = timed(step_resident, args.steps, args.warmup, profile=os.environ.get("MORIG_BENCH_PROFILE") == "graph")
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    ms_e2e_serial = timed(step_e2e, args.steps, args.warmup)
+    pipe = morig_b200.HostPipeline(model, depth=2)
+
+    def timed_pipeline(steps, warmup):
+        with torch.no_grad():
+            for _ in range(warmup):
+                pipe.submit(host, host.pred_flow)
+                pipe.result()
+            barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(stream)
+            for _ in range(steps):
+                flush_buf.fill_(1)                    # L2 flush between forwards (compute stream)
+                if pipe.in_flight == len(pipe.slots):
+                    pipe.result()                     # host reads the oldest step's outputs
+                pipe.submit(host, host.pred_flow)
+            while pipe.in_flight:
+                pipe.result()
+            pipe.join(stream)
+            e.record(stream)
+            barrier()
+        t = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_e2e = timed_pipeline(args.steps, args.warmup)
     # instrumented pass (same steps, plain stream launches): per-kernel CUDA events + launch count.  Events cannot
     # be placed between the nodes of a replayed graph, so the per-kernel durations come from this pass.
     engine.set_hooks(counter, prof)
@@ -259,7 +287,11 @@ def run_ours(args):
                            "parallelism": f"dp{world}: whole meshes per rank, no forward collective"},
                 "clocks": clocks,
                 "e2e": {"value": meshes / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                        "api": "morig_b200.HostPipeline(model, depth=2): pinned host batch in, pinned host outputs "
+                               "out, every step; copies of neighbouring steps overlap the forward",
+                        "serial": {"value": meshes / (ms_e2e_serial / 1e3), "ms_per_step": ms_e2e_serial / args.steps,
+                                   "api": "model(data.to(dev), flow) then .to('cpu'), one step after the other"}},
                 "gpu_launches": launches,
                 "launch_mode": "timed steps replay one CUDA graph per step (same kernels, graph preparation included); "
                                "gpu_launches / kernels / roofline come from an instrumented pass of the same "

@@ -5,6 +5,9 @@
     model.load_state_dict(reference_checkpoint["state_dict"])        # same keys as the reference
     motion_all, motion_aggr, pred = model(data, data.pred_flow)      # same call as training/train_rig.py:223
 
+    pipe = morig_b200.HostPipeline(model)                            # host batches in, pinned host results out,
+    for outs in pipe.run(host_batches): ...                          # copies overlapped with the forwards
+
 or, to swap the networks inside an unmodified reference checkout:
 
     import models, morig_b200
@@ -13,11 +16,13 @@ or, to swap the networks inside an unmodified reference checkout:
 from __future__ import annotations
 
 from .basic_modules import GCU, MLP, EdgeConv, EdgeConvMotion, GCUMotion
+from .pipeline import HostPipeline
 from .rignet import (GCNRig, JointNetMotion, MaskNetMotion, SkinMotion, SkinNet_inner, TemporalAttn,
                      jointnet_motion, masknet_motion, skinnet_motion)
 
 __all__ = ["jointnet_motion", "masknet_motion", "skinnet_motion", "JointNetMotion", "MaskNetMotion", "SkinMotion",
-           "SkinNet_inner", "GCNRig", "TemporalAttn", "GCUMotion", "EdgeConvMotion", "GCU", "EdgeConv", "MLP", "install"]
+           "SkinNet_inner", "GCNRig", "TemporalAttn", "GCUMotion", "EdgeConvMotion", "GCU", "EdgeConv", "MLP", "install",
+           "HostPipeline"]
 
 __version__ = "0.1.0"
 

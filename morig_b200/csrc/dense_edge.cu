@@ -1,51 +1,239 @@
-// Host launchers for the FP32 tile engine (vertex dense layers, fused EdgeConv branch) and the
-// narrow-channel EdgeConv branch kernel (H <= 32: warp per target vertex, lanes = channels).
+// Host launchers for the tile engines (vertex dense layers, fused EdgeConv branch) and the narrow-channel EdgeConv
+// branch kernel (H <= 32: warp per 32 CSR slots, mma.sync 3xTF32, in-register segmented max).
 #include <stdlib.h>
 #include "gemm_tc.cuh"
 
 namespace morig {
 
-// ---- narrow EdgeConv branch --------------------------------------------------------------------
-// One warp per (key-frame, target vertex).  H lanes hold the H output channels; 32/H edges of the
-// segment are processed side by side.  h = relu(P[i] + Q[j]) lives one channel per lane and is
-// broadcast with shuffles for the H x H second layer, whose column sits in registers.
-// No atomics: the warp owns the whole segment.
+// ---- narrow EdgeConv branch (H = 16 / 32) --------------------------------------------------------
+// Warp-level tensor-core kernel for the layers that are too small for the tcgen05 tile engine (gcu_1's x branch and
+// every pos branch of the joint / mask networks: 2 E H^2 FLOPs on 16- or 32-wide rows, bound by the gathers and the
+// segmented max, not by the MMAs).  One warp owns a tile of 32 consecutive CSR slots (edges sorted by target) and
+//   * gathers relu(P[tgt] + Q[col]) straight into mma.sync A fragments (no shared-memory staging): lane (g, t) owns
+//     the four edges 4g..4g+3 of the tile and, of each row, the H/4 contiguous channels [t H/4, (t+1) H/4) -- the
+//     contraction index is permuted identically on the weight side, so every global load is a full 16-byte chunk;
+//   * multiplies by the H x H second Linear with 3 x TF32 error compensation (hi/lo splits of both operands,
+//     A_lo B_hi + A_hi B_lo + A_hi B_hi, fp32 accumulate); the split weight fragments live in registers for the
+//     whole kernel;
+//   * applies bias -> ReLU -> BatchNorm affine and reduces with a segmented max scan over the tile: four edges in
+//     registers, then three shuffle steps across the eight lane groups; segment tails store (segments cut by the
+//     tile boundary merge with the ordered-int atomic max, so the result is exact and order independent).
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                 "{%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int EDGE_MMA_THREADS = 128;
+
 template <int H>
-__global__ void __launch_bounds__(256) edge_small_kernel(const morig_edge_desc d) {
-    constexpr int G = 32 / H;                       // edges in flight per warp
-    const int lane = threadIdx.x & 31;
-    const int c = lane % H, sub = lane / H;
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= (int64_t)d.N * d.n_frames) return;      // whole warps leave together
-    const int f = (int)(w / d.N), i = (int)(w % d.N);
-    const size_t fb = (size_t)f * d.N;
-
-    float wcol[H];
-#pragma unroll
-    for (int k = 0; k < H; ++k) wcol[k] = d.W1[(size_t)k * d.ldw + c];
-    const float b1 = d.b1[c], sc = d.scale[c], sh = d.shift[c];
-
-    const float pi = d.PQ[(fb + i) * (size_t)d.ldpq + d.p_off + c];
-    const int lo = d.rowptr[i], hi = d.rowptr[i + 1];
-    float m = neg_inf();
-    for (int e0 = lo; e0 < hi; e0 += G) {
-        const int e = e0 + sub;
-        const bool act = e < hi;
-        const int j = act ? d.col[e] : i;
-        const float h0 = fmaxf(pi + d.PQ[(fb + j) * (size_t)d.ldpq + d.q_off + c], 0.f);
-        float acc = b1;
-#pragma unroll
-        for (int k = 0; k < H; ++k) acc = fmaf(__shfl_sync(0xffffffffu, h0, k, H), wcol[k], acc);
-        const float z = fmaf(fmaxf(acc, 0.f), sc, sh);
-        if (act) m = fmaxf(m, z);
+__global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const morig_edge_desc d) {
+    constexpr int KT = H / 8, NT = H / 8;           // k-tiles and n-tiles of the m16n8k8 shape
+    constexpr int KPL = H / 4;                      // contraction values of one row held by one lane
+    constexpr int CPL = 2 * NT;                     // output columns held by one lane: 8 nt + 2 t + {0, 1}
+    constexpr uint32_t FULL = 0xffffffffu;
+    __shared__ float2 s_bias[H / 2], s_scale[H / 2], s_shift[H / 2];
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        reinterpret_cast<float *>(s_bias)[i] = d.b1[i];
+        reinterpret_cast<float *>(s_scale)[i] = d.scale[i];
+        reinterpret_cast<float *>(s_shift)[i] = d.shift[i];
     }
+    // weight fragments: slot (kt, t) of the instruction reads contraction index KPL t + 2 kt, slot (kt, t + 4) the next
+    uint32_t bh[KT][NT][2], bl[KT][NT][2];
 #pragma unroll
-    for (int off = 16; off >= H; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-    if (sub == 0) {
-        for (int r = 0; r < d.out_repeat; ++r)
-            d.out[((size_t)(f + r) * d.N + i) * (size_t)d.ldo + d.out_off + c] = m;
+    for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const float w = d.W1[(size_t)(KPL * t + 2 * kt + s) * d.ldw + 8 * nt + g];
+                const float hi = tc::tf32_hi(w);
+                bh[kt][nt][s] = __float_as_uint(hi);
+                bl[kt][nt][s] = __float_as_uint(w - hi);
+            }
+    __syncthreads();
+
+    const int N = d.N;
+    const int Ep = d.rowptr[N];                     // real edge count (E' lives on the device only)
+    const int n_tiles = (Ep + 31) >> 5;
+    const long long total = (long long)n_tiles * d.n_frames;
+    const int warps_total = gridDim.x * (EDGE_MMA_THREADS / 32);
+    const bool vec2 = ((d.ldo | d.out_off) & 1) == 0 && (reinterpret_cast<uintptr_t>(d.out) & 7u) == 0;
+    const float *Pb = d.PQ + d.p_off + KPL * t;
+    const float *Qb = d.PQ + d.q_off + KPL * t;
+    float am = 0.f;
+
+    for (long long id = (long long)blockIdx.x * (EDGE_MMA_THREADS / 32) + (threadIdx.x >> 5); id < total; id += warps_total) {
+        const int f = (int)(id / n_tiles);
+        const int s0 = (int)(id - (long long)f * n_tiles) * 32;
+        const size_t fb = (size_t)f * N;
+        // ---- indices of this lane's four edges ----
+        int key[4], cj[4];
+        const int e0 = s0 + 4 * g;
+        if (e0 + 3 < Ep) {
+            const int4 k4 = *reinterpret_cast<const int4 *>(d.tgt + e0);
+            const int4 c4 = *reinterpret_cast<const int4 *>(d.col + e0);
+            key[0] = k4.x; key[1] = k4.y; key[2] = k4.z; key[3] = k4.w;
+            cj[0] = c4.x; cj[1] = c4.y; cj[2] = c4.z; cj[3] = c4.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool ok = e0 + j < Ep;
+                key[j] = ok ? d.tgt[e0 + j] : -1;
+                cj[j] = ok ? d.col[e0 + j] : 0;
+            }
+        }
+        // ---- gather: x[j] = relu(P[tgt] + Q[col]), this lane's KPL channels ----
+        float x[4][KPL];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float *pp = Pb + (fb + (size_t)max(key[j], 0)) * d.ldpq;
+            const float *qq = Qb + (fb + (size_t)cj[j]) * d.ldpq;
+#pragma unroll
+            for (int v = 0; v < KPL / 4; ++v) {
+                const float4 a = *reinterpret_cast<const float4 *>(pp + 4 * v);
+                const float4 b = *reinterpret_cast<const float4 *>(qq + 4 * v);
+                x[j][4 * v + 0] = fmaxf(a.x + b.x, 0.f);
+                x[j][4 * v + 1] = fmaxf(a.y + b.y, 0.f);
+                x[j][4 * v + 2] = fmaxf(a.z + b.z, 0.f);
+                x[j][4 * v + 3] = fmaxf(a.w + b.w, 0.f);
+            }
+        }
+        // ---- segment structure of the tile (identical in the four lanes of a group) ----
+        const int key_prev = __shfl_up_sync(FULL, key[3], 4);
+        const int key_next = __shfl_down_sync(FULL, key[0], 4);
+        bool head[4], tail[4];
+        head[0] = (g == 0) || key[0] != key_prev;
+        tail[3] = (g == 7) || key[3] != key_next;
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+            head[j] = key[j] != key[j - 1];
+            tail[j - 1] = head[j];
+        }
+        const int first_key = __shfl_sync(FULL, key[0], 0);
+        const int last_key = __shfl_sync(FULL, key[3], 31);
+        // segments cut by the tile boundary merge through atomics
+        const bool cut_first = first_key >= 0 && d.rowptr[first_key] < s0;
+        const bool cut_last = last_key >= 0 && d.rowptr[last_key + 1] > s0 + 32;
+
+        // ---- second Linear on the tensor cores: two m16 tiles (edges {0,1} and {2,3} of every lane) ----
+        float z[4][CPL];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            float acc[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) {
+                uint32_t ah[4], al[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {                 // a0: row g, a1: row g + 8, a2 / a3: the t + 4 slots
+                    const float v = x[2 * m + (i & 1)][2 * kt + (i >> 1)];
+                    const float hi = tc::tf32_hi(v);
+                    ah[i] = __float_as_uint(hi);
+                    al[i] = __float_as_uint(v - hi);
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    mma_tf32_16x8x8(acc[nt], al[0], al[1], al[2], al[3], bh[kt][nt][0], bh[kt][nt][1]);
+                    mma_tf32_16x8x8(acc[nt], ah[0], ah[1], ah[2], ah[3], bl[kt][nt][0], bl[kt][nt][1]);
+                    mma_tf32_16x8x8(acc[nt], ah[0], ah[1], ah[2], ah[3], bh[kt][nt][0], bh[kt][nt][1]);
+                }
+            }
+            // bias -> ReLU -> BatchNorm affine (before any max: the scale may be negative)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const float2 b = s_bias[4 * nt + t], sc = s_scale[4 * nt + t], sh = s_shift[4 * nt + t];
+                z[2 * m][2 * nt] = fmaf(fmaxf(acc[nt][0] + b.x, 0.f), sc.x, sh.x);
+                z[2 * m][2 * nt + 1] = fmaf(fmaxf(acc[nt][1] + b.y, 0.f), sc.y, sh.y);
+                z[2 * m + 1][2 * nt] = fmaf(fmaxf(acc[nt][2] + b.x, 0.f), sc.x, sh.x);
+                z[2 * m + 1][2 * nt + 1] = fmaf(fmaxf(acc[nt][3] + b.y, 0.f), sc.y, sh.y);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (key[j] >= 0) {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) am = fmaxf(am, fabsf(z[j][c]));
+            }
+
+        // ---- segmented inclusive max scan over the 32 edges ----
+#pragma unroll
+        for (int j = 1; j < 4; ++j)
+            if (!head[j]) {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) z[j][c] = fmaxf(z[j][c], z[j - 1][c]);
+            }
+        float v[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) v[c] = z[3][c];
+        bool F = head[0] | head[1] | head[2] | head[3];       // a segment starts inside this lane's edges
+#pragma unroll
+        for (int dlt = 1; dlt < 8; dlt <<= 1) {
+            const bool Fp = __shfl_up_sync(FULL, F, 4 * dlt);
+            const bool take = (g >= dlt) && !F;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const float vp = __shfl_up_sync(FULL, v[c], 4 * dlt);
+                if (take) v[c] = fmaxf(v[c], vp);
+            }
+            if (g >= dlt) F = F | Fp;
+        }
+        {
+            bool open = g > 0;                                    // edges before the lane's first head continue a segment
+            float cin[CPL];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) cin[c] = __shfl_up_sync(FULL, v[c], 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                open = open && !head[j];
+                if (open) {
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) z[j][c] = fmaxf(z[j][c], cin[c]);
+                }
+            }
+        }
+        // ---- segment tails hold the maxima ----
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (!tail[j] || key[j] < 0) continue;
+            const bool atomic = (cut_first && key[j] == first_key) || (cut_last && key[j] == last_key);
+            for (int r = 0; r < d.out_repeat; ++r) {
+                float *dst = d.out + ((size_t)(f + r) * N + key[j]) * (size_t)d.ldo + d.out_off + 2 * t;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    if (atomic) {
+                        atomic_max_f32(dst + 8 * nt, z[j][2 * nt]);
+                        atomic_max_f32(dst + 8 * nt + 1, z[j][2 * nt + 1]);
+                    } else if (vec2) {
+                        *reinterpret_cast<float2 *>(dst + 8 * nt) = make_float2(z[j][2 * nt], z[j][2 * nt + 1]);
+                    } else {
+                        dst[8 * nt] = z[j][2 * nt];
+                        dst[8 * nt + 1] = z[j][2 * nt + 1];
+                    }
+                }
+            }
+        }
     }
-    amax_commit(d.out_amax, fabsf(m));
+    amax_commit(d.out_amax, am);
+}
+
+template <int H>
+static int launch_edge_mma(const morig_edge_desc &d, cudaStream_t stream) {
+    static thread_local int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        MORIG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, edge_mma_kernel<H>, EDGE_MMA_THREADS, 0));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    const long long tiles = (long long)ceil_div(d.E_max, 32) * d.n_frames;          // upper bound (E' <= E_max)
+    const long long want = ceil_div64(tiles, EDGE_MMA_THREADS / 32);
+    const long long cap = (long long)sm_count() * blocks_per_sm;                    // persistent: warps stride over tiles
+    edge_mma_kernel<H><<<(unsigned)(want < cap ? want : cap), EDGE_MMA_THREADS, 0, stream>>>(d);
+    MORIG_LAUNCH_CHECK("edge_mma_kernel");
+    return 0;
 }
 
 template <int BM, int BN, int AMODE, int EPI>
@@ -228,12 +416,10 @@ extern "C" MORIG_API int morig_edgeconv_fwd(const morig_edge_desc *d, void *stre
     MORIG_CHECK_ARG(d->out_repeat == 1 || d->n_frames == 1, "edgeconv_fwd: out_repeat needs n_frames == 1");
     const int H = d->H;
     if (H == 16 || H == 32) {
-        const int64_t warps = (int64_t)d->N * d->n_frames;
-        const unsigned blocks = (unsigned)ceil_div64(warps * 32, 256);
-        if (H == 16) edge_small_kernel<16><<<blocks, 256, 0, stream>>>(*d);
-        else edge_small_kernel<32><<<blocks, 256, 0, stream>>>(*d);
-        MORIG_LAUNCH_CHECK("edge_small_kernel");
-        return 0;
+        MORIG_CHECK_ARG(d->ldpq % 4 == 0 && d->p_off % 4 == 0 && d->q_off % 4 == 0 && aligned16(d->PQ),
+                        "edgeconv_fwd: PQ must be 16B aligned (ldpq, p_off, q_off multiples of 4)");
+        MORIG_CHECK_ARG(aligned16(d->col) && aligned16(d->tgt), "edgeconv_fwd: col / tgt must be 16B aligned");
+        return H == 16 ? launch_edge_mma<16>(*d, stream) : launch_edge_mma<32>(*d, stream);
     }
     MORIG_CHECK_ARG(H == 64 || H == 128 || H == 256, "edgeconv_fwd: H=%d unsupported (16,32,64,128,256)", H);
     MORIG_CHECK_ARG(d->out_repeat == 1, "edgeconv_fwd: out_repeat only for H<=32");

@@ -311,10 +311,14 @@ FP32_FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # nominal CUDA-core p
 def roofline_report(kstats, peaks, ms_per_step: float, alg_flops_step: float, traffic_bytes=None) -> dict:
     """`roofline` object of the bench line for the dominant kernel (largest share of the step).
 
-    The dominant kernels run on the tcgen05 tensor pipe with 3xTF32 error compensation: every algorithmic fp32
-    FLOP costs three kind::tf32 MMA FLOPs, and kind::tf32 runs at half the bf16 rate.  `peak` is the measured bf16
-    dense figure of MEASURED_PEAKS.json (the only compute peak the driver measures); `fp32_equiv_peak` = peak / 6 is
-    what this arithmetic could reach at best, and `frac_of_fp32_equiv_peak` is the honest utilisation figure."""
+    The dominant kernels run on the tcgen05 tensor pipe with split-operand error compensation: every algorithmic
+    fp32 FLOP costs three MMA FLOPs (hi*hi + hi*lo + lo*hi).  `kind::f16` (default) issues them at the bf16/fp16
+    rate, `kind::tf32` (`MORIG_TC_KIND=tf32`) at half of it.  `peak` is the measured bf16 dense figure of
+    MEASURED_PEAKS.json (the only compute peak the driver measures); `fp32_equiv_peak` = peak / 3 (f16) or peak / 6
+    (tf32) is what this arithmetic could reach at best, and `frac_of_fp32_equiv_peak` is the utilisation figure."""
+    from .packing import tc_kind
+    f16 = tc_kind() == KIND_F16
+    div = 3 if f16 else 6
     if not kstats:
         return {"bound": "tensor", "achieved": None, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": None, "traffic": None}
@@ -322,16 +326,20 @@ def roofline_report(kstats, peaks, ms_per_step: float, alg_flops_step: float, tr
     per_step_ms = sum(k["total_ms"] for k in kstats)
     achieved = top["tflops"]
     peak = peaks["bf16_tflops_sustained"]
+    pipe = ("tcgen05 kind::f16 on fp16 hi/lo operand splits (power-of-two scaled), 3 MMAs per algorithmic FLOP, "
+            "fp32 accumulate in TMEM") if f16 else \
+           "tcgen05 kind::tf32, 3 MMAs per algorithmic FLOP (3xTF32 compensation, fp32 accumulate in TMEM)"
     return {"bound": "tensor", "kernel": top["kernel"], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": (achieved / peak if achieved else None), "traffic": traffic_bytes,
             "peak_source": peaks["source"] + " bf16 dense, sustained (kernel timed inside a long step)",
             "avg_launch_ms": top["avg_ms"], "alg_gflop_per_launch": top["alg_gflop_per_launch"],
             "alg_mb_per_launch": top["alg_mb_per_launch"],
             "share_of_kernel_time": round(top["total_ms"] / per_step_ms, 4) if per_step_ms else None,
-            "pipe": "tcgen05 kind::tf32, 3 MMAs per algorithmic FLOP (3xTF32 compensation, fp32 accumulate in TMEM)",
+            "pipe": pipe,
             "tensor_tflops_issued": round(3 * achieved, 1) if achieved else None,
-            "fp32_equiv_peak": round(peak / 6, 1),
-            "frac_of_fp32_equiv_peak": (round(achieved / (peak / 6), 4) if achieved else None),
+            "frac_issued_of_peak": (round(3 * achieved / peak, 4) if achieved else None),
+            "fp32_equiv_peak": round(peak / div, 1),
+            "frac_of_fp32_equiv_peak": (round(achieved / (peak / div), 4) if achieved else None),
             "fp32_ffma_nominal_peak": round(FP32_FFMA_PEAK_TFLOPS, 1),
             "hbm_gbs_same_kernel": top["gbs"], "hbm_frac_same_kernel": (round(top["gbs"] / peaks["hbm_gbs"], 4)
                                                                        if top["gbs"] else None)}
@@ -433,8 +441,7 @@ def run_gcu(ws: Workspace, tag: str, gp: GCUPack, x: torch.Tensor, x_off: int, l
     pq = ws.get(tag + ".pq", (R, 4 * H), dev)
     ec = ws.get(tag + ".ec", (R, wec), dev)
     dense(gp.pq_x, x, x_off, ldx, R, K=k_x, C=pq, ldc=4 * H)
-    if H >= 64 or Dp >= 64:
-        fill(ec, NEG_INF)       # tiles of the wide kernel merge straddling segments with atomic max
+    fill(ec, NEG_INF)           # edge tiles merge the segments they cut with an (exact, ordered-int) atomic max
     ldpp = pqpos.shape[1]
     for s, (g, bx, bp) in enumerate(((gt, gp.x_tpl, gp.pos_tpl), (gg, gp.x_geo, gp.pos_geo))):
         base = s * (H + Dp)

@@ -41,3 +41,13 @@ def test_forward_modules_have_no_torch_compute_fallback():
         src = open(os.path.join(PKG, name)).read()
         for b in banned:
             assert b not in src, (name, b)
+
+
+def test_host_pipeline_refuses_cpu_models():
+    """no CPU path: the streaming front-end needs the model on a CUDA device"""
+    import pytest
+    import morig_b200
+    from morig_b200 import synth
+    model = morig_b200.jointnet_motion(**synth.ARCH_KWARGS["jointnet_motion"]).eval()
+    with pytest.raises(RuntimeError):
+        morig_b200.HostPipeline(model)

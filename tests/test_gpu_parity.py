@@ -148,6 +148,38 @@ def test_edgeconv_tensor_core_kinds(H, frames, mag, kind):
         assert helpers.max_abs_diff(out[f * n:(f + 1) * n], ref) < 1e-5 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("H,frames,repeat,n,e,ldo_pad", [(16, 1, 1, 1500, 12000, 0), (16, 1, 5, 1500, 12000, 3),
+                                                        (32, 3, 1, 1500, 12000, 0), (32, 1, 1, 5, 3, 1),
+                                                        (16, 2, 1, 40, 0, 0), (32, 5, 1, 4096, 61440, 0)])
+def test_edgeconv_narrow_kernel(H, frames, repeat, n, e, ldo_pad):
+    """narrow EdgeConv branch (mma.sync 3xTF32 kernel, H = 16 / 32): ragged graph with a target whose segment
+    spans many 32-slot tiles, isolated vertices (self loop only), duplicates, key-frames, out_repeat, odd strides"""
+    g = torch.Generator().manual_seed(H + frames + n)
+    ei = torch.randint(0, max(n - 3, 1), (2, e), generator=g)
+    if e > 1000:
+        ei[1, :900] = 7
+    gr = engine.graph_prep(ei.to(DEV), n)
+    pq = torch.randn(n * frames, 2 * H, generator=g)
+    W1 = torch.randn(H, H, generator=g, dtype=torch.float64) / H ** 0.5
+    b1, sc, sh = (torch.randn(H, generator=g) for _ in range(3))
+    br = packing.EdgeBranch(W1=packing._pack_wt(W1).to(DEV), b1=b1.to(DEV), scale=sc.to(DEV), shift=sh.to(DEV), H=H)
+    ldo, off = H + 2 + ldo_pad, 2 + (ldo_pad & 1)
+    rows = n * frames * repeat
+    out = torch.full((rows, ldo), float("-inf"), device=DEV)
+    engine.edgeconv(br, pq.to(DEV), 2 * H, 0, H, gr, frames, out, ldo, off, out_repeat=repeat)
+    e_real = int(gr.rowptr[n])
+    i, j = gr.tgt[:e_real].long().cpu(), gr.col[:e_real].long().cpu()
+    got = out.cpu()
+    assert torch.isinf(got[:, :off]).all() and torch.isinf(got[:, off + H:]).all()       # neighbours untouched
+    for f in range(frames):
+        P, Q = pq[f * n:(f + 1) * n, :H].double(), pq[f * n:(f + 1) * n, H:].double()
+        z = torch.relu(torch.relu(P[i] + Q[j]) @ W1.t() + b1.double()) * sc.double() + sh.double()
+        ref = torch.full((n, H), float("-inf"), dtype=torch.float64).scatter_reduce(0, i[:, None].expand_as(z), z, "amax")
+        for r in range(repeat):
+            blk = got[(f + r) * n:(f + r + 1) * n, off:off + H]
+            assert helpers.max_abs_diff(blk, ref) < 1e-5 * max(1.0, float(ref.abs().max()))
+
+
 def test_dense_tensor_core_pool_and_rowbias():
     n, frames, B, K, N = 700, 3, 4, 64, 200
     g = torch.Generator().manual_seed(0)
@@ -395,3 +427,47 @@ def test_rejects_cpu_tensors_and_train_mode():
     model.train()
     with pytest.raises(NotImplementedError):
         model(data.to(DEV), data.pred_flow.to(DEV))
+
+
+# ---- host-to-host streaming (morig_b200.HostPipeline) ---------------------------------------------------
+@pytest.mark.parametrize("arch", ["jointnet_motion", "skinnet_motion"])
+def test_host_pipeline_matches_direct_calls_in_order(arch):
+    """Different host batches of one shape through the 3-stream pipeline: results come back in submission
+    order, equal bit for bit to sequential `model(data.to(dev), flow)` calls, and match the oracle."""
+    import morig_b200
+    kw = synth.ARCH_KWARGS[arch]
+    skin = arch == "skinnet_motion"
+    model = helpers.build_model(arch, kw, 5, DEV)
+    batches = [synth.make_batch(2, 512, seed=40 + 2 * i, with_skin=skin).pin_memory() for i in range(5)]
+    direct = []
+    with torch.no_grad():
+        for b in batches:
+            d = b.to(DEV)
+            direct.append([o.cpu() for o in model(d, d.pred_flow)])
+    pipe = morig_b200.HostPipeline(model, depth=2)
+    got = [[o.clone() for o in outs] for outs in pipe.run(batches)]
+    assert len(got) == len(batches) and pipe.in_flight == 0
+    for g, d in zip(got, direct):
+        for a, b_ in zip(g, d):
+            assert a.device.type == "cpu" and torch.equal(a, b_)
+    expect = helpers.oracle_forward(arch, kw, model, batches[3], batches[3].pred_flow)
+    for a, e in zip(got[3], expect):
+        assert helpers.max_abs_diff(a, e) < helpers.TOL
+
+
+def test_host_pipeline_slot_discipline():
+    import morig_b200
+    kw = synth.ARCH_KWARGS["masknet_motion"]
+    model = helpers.build_model("masknet_motion", kw, 2, DEV)
+    b = synth.make_batch(1, 256, seed=3)
+    pipe = morig_b200.HostPipeline(model, depth=1)
+    with pytest.raises(RuntimeError):
+        pipe.result()
+    pipe.submit(b, b.pred_flow)
+    with pytest.raises(RuntimeError):
+        pipe.submit(b, b.pred_flow)
+    outs = pipe.result()
+    assert all(o.is_pinned() for o in outs)
+    with pytest.raises(TypeError):
+        d = b.to(DEV)
+        pipe.submit(d, d.pred_flow)
