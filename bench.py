@@ -225,8 +225,11 @@ def run_ours(args):
 
     def timed_pipeline(steps, warmup):
         with torch.no_grad():
-            for _ in range(warmup):
+            for _ in range(max(warmup, len(pipe.slots) + 1)):      # warm up with the slots in flight, as in the timed loop
+                if pipe.in_flight == len(pipe.slots):
+                    pipe.result()
                 pipe.submit(host, host.pred_flow)
+            while pipe.in_flight:
                 pipe.result()
             barrier()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

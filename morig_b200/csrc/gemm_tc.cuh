@@ -98,36 +98,33 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster.  Default semantics (release at
+// CTA scope) on purpose: `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR in front of every arrive, which drains
+// the producer's prefetched loads once per stage; what the remote waiter consumes is shared memory written before a
+// fence.proxy.async (or TMEM reads retired before tcgen05.fence::before_thread_sync), which that fence already orders.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
     asm volatile(
         "{\n\t"
         ".reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
         "}" ::"r"(bar), "r"(cta) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Waits use the default acquire at CTA scope also for barriers that are signalled from the peer CTA or by a multicast
+// tcgen05.commit: `.acquire.cluster` makes ptxas append CCTL.IVALL (an L1 invalidation of the whole SM, i.e. of the
+// P[tgt] lines the producers keep hitting) to every successful wait.
 template <bool CLUSTER>
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    if (CLUSTER) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } else {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    }
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
 // A pipeline bug must surface as a launch failure, never as a hung GPU: trap after ~2 s of waiting.

@@ -1,12 +1,17 @@
 #!/bin/bash
-# Evidence run: launch list of the timed (graph-replayed) steps + full ncu capture of the tensor-core / edge kernels
-# of one instrumented step.  Outputs -> gpurun_out/
+# Evidence run: (1) launch list of the timed (graph-replayed) bench steps; (2) full ncu capture (source attached) of
+# one launch of each dominant kernel shape.  Text exports -> gpurun_out/ (the .ncu-rep too when it is small enough).
 set -u
 mkdir -p gpurun_out
 MORIG_BENCH_PROFILE=graph timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off \
     --csv --log-file gpurun_out/launches_graph.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launch.log 2>&1
-tail -2 gpurun_out/ncu_launch.log | cut -c1-300
-MORIG_BENCH_PROFILE=eager timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off \
-    -k regex:"gemm_kernel|edge_mma" -c ${1:-70} -o gpurun_out/prof_bench_tc python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_full.log 2>&1
-tail -2 gpurun_out/ncu_full.log | cut -c1-300
+tail -1 gpurun_out/ncu_launch.log | cut -c1-200
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
+    -k regex:"gemm_kernel|edge_mma" -o /tmp/prof_kernels python scripts/prof_kernels.py "$@" > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log | cut -c1-200
+ncu -i /tmp/prof_kernels.ncu-rep --page raw --csv > gpurun_out/prof_kernels_raw.csv 2>/dev/null
+ncu -i /tmp/prof_kernels.ncu-rep --page details > gpurun_out/prof_kernels_details.txt 2>/dev/null
+sz=$(stat -c %s /tmp/prof_kernels.ncu-rep)
+echo "report bytes: $sz"
+if [ "$sz" -lt 40000000 ]; then cp /tmp/prof_kernels.ncu-rep gpurun_out/; fi
 ls -la gpurun_out/
