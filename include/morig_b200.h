@@ -100,7 +100,7 @@ typedef struct morig_dense_desc {
      * When non-NULL (and A is 16-byte aligned with lda % 4 == 0, K % 4 == 0) the layer runs on the tcgen05
      * split-precision engine (3 MMAs per product, fp32-class results), otherwise on the fp32 CUDA-core
      * engine using W. */
-    const void    *Wtc;      int32_t tc_bn;   /* tc_bn in {64, 128, 256}                        */
+    const void    *Wtc;      int32_t tc_bn;   /* tc_bn in {128, 256} (channels per n-tile)      */
     int32_t        tc_kind;  float   tc_w_inv;
     const float   *a_amax;                     /* device scalar, required for tc_kind 1          */
     /* optional device scalar: atomically raised to max |C[r, n]| over everything this call stores

@@ -311,7 +311,7 @@ static int launch_tc2(const GemmP &p, const void *blob, int frames, cudaStream_t
 
 template <int KIND, int BN, int AMODE, int EPI>
 static int launch_tc(const GemmP &p, const void *blob, int frames, cudaStream_t stream, const char *name) {
-    if constexpr (BN >= 128) {
+    if constexpr (BN == 256) {
         if (!env_flag("MORIG_NO_2CTA")) {
             // enough pair-tiles to give every 2-CTA cluster of the machine at least one
             const long long pairs = (long long)ceil_div(p.N, BN) * ceil_div(ceil_div(p.M, tc::BM), 2) * frames;
@@ -394,10 +394,9 @@ extern "C" MORIG_API int morig_dense_fwd(const morig_dense_desc *d, void *stream
             p.w_inv = d->tc_w_inv;
         }
         switch (d->tc_bn) {
-            case 64:  return launch_tc_kind<64, AMODE_PLAIN, EPI_STORE>(d->tc_kind, p, d->Wtc, 1, stream, "tc_dense<64>");
             case 128: return launch_tc_kind<128, AMODE_PLAIN, EPI_STORE>(d->tc_kind, p, d->Wtc, 1, stream, "tc_dense<128>");
             case 256: return launch_tc_kind<256, AMODE_PLAIN, EPI_STORE>(d->tc_kind, p, d->Wtc, 1, stream, "tc_dense<256>");
-            default:  MORIG_CHECK_ARG(false, "dense_fwd: tc_bn=%d unsupported (64,128,256)", d->tc_bn);
+            default:  MORIG_CHECK_ARG(false, "dense_fwd: tc_bn=%d unsupported (128,256)", d->tc_bn);
         }
     }
     if (d->N <= 64) {
@@ -445,8 +444,7 @@ extern "C" MORIG_API int morig_edgeconv_fwd(const morig_edge_desc *d, void *stre
             p.w_inv = d->tc_w_inv;
         }
         const int kind = d->tc_kind;
-        if (H == 64)  return launch_tc_kind<64, AMODE_GATHER, EPI_SEGMAX>(kind, p, d->W1tc, d->n_frames, stream, "tc_edge<64>");
-        if (H == 128) return launch_tc_kind<128, AMODE_GATHER, EPI_SEGMAX>(kind, p, d->W1tc, d->n_frames, stream, "tc_edge<128>");
+        if (H <= 128) return launch_tc_kind<128, AMODE_GATHER, EPI_SEGMAX>(kind, p, d->W1tc, d->n_frames, stream, "tc_edge<128>");
         return launch_tc_kind<256, AMODE_GATHER, EPI_SEGMAX>(kind, p, d->W1tc, d->n_frames, stream, "tc_edge<256>");
     }
     if (H == 64) {

@@ -12,27 +12,35 @@
 //              producing kernel maintains (GemmP::amax_in / amax_out); the epilogue multiplies by the exact inverse.
 //              Elements down to 2^-17 of the buffer's max keep all 22 bits (fp16 subnormals resolve 2^-24 * 2^-15).
 //
+// The MMA is issued "transposed": the WEIGHT image is the tensor core's A operand (M = 128 output channels per CTA)
+// and the activation stage its B operand (N = 128 rows per CTA), so the accumulator in TMEM is D^T -- TMEM lane =
+// output channel, TMEM column = row (edge / vertex) of the tile.  tcgen05.ld (32 lanes x 32 columns) then hands every
+// epilogue lane ONE CHANNEL and 32 consecutive rows in registers: per-channel constants are per-lane scalars, the
+// segmented max over rows runs over registers with compile-time indices, and every global access is a coalesced
+// 128-byte row segment -- no shared-memory transposition (an earlier version staged every 32x32 block through shared
+// memory; timeline traces showed the epilogue warps, not the MMAs, bounding the fused EdgeConv kernels).
+//
 // One CTA per SM walks tiles; three roles run decoupled through mbarriers:
 //   warps 0-7   A producers: 32 k-columns per stage written straight into 128B-swizzled K-major shared memory;
 //               plain activation rows, or relu(P[tgt[e]] + Q[col[e]]) gathered per CSR slot (fused EdgeConv);
 //               the raw operands of the next chunk are in flight in registers while the current one is stored
-//   warp  12    one elected lane: cp.async.bulk of the pre-split / pre-swizzled weight image of each
-//               (n-tile, k-chunk) (TMA engine, mbarrier complete_tx) and the 12 tcgen05.mma per stage;
-//               tcgen05.commit releases stages and publishes accumulators
-//   warps 8-11  epilogue: tcgen05.ld of one of the TWO accumulator buffers (the next tile's MMAs overlap), 32x32
-//               blocks transposed through a 4 KB per-warp staging tile so that lanes become columns, then
+//   warp  16    one elected lane: cp.async.bulk of the pre-split / pre-swizzled weight image of each
+//               (n-tile, k-chunk) (TMA engine, mbarrier complete_tx) and the 12 tcgen05.mma per 128 channels and
+//               stage; tcgen05.commit releases stages and publishes accumulators
+//   warps 8-15  epilogue, two per TMEM lane quarter (= 32 channels), alternating 32-row blocks of one of the TWO
+//               accumulator buffers (the next tile's MMAs overlap):
 //               bias (+ per-graph bias) -> ReLU -> BatchNorm affine and
 //                 coalesced row stores / per-graph column max / segmented max over the CSR target
-//               (running max restarted at segment heads, flushed at tails; segments crossing a warp's 32 rows
-//                merge with ordered-int atomic max: exact and order independent, hence deterministic)
+//               (running max restarted at segment heads, flushed at tails; segments cut by a 32-row block merge
+//                with the ordered-int atomic max: exact and order independent, hence deterministic)
 //
 // Two kernels share the role code:
-//   tc_gemm_kernel<BN,...>   cta_group::1, UMMA 128 x BN; weight image streamed per stage or, when the CTA sees a
-//                            single n-tile and the image fits, kept resident in shared memory
-//   tc2_gemm_kernel<...>     cta_group::2 on a 2-CTA cluster, UMMA 256 x 256: each CTA produces its own 128 rows
-//                            of A and loads HALF of every weight chunk (the pair shares B through the tensor
-//                            core's cross-CTA operand path), which halves the L2 -> SM weight traffic that
-//                            bounds the streamed layers
+//   tc_gemm_kernel<BN,...>   cta_group::1, BN / 128 UMMAs of 128 x 128 per k-step; weight image streamed per stage or,
+//                            when the CTA sees a single n-tile and the image fits, kept resident in shared memory
+//   tc2_gemm_kernel<...>     cta_group::2 on a 2-CTA cluster, UMMA 256 x 256: CTA r holds channels [128 r, 128 r + 128)
+//                            of the n-tile (its half of every weight chunk) and produces rows [128 r, 128 r + 128) of
+//                            the 256-row pair tile (the pair shares the activation operand through the tensor core's
+//                            cross-CTA path), which halves the L2 -> SM weight traffic of the streamed layers
 #pragma once
 #include <cuda_fp16.h>
 #include "gemm_simt.cuh"
@@ -52,7 +60,7 @@ template <int KIND> struct KindCfg {
 constexpr int A_HALF_BYTES = BM * 128;       // 16 KB: hi (then lo) image of the A stage
 constexpr int A_STAGE_BYTES = 2 * A_HALF_BYTES;
 constexpr int PRODUCER_WARPS = 8;
-constexpr int EPILOGUE_WARPS = 8;                                // two per TMEM lane quarter, alternating 32-column blocks
+constexpr int EPILOGUE_WARPS = 8;                                // two per TMEM lane quarter, alternating 32-row blocks
 constexpr int CONTROL_WARP = PRODUCER_WARPS + EPILOGUE_WARPS;
 constexpr int THREADS = 32 * (PRODUCER_WARPS + EPILOGUE_WARPS + 4);    // control warp + 3 idle warps: a full warpgroup
 // Register budget: 20 warps x 96 registers at launch (640 threads cap the launch allocation at 61440 of the 65536
@@ -64,17 +72,16 @@ constexpr int THREADS = 32 * (PRODUCER_WARPS + EPILOGUE_WARPS + 4);    // contro
 constexpr int REGS_PRODUCER = 112, REGS_EPILOGUE = 104, REGS_CONTROL = 48;
 static_assert(2 * REGS_PRODUCER + 2 * REGS_EPILOGUE + REGS_CONTROL <= 5 * 96, "setmaxnreg budget exceeds the launch allocation");
 constexpr int ROWS_PER_THREAD = BM / (PRODUCER_WARPS * 4);       // 4 rows, one 16-byte fp32 chunk each
-constexpr int STG_LD = 33;                                       // staging tile row stride (floats)
-constexpr int STG_BYTES = EPILOGUE_WARPS * 32 * STG_LD * 4;      // 33 KB (the pad column of each tile holds the row keys)
 constexpr int AUX_BYTES = 1024;                                  // barriers, tmem pointer
 constexpr int PIPE_BYTES = 192 * 1024;                           // operand ring (every configuration)
-constexpr int SMEM_BYTES = PIPE_BYTES + STG_BYTES + AUX_BYTES + 1024;   // + slack for 1024 B alignment = 227 KB
+constexpr int SMEM_BYTES = PIPE_BYTES + AUX_BYTES + 1024;        // + slack for 1024 B alignment
 
 template <int BN> struct Cfg {
     static constexpr int B_HALF_BYTES = BN * 128;
     static constexpr int B_CHUNK_BYTES = 2 * B_HALF_BYTES;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_CHUNK_BYTES;
-    static constexpr int STAGES = PIPE_BYTES / STAGE_BYTES;                  // 2 / 3 / 4 for BN = 256 / 128 / 64
+    static constexpr int STAGES = PIPE_BYTES / STAGE_BYTES;                  // 2 / 3 for BN = 256 / 128
+    static constexpr int NH = BN / 128;                                      // 128-channel accumulators per buffer
     static constexpr int TMEM_COLS = 2 * BN;                                 // two accumulator buffers
     // resident-B mode (all k-chunks of the weight image stay in shared memory for the whole kernel):
     // possible when the CTA only ever sees one n-tile and the image leaves room for >= 2 A stages
@@ -196,26 +203,22 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a_desc, uint64_t 
     }
 }
 #undef MORIG_UMMA
-// asynchronous TMEM -> register load of 32 lanes x 32 columns; the registers are valid after tmem_ld_wait()
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+// asynchronous TMEM -> register load of 32 lanes x 16 columns; the registers are valid after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
-// the "+r" operands tie every later use of the registers to this wait
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+// waits for every tcgen05.ld of this thread; the "+r" operands tie every later use of both halves to this wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[16], uint32_t (&b)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
-                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
-                   "+r"(r[30]), "+r"(r[31])
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                   "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
+                   "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+                   "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
                  :: "memory");
 }
 
@@ -435,182 +438,197 @@ __device__ __forceinline__ void producer_role(const GemmP &p, float a_scale, uin
 }
 
 // ================= epilogue warps =================
-// tcgen05.ld hands every lane one accumulator ROW (32 consecutive columns).  Each 32x32 block is transposed through a
-// 4 KB per-warp staging tile so that lanes become COLUMNS: the per-column constants then live in registers, the 32
-// rows of the column are processed from registers with compile-time indices, a running max is restarted at segment
-// heads and flushed at segment tails, and every global access is a coalesced 128-byte row segment.
-// `release(buf)` hands the accumulator buffer back to the MMA issuer.
-template <int BN, int EPI, class Release>
-__device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, float *stg_all, uint8_t *aux, uint32_t aux_addr,
-                                              uint32_t tmem_base, int M, const TileMap &tm, int warp, int lane,
-                                              Release release, long long *trace = nullptr) {
-    constexpr int NB = BN / 32;                  // 32-column blocks per tile
-    static_assert(NB >= 2, "two epilogue warps share every TMEM lane quarter");   // this warp: cb = half, half + 2, ...
-    const int e = warp - PRODUCER_WARPS;         // epilogue warp 0..7
-    const int q = warp & 3;                      // TMEM lane quarter this warp may read (hardware: warp id % 4)
+// TMEM lane = output channel, TMEM column = row of the tile: tcgen05.ld gives every lane one channel and 16 consecutive
+// rows per instruction.  A warp owns the 32 channels of its lane quarter and every second 32-row block of the tile.
+// Rows of a block are walked from registers with compile-time indices; the segment structure of the block (bit masks
+// of segment heads / tails from a ballot over the row keys) is warp-uniform, so restarting the running max and
+// flushing a finished segment are uniform branches.  `release(buf)` hands the accumulator buffer back to the issuer.
+struct RowKeys { int key, ext; };                // key of row (block base + lane); lane 0 / 31: key of the row before / after the block
+
+// w[r] for a warp-uniform runtime r: a jump over 32 register moves (registers cannot be indexed dynamically)
+__device__ __forceinline__ float pick32(const float (&w)[32], int r) {
+    float x;
+    switch (r) {
+#define MORIG_PICK(i) case i: x = w[i]; break;
+        MORIG_PICK(0) MORIG_PICK(1) MORIG_PICK(2) MORIG_PICK(3) MORIG_PICK(4) MORIG_PICK(5) MORIG_PICK(6) MORIG_PICK(7)
+        MORIG_PICK(8) MORIG_PICK(9) MORIG_PICK(10) MORIG_PICK(11) MORIG_PICK(12) MORIG_PICK(13) MORIG_PICK(14)
+        MORIG_PICK(15) MORIG_PICK(16) MORIG_PICK(17) MORIG_PICK(18) MORIG_PICK(19) MORIG_PICK(20) MORIG_PICK(21)
+        MORIG_PICK(22) MORIG_PICK(23) MORIG_PICK(24) MORIG_PICK(25) MORIG_PICK(26) MORIG_PICK(27) MORIG_PICK(28)
+        MORIG_PICK(29) MORIG_PICK(30)
+#undef MORIG_PICK
+        default: x = w[31]; break;
+    }
+    return x;
+}
+
+template <int CTAS, int BN, int EPI, class Release>
+__device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_t aux_addr, uint32_t tmem_base, int M,
+                                              const TileMap &tm, int rank, int warp, int lane, Release release,
+                                              long long *trace = nullptr) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr int NH = (CTAS == 1) ? BN / 128 : 1;   // 128-channel accumulators per buffer in this CTA's TMEM
+    constexpr int NRB = (CTAS == 1) ? 4 : 8;         // 32-row blocks per tile (128 rows, or the 256 rows of a pair)
+    constexpr int RBW = NRB / 2;                     // row blocks per warp
+    constexpr int BUF_COLS = (CTAS == 1) ? BN : 256; // TMEM columns per accumulator buffer
+    const int e = warp - PRODUCER_WARPS;             // epilogue warp 0..7
+    const int q = warp & 3;                          // TMEM lane quarter this warp may read (hardware: warp id % 4)
     const int half = e >> 2;
     Tracer tr{(trace && blockIdx.x == 0 && e == 0 && lane == 0) ? trace + 2 * 2048 : nullptr, 0};
-    float *stg = stg_all + e * 32 * STG_LD;      // private 32 x 33 staging tile; column 32 of row r holds key[r]
-    (void)aux;
+    const bool need_keys = (EPI == EPI_SEGMAX) || p.pool != nullptr || p.rowbias != nullptr;
+    const bool has_rb = (EPI == EPI_STORE) && p.rowbias != nullptr;
+    const bool want_max = (EPI == EPI_STORE) && p.pool != nullptr;
+    const float relu_floor = ((EPI == EPI_SEGMAX) || p.relu) ? 0.f : neg_inf();
 
-    // Everything that does not depend on the accumulator is fetched ahead so that no global-memory latency sits
-    // between two tiles: the segment key of this lane's row two tiles ahead, the tail/complete flags one tile ahead.
-    auto load_key = [&](int t) -> int {
-        if (t >= tm.total) return -1;
-        const TileCoord c = tm.decode(t);
-        const int r = c.m0 + q * 32 + lane;
-        if (r >= M) return -1;
+    auto key_of = [&](int r) -> int {
+        if (r < 0) return -2;                        // before the first row: differs from every key
+        if (r >= M) return -1;                       // past the end: never flushed
         if (EPI == EPI_SEGMAX) return p.tgt[r];
         return p.batch ? (r / p.n_vtx) * p.n_graphs + p.batch[r % p.n_vtx] : 0;
     };
-    struct Flags { uint32_t tail_mask, complete_mask; };
-    auto make_flags = [&](int t, int key) -> Flags {
-        Flags f;
-        const int key_dn = __shfl_down_sync(0xffffffffu, key, 1);
-        const bool is_tail = (key >= 0) && ((lane == 31) || (key != key_dn));
-        f.tail_mask = __ballot_sync(0xffffffffu, is_tail);
-        bool complete = false;                   // segment entirely inside this warp's 32 rows -> plain store
-        if (EPI == EPI_SEGMAX && is_tail) {
-            const int rbase = tm.decode(t).m0 + q * 32;
-            complete = p.rowptr[key] >= rbase && p.rowptr[key + 1] <= rbase + 32;
-        }
-        f.complete_mask = __ballot_sync(0xffffffffu, complete);
-        return f;
+    auto tile_row0 = [&](int t) { return tm.decode(t).m0 - (CTAS == 2 ? rank * BM : 0); };
+    // keys of the i-th row block of this warp in tile t; fetched one tile ahead so that no global-memory latency
+    // sits between two tiles
+    auto load_keys = [&](int t, int i) -> RowKeys {
+        RowKeys k; k.key = -1; k.ext = -1;
+        if (!need_keys || t >= tm.total) return k;
+        const int rbase = tile_row0(t) + (half + 2 * i) * 32;
+        k.key = key_of(rbase + lane);
+        if (EPI == EPI_SEGMAX && (lane == 0 || lane == 31)) k.ext = key_of(lane == 0 ? rbase - 1 : rbase + 32);
+        return k;
     };
 
-    int key_cur = load_key(tm.first);
-    int key_nxt = load_key(tm.first + tm.step);
-    Flags fl_cur = make_flags(tm.first, key_cur);
+    RowKeys nxt[RBW];
+#pragma unroll
+    for (int i = 0; i < RBW; ++i) nxt[i] = load_keys(tm.first, i);
     float amax_l = 0.f;                              // max |stored value| seen by this lane (GemmP::amax_out)
 
     int li = 0;
     for (int t = tm.first; t < tm.total; t += tm.step, ++li) {
         const TileCoord tcd = tm.decode(t);
         const int buf = li & 1;
-        const int n0 = tcd.n_tile * BN;
-        const int rbase = tcd.m0 + q * 32;       // first row (CSR slot) of this warp
-        const int valid_rows = min(32, max(0, M - rbase));
-        const int key = key_cur;
-        const Flags fl = fl_cur;
-        // look-ahead: key two tiles ahead (load), flags one tile ahead (needs its key, loaded a tile ago)
-        const int key_nn = load_key(t + 2 * tm.step);
-        if (t + tm.step < tm.total) fl_cur = make_flags(t + tm.step, key_nxt);
-        key_cur = key_nxt;
-        key_nxt = key_nn;
-
+        const int row0 = tcd.m0 - (CTAS == 2 ? rank * BM : 0);
+        const int n0 = tcd.n_tile * ((CTAS == 1) ? BN : 256) + (CTAS == 2 ? rank * 128 : 0) + q * 32 + lane;
+        RowKeys cur[RBW];
+#pragma unroll
+        for (int i = 0; i < RBW; ++i) { cur[i] = nxt[i]; nxt[i] = load_keys(t + tm.step, i); }
         const size_t frame_base = (EPI == EPI_SEGMAX) ? (size_t)tcd.frame * p.n_vtx_frame : 0;
-        __syncwarp();
-        stg[lane * STG_LD + 32] = __int_as_float(key);
-        const float relu_floor = ((EPI == EPI_SEGMAX) || p.relu) ? 0.f : neg_inf();
-        const bool has_rb = (EPI == EPI_STORE) && p.rowbias != nullptr;
-        const uint32_t tails = fl.tail_mask;
-        // fast path: a full 32-row block (all but the last tile) and, for the dense epilogue, a single segment
-        // (tiles that straddle two graphs of the batch take the general path)
-        const bool fast = valid_rows == 32 && (EPI == EPI_SEGMAX || tails == 0x80000000u);
 
         tr(10);
         mbar_wait(aux_addr + AUX_ACC_FULL + 8u * buf, (uint32_t)((li >> 1) & 1));
         tr(11);
         tc_fence_after();
-        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BUF_COLS);
         uint32_t v[32];
-        tmem_ld32_issue(tbase + (uint32_t)(half * 32), v);
-        // The block loop is deliberately NOT unrolled: the walk below is ~400 instructions of straight-line code and
-        // sixteen warps of two roles share the instruction cache.
+        uint32_t (&va)[16] = reinterpret_cast<uint32_t (&)[16]>(v[0]);
+        uint32_t (&vb)[16] = reinterpret_cast<uint32_t (&)[16]>(v[16]);
+        tmem_ld16_issue(tbase + (uint32_t)(half * 32), va);
+        tmem_ld16_issue(tbase + (uint32_t)(half * 32 + 16), vb);
+        // The unit loop is deliberately NOT unrolled: twenty warps of three roles share the instruction cache.
 #pragma unroll 1
-        for (int cb = half; cb < NB; cb += 2) {
-            const int col0 = cb * 32;
-            const int nl = n0 + col0 + lane;
+        for (int u = 0; u < RBW * NH; ++u) {
+            const int i = u / NH, h = u - i * NH;
+            const int rb = half + 2 * i;
+            const int rbase = row0 + rb * 32;        // first row of the block
+            const int valid_rows = min(32, max(0, M - rbase));
+            const int nl = n0 + h * 128;             // this lane's output channel
             const bool nl_ok = nl < p.N;
-            // per-column constants (L1/L2 hits; their latency hides behind the accumulator load and the transposition)
+            // per-channel constants (L1/L2 hits; their latency hides behind the accumulator load)
             const float bias_l = (nl_ok && p.bias) ? p.bias[nl] : 0.f;
             const float scale_l = (nl_ok && p.scale) ? p.scale[nl] : 1.f;
             const float shift_l = (nl_ok && p.shift) ? p.shift[nl] : 0.f;
-            tmem_ld_wait(v);
-            tr(13);
-            __syncwarp();                        // previous block's reads of the staging tile are done
+            // segment structure of the block: warp-uniform masks
+            RowKeys rk = cur[0];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) stg[lane * STG_LD + j] = __uint_as_float(v[j]);
-            __syncwarp();
-            tr(14);
-            if (cb + 2 < NB) tmem_ld32_issue(tbase + (uint32_t)(col0 + 64), v);   // overlaps this block's walk
-            // lane = column from here on; rows of this column are read back from the staging tile
-            float *crow = (EPI == EPI_STORE && p.C) ? p.C + (size_t)rbase * p.ldc + nl : nullptr;
-            auto seg_key = [&](int r) { return __float_as_int(stg[r * STG_LD + 32]); };
-            auto flush = [&](int r, float m) {              // the segment ending at row r is complete (warp-uniform call)
-                if (!nl_ok) return;
-                const int k_seg = seg_key(r);
+            for (int ii = 1; ii < RBW; ++ii) if (ii == i) rk = cur[ii];
+            const int key = rk.key;
+            uint32_t tails = 0x80000000u;
+            bool first_cut = false, last_cut = false;
+            int first_tail = 31;
+            if (need_keys) {
+                const int key_dn = __shfl_down_sync(FULL, key, 1);
+                tails = __ballot_sync(FULL, (lane == 31) || (key != key_dn));
+                if (EPI == EPI_SEGMAX) {
+                    first_cut = __shfl_sync(FULL, key, 0) == __shfl_sync(FULL, rk.ext, 0);     // continues from the previous block
+                    last_cut = __shfl_sync(FULL, key, 31) == __shfl_sync(FULL, rk.ext, 31);    // ... into the next block
+                    first_tail = __ffs(tails) - 1;
+                }
+            }
+            const uint32_t heads = (tails << 1) | 1u;
+            float *crow = (EPI == EPI_STORE && p.C && nl_ok) ? p.C + (size_t)rbase * p.ldc + nl : nullptr;
+            auto flush = [&](int r, float m) {       // the segment ending at row r is complete (warp-uniform call)
+                const int k_seg = __shfl_sync(FULL, key, r);
+                if (k_seg < 0 || !nl_ok) return;
                 if (EPI == EPI_SEGMAX) {
                     float *dst = p.C + (frame_base + k_seg) * (size_t)p.ldc + nl;
-                    if ((fl.complete_mask >> r) & 1u) *dst = m;
-                    else atomic_max_f32(dst, m);
-                } else if (p.pool) {
+                    if ((first_cut && r == first_tail) || (last_cut && r == 31)) atomic_max_f32(dst, m);
+                    else *dst = m;
+                    amax_l = fmaxf(amax_l, fabsf(m));                         // only the maxima are stored
+                } else {
                     atomic_max_f32(p.pool + (size_t)k_seg * p.ldpool + nl, m);
                 }
             };
-            if (fast) {
-                // Branch-free straight-line code over the 32 rows.  Segment boundaries are warp-uniform bit masks
-                // (every lane walks the same rows): the running max restarts at heads, its value after every row goes
-                // back to the staging tile (this lane's own column), and a short loop over the tails flushes results.
-                const uint32_t heads = (tails << 1) | 1u;
-                float b_cur = bias_l;
-                if (has_rb && nl_ok) {
-                    const int k_seg = seg_key(31);
-                    if (k_seg >= 0) b_cur += p.rowbias[(size_t)k_seg * p.ldrb + nl];
+            auto head_bias = [&](int r) -> float {   // per-graph bias of the segment starting at row r (uniform call)
+                const int k_seg = __shfl_sync(FULL, key, r);
+                return (has_rb && k_seg >= 0 && nl_ok) ? p.rowbias[(size_t)k_seg * p.ldrb + nl] : 0.f;
+            };
+            tmem_ld_wait(va, vb);
+            tr(13);
+            float w[32];
+            if (EPI == EPI_SEGMAX) {
+                // Straight-line code (32 independent rows give the FP pipes their instruction-level parallelism; a
+                // branch per row made every row its own dependent chain): bias -> ReLU -> BatchNorm affine, then the
+                // running max restarts at segment heads; the value after the last row of a segment is its maximum.
+#pragma unroll
+                for (int r = 0; r < 32; ++r)
+                    w[r] = fmaf(fmaxf(fmaf(__uint_as_float(v[r]), inv, bias_l), 0.f), scale_l, shift_l);
+#pragma unroll
+                for (int r = 1; r < 32; ++r) w[r] = ((heads >> r) & 1u) ? w[r] : fmaxf(w[r - 1], w[r]);
+                for (uint32_t tl = tails; tl; tl &= tl - 1) {
+                    const int r = __ffs(tl) - 1;
+                    flush(r, pick32(w, r));
                 }
-                float m = neg_inf();
-                float am_blk = 0.f;
+            } else if (tails == 0x80000000u && valid_rows == 32) {
+                // dense layer, one segment (graph) in the block: straight-line stores, one pooled max at the end
+                const float b_cur = bias_l + (has_rb ? head_bias(0) : 0.f);
+                float am0 = 0.f, am1 = 0.f;
 #pragma unroll
-                for (int hb = 0; hb < 2; ++hb) {
-                    float xr[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) xr[j] = stg[(hb * 16 + j) * STG_LD + lane];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int r = hb * 16 + j;
-                        const float x = fmaxf(fmaf(xr[j], inv, b_cur), relu_floor);   // inv undoes the fp16 operand scales
-                        const float z = fmaf(x, scale_l, shift_l);       // BatchNorm affine BEFORE any max (scale may be < 0)
-                        am_blk = fmaxf(am_blk, fabsf(z));
-                        if (EPI == EPI_STORE) {
-                            if (crow && nl_ok) crow[(size_t)r * p.ldc] = z;
-                            m = fmaxf(m, z);
-                        } else {
-                            m = fmaxf(((heads >> r) & 1u) ? neg_inf() : m, z);
-                            stg[r * STG_LD + lane] = m;
-                        }
-                    }
+                for (int r = 0; r < 32; ++r) {
+                    w[r] = fmaf(fmaxf(fmaf(__uint_as_float(v[r]), inv, b_cur), relu_floor), scale_l, shift_l);
+                    if (r & 1) am1 = fmaxf(am1, fabsf(w[r])); else am0 = fmaxf(am0, fabsf(w[r]));
+                    if (crow) crow[(size_t)r * p.ldc] = w[r];
                 }
-                if (nl_ok) amax_l = fmaxf(amax_l, am_blk);
-                if (EPI == EPI_STORE) {
-                    flush(31, m);
-                } else {
-                    uint32_t tl = tails;
-                    while (tl) {
-                        const int r = __ffs(tl) - 1;
-                        flush(r, stg[r * STG_LD + lane]);
-                        tl &= tl - 1;
-                    }
+                if (nl_ok) amax_l = fmaxf(amax_l, fmaxf(am0, am1));
+                if (want_max) {
+#pragma unroll
+                    for (int st = 16; st > 0; st >>= 1)
+#pragma unroll
+                        for (int r = 0; r < st; ++r) w[r] = fmaxf(w[r], w[r + st]);
+                    flush(31, w[0]);
                 }
             } else {
-                // general path (ragged last tile, tiles that straddle graphs): walk segment by segment
-                uint32_t tl = tails;
-                int rr = 0;
-                while (rr < valid_rows) {
-                    const int seg_end = tl ? (__ffs(tl) - 1) : (valid_rows - 1);
-                    const int k_seg = seg_key(seg_end);
-                    float b_seg = bias_l;
-                    if (has_rb && nl_ok && k_seg >= 0) b_seg += p.rowbias[(size_t)k_seg * p.ldrb + nl];
-                    float m = neg_inf();
-                    for (; rr <= seg_end; ++rr) {
-                        const float x = fmaxf(fmaf(stg[rr * STG_LD + lane], inv, b_seg), relu_floor);
-                        const float z = fmaf(x, scale_l, shift_l);
-                        if (nl_ok) amax_l = fmaxf(amax_l, fabsf(z));
-                        if (EPI == EPI_STORE && crow && nl_ok) crow[(size_t)rr * p.ldc] = z;
-                        m = fmaxf(m, z);
+                // dense layer, general block (ragged last tile, block straddling two graphs): row by row
+                float b_cur = bias_l, m = neg_inf(), am = 0.f;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    if ((heads >> r) & 1u) b_cur = bias_l + head_bias(r);       // uniform branch
+                    const float z = fmaf(fmaxf(fmaf(__uint_as_float(v[r]), inv, b_cur), relu_floor), scale_l, shift_l);
+                    if (r < valid_rows) {
+                        am = fmaxf(am, fabsf(z));
+                        if (crow) crow[(size_t)r * p.ldc] = z;
                     }
-                    if (tl) flush(seg_end, m);
-                    tl &= tl - 1;
+                    if (want_max) {
+                        m = ((heads >> r) & 1u) ? z : fmaxf(m, z);
+                        if ((tails >> r) & 1u) flush(r, m);                   // uniform branch
+                    }
                 }
+                if (nl_ok) amax_l = fmaxf(amax_l, am);
+            }
+            if (u + 1 < RBW * NH) {
+                // next unit: same row block, next channel half -- or the next row block
+                const int un = u + 1, in_ = un / NH, hn = un - in_ * NH;
+                const uint32_t tnext = tbase + (uint32_t)(hn * 128 + (half + 2 * in_) * 32);
+                tmem_ld16_issue(tnext, va);
+                tmem_ld16_issue(tnext + 16u, vb);
             }
             tr(16);
         }
@@ -624,7 +642,7 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, float *
 }
 
 // =============================================================================================================
-// cta_group::1 kernel: UMMA 128 x BN
+// cta_group::1 kernel: BN / 128 UMMAs of 128 (channels) x 128 (rows) per k-step
 // =============================================================================================================
 template <int KIND, int BN, int AMODE, int EPI>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
@@ -641,9 +659,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
     const uint32_t a_stride = resb ? (uint32_t)A_STAGE_BYTES : (uint32_t)C::STAGE_BYTES;
     const uint32_t b_region = resb ? (uint32_t)(S * A_STAGE_BYTES) : (uint32_t)A_STAGE_BYTES;
     const uint32_t b_stride = resb ? (uint32_t)C::B_CHUNK_BYTES : (uint32_t)C::STAGE_BYTES;
-    float *stg_all = reinterpret_cast<float *>(smem + PIPE_BYTES);
-    uint8_t *aux = smem + PIPE_BYTES + STG_BYTES;
-    const uint32_t aux_addr = base + PIPE_BYTES + STG_BYTES;
+    uint8_t *aux = smem + PIPE_BYTES;
+    const uint32_t aux_addr = base + PIPE_BYTES;
     auto bar_a = [&](int s) { return aux_addr + AUX_A_FULL + 8u * s; };
     auto bar_b = [&](int s) { return aux_addr + AUX_B_FULL + 8u * s; };
     auto bar_m = [&](int s) { return aux_addr + AUX_MMA_DONE + 8u * s; };
@@ -692,7 +709,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
         if (warp == CONTROL_WARP) {
             const bool leader = lane == 0;
             Tracer tr{(tp.trace && blockIdx.x == 0 && leader) ? tp.trace + 2048 : nullptr, 0};
-            const uint32_t idesc = make_idesc<KIND>(BM, BN);
+            const uint32_t idesc = make_idesc<KIND>(128, BM);      // M = 128 output channels, N = the tile's 128 rows
             const uint32_t b_bytes = (uint32_t)C::B_CHUNK_BYTES;
             const uint8_t *gB = reinterpret_cast<const uint8_t *>(tp.Bblob);
             const int my_tiles = tm.my_tiles();
@@ -749,9 +766,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
                     if (leader) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {                // 8 tf32 / 16 fp16 = 32 bytes along the swizzled row
-                            umma<KIND, 1>(tmem_d, desc64(lal + 2 * k), desc64(lbh + 2 * k), idesc, (kc | k) != 0);
-                            umma<KIND, 1>(tmem_d, desc64(lah + 2 * k), desc64(lbl + 2 * k), idesc, 1);
-                            umma<KIND, 1>(tmem_d, desc64(lah + 2 * k), desc64(lbh + 2 * k), idesc, 1);
+#pragma unroll
+                            for (int h = 0; h < C::NH; ++h) {        // weights = A operand (rows 128 h .. of the image)
+                                const uint32_t wo = (uint32_t)(h * 128 * 128) >> 4;
+                                const uint32_t td = tmem_d + (uint32_t)(h * 128);
+                                umma<KIND, 1>(td, desc64(lbh + wo + 2 * k), desc64(lal + 2 * k), idesc, (kc | k) != 0);
+                                umma<KIND, 1>(td, desc64(lbl + wo + 2 * k), desc64(lah + 2 * k), idesc, 1);
+                                umma<KIND, 1>(td, desc64(lbh + wo + 2 * k), desc64(lah + 2 * k), idesc, 1);
+                            }
                         }
                         umma_commit<1>(bar_m(s));                    // frees stage s when these MMAs retire
                     }
@@ -775,8 +797,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
                                    [&](int s) { mbar_arrive(bar_a(s)); }, tp.trace);
     } else {
         reg_inc<REGS_EPILOGUE>();
-        epilogue_role<BN, EPI>(p, inv, stg_all, aux, aux_addr, tmem_base, M, tm, warp, lane,
-                               [&](int b) { mbar_arrive(bar_acce(b)); }, tp.trace);
+        epilogue_role<1, BN, EPI>(p, inv, aux_addr, tmem_base, M, tm, 0, warp, lane,
+                                  [&](int b) { mbar_arrive(bar_acce(b)); }, tp.trace);
     }
     tc_fence_before();
     __syncthreads();
@@ -784,9 +806,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
 }
 
 // =============================================================================================================
-// cta_group::2 kernel: 2-CTA cluster, UMMA 256 x BN2 (BN2 = 256 or 128).  CTA rank r of the pair owns rows (2*mp + r)*128.. of the
-// pair-tile and rows [r*128, r*128+128) of every weight chunk.  Only the leader (rank 0) issues MMAs; its barriers
-// collect the arrivals of both CTAs, and tcgen05.commit multicasts completions to both.
+// cta_group::2 kernel: 2-CTA cluster, UMMA 256 (channels) x 256 (rows).  CTA rank r of the pair holds channels
+// [128 r, 128 r + 128) of the n-tile (rows of every weight chunk) in its TMEM lanes and produces rows (2*mp + r)*128..
+// of the pair-tile.  Only the leader (rank 0) issues MMAs; its barriers collect the arrivals of both CTAs, and
+// tcgen05.commit multicasts completions to both.
 // =============================================================================================================
 template <int BN2> struct Cfg2 {
     static constexpr int HALF_B = (BN2 / 2) * 128;                              // this CTA's rows of the hi (or lo) image
@@ -803,6 +826,7 @@ template <int BN2> struct Cfg2 {
 
 template <int KIND, int BN2, int AMODE, int EPI>
 __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
+    static_assert(BN2 == 256, "the pair kernel needs 128 channels (TMEM lanes) per CTA");
     using C2 = Cfg2<BN2>;
     const GemmP &p = tp.g;
     extern __shared__ uint8_t smem_raw[];
@@ -818,9 +842,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
     const uint32_t a_stride = resb ? (uint32_t)A_STAGE_BYTES : (uint32_t)C2::STAGE_BYTES;
     const uint32_t b_region = resb ? (uint32_t)(S * A_STAGE_BYTES) : (uint32_t)A_STAGE_BYTES;
     const uint32_t b_stride = resb ? (uint32_t)C2::B_BYTES : (uint32_t)C2::STAGE_BYTES;
-    float *stg_all = reinterpret_cast<float *>(smem + PIPE_BYTES);
-    uint8_t *aux = smem + PIPE_BYTES + STG_BYTES;
-    const uint32_t aux_addr = base + PIPE_BYTES + STG_BYTES;
+    uint8_t *aux = smem + PIPE_BYTES;
+    const uint32_t aux_addr = base + PIPE_BYTES;
     auto bar_a = [&](int s) { return aux_addr + AUX_A_FULL + 8u * s; };        // leader: 8 producer warps of the pair
     auto bar_b = [&](int s) { return aux_addr + AUX_B_FULL + 8u * s; };        // local: this CTA's half chunk landed
     auto bar_bp = [&](int s) { return aux_addr + AUX_B_PEER + 8u * s; };       // leader: the peer's half landed
@@ -905,7 +928,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
             int s = 0, prev_s = 0;
             uint32_t ph = 0, prev_ph = 0;
             bool first = true;
-            const uint32_t idesc = make_idesc<KIND>(2 * BM, BN2);
+            const uint32_t idesc = make_idesc<KIND>(BN2, 2 * BM);     // M = 256 channels, N = 256 rows over the pair
             Tracer tr{(tp.trace && blockIdx.x == 0 && leader) ? tp.trace + 2048 : nullptr, 0};
             if (!(resb && rank != 0)) {                            // resident mode: the peer's control warp is done
                 for (int li = 0; li < my_tiles; ++li) {
@@ -931,10 +954,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
                             const uint32_t lbh = desc_lo(b_hi), lbl = desc_lo(b_hi + HALF_B);
                             if (leader) {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    umma<KIND, 2>(tmem_d, desc64(lal + 2 * k), desc64(lbh + 2 * k), idesc, (kc | k) != 0);
-                                    umma<KIND, 2>(tmem_d, desc64(lah + 2 * k), desc64(lbl + 2 * k), idesc, 1);
-                                    umma<KIND, 2>(tmem_d, desc64(lah + 2 * k), desc64(lbh + 2 * k), idesc, 1);
+                                for (int k = 0; k < 4; ++k) {                  // weights = A operand, activations = B
+                                    umma<KIND, 2>(tmem_d, desc64(lbh + 2 * k), desc64(lal + 2 * k), idesc, (kc | k) != 0);
+                                    umma<KIND, 2>(tmem_d, desc64(lbl + 2 * k), desc64(lah + 2 * k), idesc, 1);
+                                    umma<KIND, 2>(tmem_d, desc64(lbh + 2 * k), desc64(lah + 2 * k), idesc, 1);
                                 }
                                 umma_commit<2>(bar_m(s));                      // both CTAs: stage s free when retired
                             }
@@ -962,7 +985,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
         }, tp.trace);
     } else {
         reg_inc<REGS_EPILOGUE>();
-        epilogue_role<BN2, EPI>(p, inv, stg_all, aux, aux_addr, tmem_base, M, tm, warp, lane, [&](int b) {
+        epilogue_role<2, BN2, EPI>(p, inv, aux_addr, tmem_base, M, tm, (int)rank, warp, lane, [&](int b) {
             if (rank == 0) mbar_arrive(bar_acce(b));
             else mbar_arrive_cluster(bar_acce(b), 0);
         }, tp.trace);

@@ -66,8 +66,9 @@ def tf32_rna(x32: torch.Tensor) -> torch.Tensor:
 
 
 def tc_tile_n(n: int) -> int:
-    """n-tile (UMMA N) used by the tcgen05 engine for a layer with n outputs"""
-    return 64 if n <= 64 else (128 if n <= 128 else 256)
+    """n-tile (output channels per tile = 128 TMEM lanes per accumulator) used by the tcgen05 engine for a layer
+    with n outputs; narrower layers are zero-padded to 128 channels"""
+    return 128 if n <= 128 else 256
 
 
 KIND_TF32, KIND_F16 = 0, 1
@@ -197,7 +198,7 @@ def _edge_mlp_parts(sd, prefix: str):
     br = EdgeBranch(W1=_pack_wt(w1f), b1=_vec(b1f), scale=_vec(s1), shift=_vec(t1), H=w1.shape[0])
     if br.H in (64, 128, 256):
         br.tc_kind = tc_kind()
-        br.W1tc, br.tc_w_inv = pack_tc_blob(w1f, br.H, br.H, br.tc_kind)
+        br.W1tc, br.tc_w_inv = pack_tc_blob(w1f, br.H, tc_tile_n(br.H), br.tc_kind)
     return wa - wb, wb, b0, br
 
 

@@ -30,7 +30,7 @@ def make_case(which, kind, frames):
         pq = torch.randn(n * frames, 2 * H, generator=gen).to(DEV)
         W1 = torch.randn(H, H, generator=gen, dtype=torch.float64) / H ** 0.5
         vec = lambda: torch.randn(H, generator=gen).to(DEV)
-        blob, w_inv = packing.pack_tc_blob(W1, H, H, kind)
+        blob, w_inv = packing.pack_tc_blob(W1, H, packing.tc_tile_n(H), kind)
         br = packing.EdgeBranch(W1=packing._pack_wt(W1).to(DEV), b1=vec(), scale=vec(), shift=vec(), H=H,
                                 W1tc=blob.to(DEV), tc_kind=kind, tc_w_inv=w_inv)
         o = torch.empty(n * frames, H, device=DEV)
@@ -59,7 +59,7 @@ with engine.forward_scope(WS, DEV):
     case()
     lib.morig_debug_set_trace(None)
 torch.cuda.synchronize()
-tr = buf.cpu().view(3, 2048, 2)[:, :1024]
+tr = buf.cpu().view(6, 1024, 2)[:3]          # roles are 2048 int64 slots (= 1024 events) apart
 for role, nm in enumerate(["producer(w0)", "control", "epilogue(w4)"]):
     ev = [(int(a), int(b)) for a, b in tr[role].tolist() if a != 0]
     if not ev:
