@@ -41,6 +41,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd = [NVCC, "-c", src, "-o", obj] + [f for f in FLAGS if f not in ("--shared", "-lcuda")]
         if verbose:
             cmd += ["-Xptxas", "-v"]
+        if os.environ.get("MORIG_TRACE") == "1":         # role timeline of scripts/tc_trace.py
+            cmd += ["-DMORIG_TRACE"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

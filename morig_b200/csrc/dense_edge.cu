@@ -388,6 +388,7 @@ extern "C" MORIG_API int morig_dense_fwd(const morig_dense_desc *d, void *stream
         MORIG_CHECK_ARG(aligned16(d->Wtc), "dense_fwd: Wtc must be 16B aligned");
         MORIG_CHECK_ARG(ceil_div(d->M, 128) <= 65535, "dense_fwd: M=%d too large for one launch", d->M);
         MORIG_CHECK_ARG((uint64_t)d->M * (uint64_t)d->lda < (1ull << 32), "dense_fwd: M*lda exceeds 32-bit element offsets");
+        MORIG_CHECK_ARG((uint64_t)d->M * (uint64_t)(d->C ? d->ldc : 1) < (1ull << 32), "dense_fwd: M*ldc exceeds 32-bit element offsets");
         MORIG_CHECK_ARG(d->tc_kind == tc::KIND_TF32 || d->tc_kind == tc::KIND_F16, "dense_fwd: tc_kind=%d", d->tc_kind);
         if (d->tc_kind == tc::KIND_F16) {
             MORIG_CHECK_ARG(d->a_amax && d->tc_w_inv > 0.f, "dense_fwd: the fp16 kind needs a_amax and tc_w_inv");
@@ -438,6 +439,8 @@ extern "C" MORIG_API int morig_edgeconv_fwd(const morig_edge_desc *d, void *stre
         MORIG_CHECK_ARG(ceil_div(d->E_max, 128) <= 65535, "edgeconv_fwd: E=%d too large for one launch", d->E_max);
         MORIG_CHECK_ARG((uint64_t)d->N * (uint64_t)d->n_frames * (uint64_t)d->ldpq < (1ull << 32),
                         "edgeconv_fwd: PQ exceeds 32-bit element offsets");
+        MORIG_CHECK_ARG((uint64_t)d->N * (uint64_t)d->n_frames * (uint64_t)d->ldo < (1ull << 32),
+                        "edgeconv_fwd: out exceeds 32-bit element offsets");
         MORIG_CHECK_ARG(d->tc_kind == tc::KIND_TF32 || d->tc_kind == tc::KIND_F16, "edgeconv_fwd: tc_kind=%d", d->tc_kind);
         if (d->tc_kind == tc::KIND_F16) {
             MORIG_CHECK_ARG(d->pq_amax && d->tc_w_inv > 0.f, "edgeconv_fwd: the fp16 kind needs pq_amax and tc_w_inv");

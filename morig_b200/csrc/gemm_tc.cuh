@@ -74,7 +74,9 @@ static_assert(2 * REGS_PRODUCER + 2 * REGS_EPILOGUE + REGS_CONTROL <= 5 * 96, "s
 constexpr int ROWS_PER_THREAD = BM / (PRODUCER_WARPS * 4);       // 4 rows, one 16-byte fp32 chunk each
 constexpr int AUX_BYTES = 1024;                                  // barriers, tmem pointer
 constexpr int PIPE_BYTES = 192 * 1024;                           // operand ring (every configuration)
-constexpr int SMEM_BYTES = PIPE_BYTES + AUX_BYTES + 1024;        // + slack for 1024 B alignment
+constexpr int KEYS_PER_WARP = 4 * 32 + 8;                        // row keys of a warp's (up to) 4 row blocks + before/after pairs
+constexpr int KEYS_BYTES = EPILOGUE_WARPS * KEYS_PER_WARP * 4;
+constexpr int SMEM_BYTES = PIPE_BYTES + AUX_BYTES + KEYS_BYTES + 1024;   // + slack for 1024 B alignment
 
 template <int BN> struct Cfg {
     static constexpr int B_HALF_BYTES = BN * 128;
@@ -123,24 +125,28 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 // Waits use the default acquire at CTA scope also for barriers that are signalled from the peer CTA or by a multicast
 // tcgen05.commit: `.acquire.cluster` makes ptxas append CCTL.IVALL (an L1 invalidation of the whole SM, i.e. of the
 // P[tgt] lines the producers keep hitting) to every successful wait.
+// try_wait carries a suspend-time hint: the hardware parks the warp until the phase completes or the hint (in ns)
+// expires, so a waiting role does not burn issue slots of the producers / epilogue warps sharing its scheduler
+// (ncu: 9 % of all executed instructions were wait-loop iterations before the hint was added).
 template <bool CLUSTER>
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        "}" : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
     return ok != 0;
 }
 // A pipeline bug must surface as a launch failure, never as a hung GPU: trap after ~2 s of waiting.
 template <bool CLUSTER = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait<CLUSTER>(bar, parity)) return;
+    uint32_t spins = 0;
     const long long t0 = clock64();
     while (!mbar_try_wait<CLUSTER>(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if ((++spins & 63u) == 0 && clock64() - t0 > 4000000000LL) __trap();
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -271,10 +277,15 @@ struct TcP {
 
 struct TileCoord { int n_tile, m0, frame; };
 
+// role timeline for scripts/tc_trace.py; compiled in only with -DMORIG_TRACE (MORIG_TRACE=1 python -m morig_b200.build)
 struct Tracer {
     long long *buf; int n;
     __device__ __forceinline__ void operator()(int tag) {
+#ifdef MORIG_TRACE
         if (buf && n < 1024) { buf[2 * n] = tag; buf[2 * n + 1] = clock64(); ++n; }
+#else
+        (void)tag;
+#endif
     }
 };
 
@@ -443,7 +454,6 @@ __device__ __forceinline__ void producer_role(const GemmP &p, float a_scale, uin
 // Rows of a block are walked from registers with compile-time indices; the segment structure of the block (bit masks
 // of segment heads / tails from a ballot over the row keys) is warp-uniform, so restarting the running max and
 // flushing a finished segment are uniform branches.  `release(buf)` hands the accumulator buffer back to the issuer.
-struct RowKeys { int key, ext; };                // key of row (block base + lane); lane 0 / 31: key of the row before / after the block
 
 // w[r] for a warp-uniform runtime r: a jump over 32 register moves (registers cannot be indexed dynamically)
 __device__ __forceinline__ float pick32(const float (&w)[32], int r) {
@@ -462,9 +472,9 @@ __device__ __forceinline__ float pick32(const float (&w)[32], int r) {
 }
 
 template <int CTAS, int BN, int EPI, class Release>
-__device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_t aux_addr, uint32_t tmem_base, int M,
-                                              const TileMap &tm, int rank, int warp, int lane, Release release,
-                                              long long *trace = nullptr) {
+__device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_t aux_addr, int *keys_smem,
+                                              uint32_t tmem_base, int M, const TileMap &tm, int rank, int warp, int lane,
+                                              Release release, long long *trace = nullptr) {
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr int NH = (CTAS == 1) ? BN / 128 : 1;   // 128-channel accumulators per buffer in this CTA's TMEM
     constexpr int NRB = (CTAS == 1) ? 4 : 8;         // 32-row blocks per tile (128 rows, or the 256 rows of a pair)
@@ -479,27 +489,32 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_
     const bool want_max = (EPI == EPI_STORE) && p.pool != nullptr;
     const float relu_floor = ((EPI == EPI_SEGMAX) || p.relu) ? 0.f : neg_inf();
 
+    // Row keys (CSR target of an edge row / graph of a vertex row) are fetched one tile ahead into registers, so that no
+    // global-memory latency sits between two tiles, and parked in a per-warp shared-memory strip for the walk (lane =
+    // row there, while the walk needs them by row index).  ext: lane 0 / 31 hold the key of the row before / after the
+    // block (-2 / -1 outside the matrix: never equal to a key).
+    int *kstrip = keys_smem + e * KEYS_PER_WARP;
     auto key_of = [&](int r) -> int {
-        if (r < 0) return -2;                        // before the first row: differs from every key
-        if (r >= M) return -1;                       // past the end: never flushed
         if (EPI == EPI_SEGMAX) return p.tgt[r];
         return p.batch ? (r / p.n_vtx) * p.n_graphs + p.batch[r % p.n_vtx] : 0;
     };
-    auto tile_row0 = [&](int t) { return tm.decode(t).m0 - (CTAS == 2 ? rank * BM : 0); };
-    // keys of the i-th row block of this warp in tile t; fetched one tile ahead so that no global-memory latency
-    // sits between two tiles
-    auto load_keys = [&](int t, int i) -> RowKeys {
-        RowKeys k; k.key = -1; k.ext = -1;
-        if (!need_keys || t >= tm.total) return k;
-        const int rbase = tile_row0(t) + (half + 2 * i) * 32;
-        k.key = key_of(rbase + lane);
-        if (EPI == EPI_SEGMAX && (lane == 0 || lane == 31)) k.ext = key_of(lane == 0 ? rbase - 1 : rbase + 32);
-        return k;
-    };
-
-    RowKeys nxt[RBW];
+    int nkey[RBW], next_[RBW];
+    auto load_keys = [&](int t) {
 #pragma unroll
-    for (int i = 0; i < RBW; ++i) nxt[i] = load_keys(tm.first, i);
+        for (int i = 0; i < RBW; ++i) { nkey[i] = -1; next_[i] = -1; }
+        if (!need_keys || t >= tm.total) return;
+        const int r0 = tm.decode(t).m0 - (CTAS == 2 ? rank * BM : 0) + half * 32;
+#pragma unroll
+        for (int i = 0; i < RBW; ++i) {
+            const int r = r0 + 64 * i + lane;
+            if (r < M) nkey[i] = key_of(r);
+            if (EPI == EPI_SEGMAX) {
+                if (lane == 0) next_[i] = (r > 0) ? ((r - 1 < M) ? key_of(r - 1) : -1) : -2;
+                if (lane == 31 && r + 1 < M) next_[i] = key_of(r + 1);
+            }
+        }
+    };
+    load_keys(tm.first);
     float amax_l = 0.f;                              // max |stored value| seen by this lane (GemmP::amax_out)
 
     int li = 0;
@@ -508,10 +523,18 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_
         const int buf = li & 1;
         const int row0 = tcd.m0 - (CTAS == 2 ? rank * BM : 0);
         const int n0 = tcd.n_tile * ((CTAS == 1) ? BN : 256) + (CTAS == 2 ? rank * 128 : 0) + q * 32 + lane;
-        RowKeys cur[RBW];
+        if (need_keys) {
+            __syncwarp();                            // the previous tile's reads of the strip are done
 #pragma unroll
-        for (int i = 0; i < RBW; ++i) { cur[i] = nxt[i]; nxt[i] = load_keys(t + tm.step, i); }
-        const size_t frame_base = (EPI == EPI_SEGMAX) ? (size_t)tcd.frame * p.n_vtx_frame : 0;
+            for (int i = 0; i < RBW; ++i) {
+                kstrip[32 * i + lane] = nkey[i];
+                if (lane == 0) kstrip[4 * 32 + 2 * i] = next_[i];
+                if (lane == 31) kstrip[4 * 32 + 2 * i + 1] = next_[i];
+            }
+            __syncwarp();
+            load_keys(t + tm.step);                  // in flight during this tile
+        }
+        const uint32_t frame_base = (EPI == EPI_SEGMAX) ? (uint32_t)(tcd.frame * p.n_vtx_frame) : 0u;
 
         tr(10);
         mbar_wait(aux_addr + AUX_ACC_FULL + 8u * buf, (uint32_t)((li >> 1) & 1));
@@ -537,39 +560,38 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_
             const float scale_l = (nl_ok && p.scale) ? p.scale[nl] : 1.f;
             const float shift_l = (nl_ok && p.shift) ? p.shift[nl] : 0.f;
             // segment structure of the block: warp-uniform masks
-            RowKeys rk = cur[0];
-#pragma unroll
-            for (int ii = 1; ii < RBW; ++ii) if (ii == i) rk = cur[ii];
-            const int key = rk.key;
+            const int *kblk = kstrip + 32 * i;
             uint32_t tails = 0x80000000u;
             bool first_cut = false, last_cut = false;
             int first_tail = 31;
             if (need_keys) {
+                const int key = kblk[lane];
                 const int key_dn = __shfl_down_sync(FULL, key, 1);
                 tails = __ballot_sync(FULL, (lane == 31) || (key != key_dn));
                 if (EPI == EPI_SEGMAX) {
-                    first_cut = __shfl_sync(FULL, key, 0) == __shfl_sync(FULL, rk.ext, 0);     // continues from the previous block
-                    last_cut = __shfl_sync(FULL, key, 31) == __shfl_sync(FULL, rk.ext, 31);    // ... into the next block
+                    first_cut = kblk[0] == kstrip[4 * 32 + 2 * i];           // segment continues from the previous block
+                    last_cut = kblk[31] == kstrip[4 * 32 + 2 * i + 1];       // ... into the next block
                     first_tail = __ffs(tails) - 1;
                 }
             }
             const uint32_t heads = (tails << 1) | 1u;
             float *crow = (EPI == EPI_STORE && p.C && nl_ok) ? p.C + (size_t)rbase * p.ldc + nl : nullptr;
+            // output offsets fit 32 bits (checked by the launchers)
             auto flush = [&](int r, float m) {       // the segment ending at row r is complete (warp-uniform call)
-                const int k_seg = __shfl_sync(FULL, key, r);
+                const int k_seg = kblk[r];
                 if (k_seg < 0 || !nl_ok) return;
                 if (EPI == EPI_SEGMAX) {
-                    float *dst = p.C + (frame_base + k_seg) * (size_t)p.ldc + nl;
+                    float *dst = p.C + ((frame_base + (uint32_t)k_seg) * (uint32_t)p.ldc + (uint32_t)nl);
                     if ((first_cut && r == first_tail) || (last_cut && r == 31)) atomic_max_f32(dst, m);
                     else *dst = m;
                     amax_l = fmaxf(amax_l, fabsf(m));                         // only the maxima are stored
                 } else {
-                    atomic_max_f32(p.pool + (size_t)k_seg * p.ldpool + nl, m);
+                    atomic_max_f32(p.pool + ((uint32_t)k_seg * (uint32_t)p.ldpool + (uint32_t)nl), m);
                 }
             };
             auto head_bias = [&](int r) -> float {   // per-graph bias of the segment starting at row r (uniform call)
-                const int k_seg = __shfl_sync(FULL, key, r);
-                return (has_rb && k_seg >= 0 && nl_ok) ? p.rowbias[(size_t)k_seg * p.ldrb + nl] : 0.f;
+                const int k_seg = kblk[r];
+                return (has_rb && k_seg >= 0 && nl_ok) ? p.rowbias[(uint32_t)k_seg * (uint32_t)p.ldrb + (uint32_t)nl] : 0.f;
             };
             tmem_ld_wait(va, vb);
             tr(13);
@@ -797,7 +819,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
                                    [&](int s) { mbar_arrive(bar_a(s)); }, tp.trace);
     } else {
         reg_inc<REGS_EPILOGUE>();
-        epilogue_role<1, BN, EPI>(p, inv, aux_addr, tmem_base, M, tm, 0, warp, lane,
+        epilogue_role<1, BN, EPI>(p, inv, aux_addr, reinterpret_cast<int *>(aux + AUX_BYTES), tmem_base, M, tm, 0, warp, lane,
                                   [&](int b) { mbar_arrive(bar_acce(b)); }, tp.trace);
     }
     tc_fence_before();
@@ -985,7 +1007,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
         }, tp.trace);
     } else {
         reg_inc<REGS_EPILOGUE>();
-        epilogue_role<2, BN2, EPI>(p, inv, aux_addr, tmem_base, M, tm, (int)rank, warp, lane, [&](int b) {
+        epilogue_role<2, BN2, EPI>(p, inv, aux_addr, reinterpret_cast<int *>(aux + AUX_BYTES), tmem_base, M, tm, (int)rank, warp,
+                                   lane, [&](int b) {
             if (rank == 0) mbar_arrive(bar_acce(b));
             else mbar_arrive_cluster(bar_acce(b), 0);
         }, tp.trace);

@@ -144,8 +144,9 @@ class DenseLayer:
         return self.W.shape[1]
 
     def with_tc(self, w_out_in: torch.Tensor, kind: Optional[int] = None) -> "DenseLayer":
-        """attach the tensor-core image when the layer is large enough to benefit (K >= 32, N >= 48)"""
-        if self.K >= 32 and self.K % 4 == 0 and self.N >= 48:
+        """attach the tensor-core image when the layer is large enough to benefit (K >= 32, N >= 16; narrow outputs are
+        zero-padded to one 128-channel tile: these layers are bound by their rows, not by the MMAs)"""
+        if self.K >= 32 and self.K % 4 == 0 and self.N >= 16:
             self.tc_bn = tc_tile_n(self.N)
             self.tc_kind = tc_kind() if kind is None else kind
             self.Wtc, self.tc_w_inv = pack_tc_blob(w_out_in, self.K, self.tc_bn, self.tc_kind)

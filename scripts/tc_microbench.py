@@ -82,7 +82,8 @@ WS = engine.Workspace()
 
 if __name__ == "__main__":
     R = 81920
-    for M, K, N in [(R, 64, 512), (R, 288, 256), (R, 256, 1024), (R, 544, 512), (R, 832, 1024), (R, 840, 1024),
+    only_edge = len(sys.argv) > 1 and sys.argv[1] == "edge"
+    for M, K, N in [] if only_edge else [(R, 64, 512), (R, 288, 256), (R, 256, 1024), (R, 544, 512), (R, 832, 1024), (R, 840, 1024),
                     (R, 1024, 256), (R, 96, 64), (16384, 64, 512), (16384, 512, 64)]:
         dense_case(M, K, N)
     for H, fr in [(64, 1), (128, 5), (256, 5), (256, 1)]:
