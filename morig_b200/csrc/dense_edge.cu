@@ -236,6 +236,56 @@ static int launch_edge_mma(const morig_edge_desc &d, cudaStream_t stream) {
     return 0;
 }
 
+// ---- skinny dense layer (M <= 32 rows) -------------------------------------------------------------
+// The per-graph layers (e.g. the [B, 1024] x [1024, 1024] bias derived from the pooled global feature,
+// models/rignet.py:64-65) have a handful of rows: the cost is streaming the weight matrix once.  A tile engine
+// would put that on N / 256 CTAs; here N / 8 CTAs each own 8 output columns, 32 thread groups split K, every
+// thread keeps the M partial sums of its column in registers, and one shared-memory pass adds the groups.
+constexpr int SKINNY_MAX_M = 32;
+constexpr int SKINNY_COLS = 8;
+constexpr int SKINNY_THREADS = 256;
+constexpr int SKINNY_KG = SKINNY_THREADS / SKINNY_COLS;
+
+__global__ void __launch_bounds__(SKINNY_THREADS) dense_skinny_kernel(const GemmP p) {
+    extern __shared__ float s_part[];               // [KG][M][COLS]
+    const int col = threadIdx.x % SKINNY_COLS, kg = threadIdx.x / SKINNY_COLS;
+    const int n = blockIdx.x * SKINNY_COLS + col;
+    const bool n_ok = n < p.N;
+    float acc[SKINNY_MAX_M];
+#pragma unroll
+    for (int m = 0; m < SKINNY_MAX_M; ++m) acc[m] = 0.f;
+    for (int k4 = 4 * kg; k4 < p.K; k4 += 4 * SKINNY_KG) {      // K % 4 == 0 (checked by the launcher)
+        float w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = n_ok ? p.W[(size_t)(k4 + j) * p.ldw + n] : 0.f;
+#pragma unroll
+        for (int m = 0; m < SKINNY_MAX_M; ++m) {
+            if (m < p.M) {
+                const float4 a = *reinterpret_cast<const float4 *>(p.A + (size_t)m * p.lda + k4);
+                acc[m] = fmaf(a.x, w[0], fmaf(a.y, w[1], fmaf(a.z, w[2], fmaf(a.w, w[3], acc[m]))));
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < SKINNY_MAX_M; ++m)
+        if (m < p.M) s_part[(kg * p.M + m) * SKINNY_COLS + col] = acc[m];
+    __syncthreads();
+    float am = 0.f;
+    for (int o = threadIdx.x; o < p.M * SKINNY_COLS; o += SKINNY_THREADS) {
+        const int m = o / SKINNY_COLS, c = o % SKINNY_COLS, nn = blockIdx.x * SKINNY_COLS + c;
+        float sum = 0.f;
+        for (int g = 0; g < SKINNY_KG; ++g) sum += s_part[(g * p.M + m) * SKINNY_COLS + c];
+        if (nn < p.N) {
+            float x = sum + (p.bias ? p.bias[nn] : 0.f);
+            if (p.relu) x = fmaxf(x, 0.f);
+            const float z = fmaf(x, p.scale ? p.scale[nn] : 1.f, p.shift ? p.shift[nn] : 0.f);
+            p.C[(size_t)m * p.ldc + nn] = z;
+            am = fmaxf(am, fabsf(z));
+        }
+    }
+    amax_commit(p.amax_out, am);
+}
+
 template <int BM, int BN, int AMODE, int EPI>
 static int launch_gemm(const GemmP &p, dim3 grid, cudaStream_t stream, const char *name) {
     auto kern = gemm_simt_kernel<BM, BN, AMODE, EPI>;
@@ -384,6 +434,12 @@ extern "C" MORIG_API int morig_dense_fwd(const morig_dense_desc *d, void *stream
     p.pool = d->pool; p.ldpool = d->ldpool;
     p.M = d->M; p.N = d->N; p.K = d->K; p.relu = d->relu;
     p.amax_in = d->a_amax; p.amax_out = d->c_amax; p.w_inv = 1.f;
+    if (d->M <= SKINNY_MAX_M && d->K >= 64 && p.a_vec && d->C && !d->pool && !d->rowbias) {
+        const size_t smem = (size_t)SKINNY_KG * d->M * SKINNY_COLS * sizeof(float);
+        dense_skinny_kernel<<<ceil_div(d->N, SKINNY_COLS), SKINNY_THREADS, smem, stream>>>(p);
+        MORIG_LAUNCH_CHECK("dense_skinny_kernel");
+        return 0;
+    }
     if (d->Wtc && p.a_vec && !tc_disabled()) {
         MORIG_CHECK_ARG(aligned16(d->Wtc), "dense_fwd: Wtc must be 16B aligned");
         MORIG_CHECK_ARG(ceil_div(d->M, 128) <= 65535, "dense_fwd: M=%d too large for one launch", d->M);

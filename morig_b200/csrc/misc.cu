@@ -25,9 +25,10 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float *__restr
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (n >= N) return;                             // whole warps leave together
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
     float am = 0.f;
+    // persistent: the 16 KB parameter image above is staged once per CTA, warps stride over the vertices
+    for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += warps_total) {
     float xt[ATT_MAX_T];
 #pragma unroll
     for (int t = 0; t < ATT_MAX_T; ++t) xt[t] = (t < T && lane < C) ? x[((size_t)n * T + t) * C + lane] : 0.f;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float *__restr
         }
         out[(size_t)n * ldo + d] = o;
         am = fmaxf(am, fabsf(o));
+    }
     }
     amax_commit(out_amax, am);
 }
@@ -155,7 +157,9 @@ extern "C" MORIG_API int morig_temporal_attn_fwd(const float *x, int32_t N, int3
     MORIG_CHECK_ARG(D >= 32 && D % 32 == 0 && (size_t)heads * C * D * 4 <= 48 * 1024,
                     "temporal_attn_fwd: D=%d unsupported (multiple of 32)", D);
     const int T_ = 256;
-    temporal_attn_kernel<<<ceil_div(N * 32, T_), T_, (size_t)heads * C * D * sizeof(float), stream>>>(
+    const int blocks = ceil_div(N * 32, T_);
+    const int cap = sm_count() * 4;
+    temporal_attn_kernel<<<blocks < cap ? blocks : cap, T_, (size_t)heads * C * D * sizeof(float), stream>>>(
         x, N, T, C, heads, D, u, l0, Mv, c0, out, ldo, out_amax);
     MORIG_LAUNCH_CHECK("temporal_attn_kernel");
     return 0;

@@ -172,10 +172,33 @@ class Graph:
     tgt: torch.Tensor
     n: int
     e_max: int
+    ready: Optional[torch.cuda.Event] = None     # set while the CSR is still being built on a side stream
+    scratch: Optional[torch.Tensor] = None       # keeps the builder's workspace alive until then
+
+    def join(self) -> None:
+        """make the current stream wait for a CSR that is being built on a side stream (no-op afterwards)"""
+        if self.ready is not None:
+            torch.cuda.current_stream(self.rowptr.device).wait_event(self.ready)
+            self.ready = None
+            self.scratch = None
 
 
-def graph_prep(edge_index: torch.Tensor, n: int) -> Graph:
-    """`morig_graph_prep` on a [2, E] int64 CUDA tensor."""
+_side: Dict[str, list] = {}                      # per device: [streams, next index]
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    ent = _side.get(str(device))
+    if ent is None:
+        ent = _side[str(device)] = [[torch.cuda.Stream(device), torch.cuda.Stream(device)], 0]
+    ent[1] ^= 1
+    return ent[0][ent[1]]
+
+
+def graph_prep(edge_index: torch.Tensor, n: int, overlap: bool = False) -> Graph:
+    """`morig_graph_prep` on a [2, E] int64 CUDA tensor.  With `overlap` the five small kernels run on a side stream
+    (the two edge sets of a forward and the first vertex layers are independent); `Graph.join()` -- called by the
+    first EdgeConv that needs the CSR -- orders the consumer after them.  Inside a CUDA-graph capture the fork and
+    the join become graph edges."""
     lib = _lib.load()
     if edge_index.dim() != 2 or edge_index.shape[0] != 2:
         raise ValueError(f"edge_index must be [2, E], got {tuple(edge_index.shape)}")
@@ -187,11 +210,22 @@ def graph_prep(edge_index: torch.Tensor, n: int) -> Graph:
     tgt = torch.empty(e + n, dtype=torch.int32, device=dev)
     ws_bytes = lib.morig_graph_prep_workspace(e, n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    g = Graph(rowptr=rowptr, col=col, tgt=tgt, n=n, e_max=e + n)
+    if overlap and not hooks_active():
+        cur = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        side.wait_stream(cur)                    # the edge list (possibly a copy queued on `cur`) is ready
+        _lib.check(lib.morig_graph_prep(ei.data_ptr(), e, n, rowptr.data_ptr(), col.data_ptr(), tgt.data_ptr(),
+                                        ws.data_ptr(), ws_bytes, side.cuda_stream), "morig_graph_prep")
+        g.ready = torch.cuda.Event()
+        g.ready.record(side)
+        g.scratch = ws
+        return g
     tok = _begin(f"graph_prep E={e} N={n}", 5, 0.0, 16.0 * e + 8.0 * (e + n)) if (_counter is not None or _timer is not None) else None
     _lib.check(lib.morig_graph_prep(ei.data_ptr(), e, n, rowptr.data_ptr(), col.data_ptr(), tgt.data_ptr(),
                                     ws.data_ptr(), ws_bytes, _lib.stream_ptr()), "morig_graph_prep")
     _end(tok)
-    return Graph(rowptr=rowptr, col=col, tgt=tgt, n=n, e_max=e + n)
+    return g
 
 
 class GraphCache:
@@ -206,7 +240,7 @@ class GraphCache:
         for ent in self._entries:
             if ent[0] is edge_index and ent[1] == edge_index._version and ent[2] == n:
                 return ent[3]
-        g = graph_prep(edge_index, n)
+        g = graph_prep(edge_index, n, overlap=True)
         self._entries.insert(0, (edge_index, edge_index._version, n, g))
         del self._entries[self._slots:]
         return g
@@ -381,6 +415,7 @@ def dense(layer: DenseLayer, A: torch.Tensor, a_off: int, lda: int, M: int, *, K
 def edgeconv(br: EdgeBranch, pq: torch.Tensor, ldpq: int, p_off: int, q_off: int, g: Graph, n_frames: int,
              out: torch.Tensor, ldo: int, out_off: int, out_repeat: int = 1) -> None:
     lib = _lib.load()
+    g.join()
     d = _lib.EdgeDesc()
     d.PQ, d.ldpq, d.p_off, d.q_off = pq.data_ptr(), ldpq, p_off, q_off
     d.rowptr, d.col, d.tgt = g.rowptr.data_ptr(), g.col.data_ptr(), g.tgt.data_ptr()

@@ -20,7 +20,7 @@ def _view(t: torch.Tensor, off: int, rows: int, cols: int, ld: int) -> torch.Ten
     return torch.as_strided(flat, (rows, cols), (ld, 1), storage_offset=flat.storage_offset() + off)
 
 
-def graph_prep(edge_index, n):
+def graph_prep(edge_index, n, overlap=False):
     rowptr, col = graph_port.csr_by_target(edge_index.numpy(), n)
     tgt = np.repeat(np.arange(n, dtype=np.int32), np.diff(rowptr))
     e = edge_index.shape[1]
