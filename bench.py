@@ -150,8 +150,18 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    json_fd = 1
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("MORIG_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
+        # stdout must carry the ONE JSON line only: NCCL prints its version banner (and, with NCCL_DEBUG=INFO in the
+        # environment, its whole log) to fd 1 from C, so fd 1 is pointed at stderr for the run and the line goes to
+        # the saved descriptor
+        if "MORIG_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["MORIG_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -306,7 +316,8 @@ def run_ours(args):
                 "kernels": kstats}
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
