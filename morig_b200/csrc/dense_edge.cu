@@ -1,5 +1,5 @@
 // Host launchers for the tile engines (vertex dense layers, fused EdgeConv branch) and the narrow-channel EdgeConv
-// branch kernel (H <= 32: warp per 32 CSR slots, mma.sync 3xTF32, in-register segmented max).
+// branch kernel (H <= 32: warp per 32 CSR slots, mma.sync split-fp16, in-register segmented max).
 #include <stdlib.h>
 #include "gemm_tc.cuh"
 
@@ -12,15 +12,17 @@ namespace morig {
 //   * gathers relu(P[tgt] + Q[col]) straight into mma.sync A fragments (no shared-memory staging): lane (g, t) owns
 //     the four edges 4g..4g+3 of the tile and, of each row, the H/4 contiguous channels [t H/4, (t+1) H/4) -- the
 //     contraction index is permuted identically on the weight side, so every global load is a full 16-byte chunk;
-//   * multiplies by the H x H second Linear with 3 x TF32 error compensation (hi/lo splits of both operands,
-//     A_lo B_hi + A_hi B_lo + A_hi B_hi, fp32 accumulate); the split weight fragments live in registers for the
-//     whole kernel;
+//   * multiplies by the H x H second Linear with split-fp16 error compensation, the same arithmetic as the tcgen05
+//     engine's fp16 kind (hi/lo fp16 splits of both operands scaled by powers of two -- the activation scale from
+//     the tracked max |PQ|, the weight scale from max |W1| -- A_lo B_hi + A_hi B_lo + A_hi B_hi, fp32 accumulate;
+//     mma.sync m16n8k16: the legacy TF32 shape runs at a fraction of this rate on sm_100); the split weight fragments
+//     live in registers for the whole kernel;
 //   * applies bias -> ReLU -> BatchNorm affine and reduces with a segmented max scan over the tile: four edges in
 //     registers, then three shuffle steps across the eight lane groups; segment tails store (segments cut by the
 //     tile boundary merge with the ordered-int atomic max, so the result is exact and order independent).
-__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+__device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                 uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
                  "{%0, %1, %2, %3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
@@ -30,7 +32,7 @@ constexpr int EDGE_MMA_THREADS = 128;
 
 template <int H>
 __global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const morig_edge_desc d) {
-    constexpr int KT = H / 8, NT = H / 8;           // k-tiles and n-tiles of the m16n8k8 shape
+    constexpr int KT = H / 16, NT = H / 8;          // k-tiles and n-tiles of the m16n8k16 shape
     constexpr int KPL = H / 4;                      // contraction values of one row held by one lane
     constexpr int CPL = 2 * NT;                     // output columns held by one lane: 8 nt + 2 t + {0, 1}
     constexpr uint32_t FULL = 0xffffffffu;
@@ -41,18 +43,41 @@ __global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const morig_
         reinterpret_cast<float *>(s_scale)[i] = d.scale[i];
         reinterpret_cast<float *>(s_shift)[i] = d.shift[i];
     }
-    // weight fragments: slot (kt, t) of the instruction reads contraction index KPL t + 2 kt, slot (kt, t + 4) the next
+    // weight fragments: the four contraction slots {2t, 2t+1, 2t+8, 2t+9} of k-tile kt read the physical indices
+    // KPL t + 4 kt + {0, 1, 2, 3} (the activation fragments use the same permutation)
+    float wv[KT][NT][4];
+    float wmax = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+                wv[kt][nt][s4] = d.W1[(size_t)(KPL * t + 4 * kt + s4) * d.ldw + 8 * nt + g];
+                wmax = fmaxf(wmax, fabsf(wv[kt][nt][s4]));
+            }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(FULL, wmax, off));   // the warp holds all of W1
+    // power-of-two operand scales: max|W1| * ws in [2^14, 2^15); relu(P + Q) * as < 2^15
+    auto pow2 = [](int sh) { sh = sh < -100 ? -100 : (sh > 100 ? 100 : sh); return __uint_as_float((uint32_t)(sh + 127) << 23); };
+    auto expo = [](float x) { int e = (int)((__float_as_uint(x) >> 23) & 0xffu); return (e == 0 || e == 255) ? 127 : e; };
+    const int w_sh = 14 - (expo(wmax) - 127);
+    const int a_sh = 14 - (expo(d.pq_amax ? *d.pq_amax : 1.f) - 126);
+    const float w_scale = pow2(w_sh), a_scale = pow2(a_sh);
+    const float inv = pow2(-w_sh) * pow2(-a_sh);
     uint32_t bh[KT][NT][2], bl[KT][NT][2];
 #pragma unroll
     for (int kt = 0; kt < KT; ++kt)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const float w = d.W1[(size_t)(KPL * t + 2 * kt + s) * d.ldw + 8 * nt + g];
-                const float hi = tc::tf32_hi(w);
-                bh[kt][nt][s] = __float_as_uint(hi);
-                bl[kt][nt][s] = __float_as_uint(w - hi);
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const float w0 = wv[kt][nt][2 * s2] * w_scale, w1 = wv[kt][nt][2 * s2 + 1] * w_scale;
+                const __half2 hi = __floats2half2_rn(w0, w1);
+                const float2 hf = __half22float2(hi);
+                const __half2 lo = __floats2half2_rn(w0 - hf.x, w1 - hf.y);
+                bh[kt][nt][s2] = *reinterpret_cast<const uint32_t *>(&hi);
+                bl[kt][nt][s2] = *reinterpret_cast<const uint32_t *>(&lo);
             }
     __syncthreads();
 
@@ -66,12 +91,15 @@ __global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const morig_
     const float *Qb = d.PQ + d.q_off + KPL * t;
     float am = 0.f;
 
-    for (long long id = (long long)blockIdx.x * (EDGE_MMA_THREADS / 32) + (threadIdx.x >> 5); id < total; id += warps_total) {
-        const int f = (int)(id / n_tiles);
-        const int s0 = (int)(id - (long long)f * n_tiles) * 32;
-        const size_t fb = (size_t)f * N;
-        // ---- indices of this lane's four edges ----
-        int key[4], cj[4];
+    // indices of a tile: this lane's four edges (target = segment key, source), plus the keys of the slots just before
+    // and after the tile (lanes 0 / 31) that tell whether its first / last segment is cut by the tile boundary.
+    // They are fetched one tile ahead, so the gathers of a tile never wait for its index loads.
+    auto load_idx = [&](long long id, int (&key)[4], int (&cj)[4], int &ext) {
+        ext = -1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { key[j] = -1; cj[j] = 0; }
+        if (id >= total) return;
+        const int s0 = (int)(id % n_tiles) * 32;
         const int e0 = s0 + 4 * g;
         if (e0 + 3 < Ep) {
             const int4 k4 = *reinterpret_cast<const int4 *>(d.tgt + e0);
@@ -81,11 +109,23 @@ __global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const morig_
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const bool ok = e0 + j < Ep;
-                key[j] = ok ? d.tgt[e0 + j] : -1;
-                cj[j] = ok ? d.col[e0 + j] : 0;
+                if (e0 + j < Ep) { key[j] = d.tgt[e0 + j]; cj[j] = d.col[e0 + j]; }
             }
         }
+        if (lane == 0) ext = s0 > 0 ? d.tgt[s0 - 1] : -2;
+        if (lane == 31 && s0 + 32 < Ep) ext = d.tgt[s0 + 32];
+    };
+    long long id = (long long)blockIdx.x * (EDGE_MMA_THREADS / 32) + (threadIdx.x >> 5);
+    int nkey[4], ncj[4], next_;
+    load_idx(id, nkey, ncj, next_);
+    for (; id < total; id += warps_total) {
+        const int f = (int)(id / n_tiles);
+        const size_t fb = (size_t)f * N;
+        int key[4], cj[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { key[j] = nkey[j]; cj[j] = ncj[j]; }
+        const int ext = next_;
+        load_idx(id + warps_total, nkey, ncj, next_);
         // ---- gather: x[j] = relu(P[tgt] + Q[col]), this lane's KPL channels ----
         float x[4][KPL];
 #pragma unroll
@@ -96,10 +136,10 @@ __global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const morig_
             for (int v = 0; v < KPL / 4; ++v) {
                 const float4 a = *reinterpret_cast<const float4 *>(pp + 4 * v);
                 const float4 b = *reinterpret_cast<const float4 *>(qq + 4 * v);
-                x[j][4 * v + 0] = fmaxf(a.x + b.x, 0.f);
-                x[j][4 * v + 1] = fmaxf(a.y + b.y, 0.f);
-                x[j][4 * v + 2] = fmaxf(a.z + b.z, 0.f);
-                x[j][4 * v + 3] = fmaxf(a.w + b.w, 0.f);
+                x[j][4 * v + 0] = fmaxf(a.x + b.x, 0.f) * a_scale;
+                x[j][4 * v + 1] = fmaxf(a.y + b.y, 0.f) * a_scale;
+                x[j][4 * v + 2] = fmaxf(a.z + b.z, 0.f) * a_scale;
+                x[j][4 * v + 3] = fmaxf(a.w + b.w, 0.f) * a_scale;
             }
         }
         // ---- segment structure of the tile (identical in the four lanes of a group) ----
@@ -116,8 +156,8 @@ __global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const morig_
         const int first_key = __shfl_sync(FULL, key[0], 0);
         const int last_key = __shfl_sync(FULL, key[3], 31);
         // segments cut by the tile boundary merge through atomics
-        const bool cut_first = first_key >= 0 && d.rowptr[first_key] < s0;
-        const bool cut_last = last_key >= 0 && d.rowptr[last_key + 1] > s0 + 32;
+        const bool cut_first = first_key >= 0 && first_key == __shfl_sync(FULL, ext, 0);
+        const bool cut_last = last_key >= 0 && last_key == __shfl_sync(FULL, ext, 31);
 
         // ---- second Linear on the tensor cores: two m16 tiles (edges {0,1} and {2,3} of every lane) ----
         float z[4][CPL];
@@ -130,27 +170,30 @@ __global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const morig_
             for (int kt = 0; kt < KT; ++kt) {
                 uint32_t ah[4], al[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {                 // a0: row g, a1: row g + 8, a2 / a3: the t + 4 slots
-                    const float v = x[2 * m + (i & 1)][2 * kt + (i >> 1)];
-                    const float hi = tc::tf32_hi(v);
-                    ah[i] = __float_as_uint(hi);
-                    al[i] = __float_as_uint(v - hi);
+                for (int i = 0; i < 4; ++i) {                 // a0: row g, a1: row g + 8, a2 / a3: the slots 2t+8, 2t+9
+                    const float v0 = x[2 * m + (i & 1)][4 * kt + 2 * (i >> 1)];
+                    const float v1 = x[2 * m + (i & 1)][4 * kt + 2 * (i >> 1) + 1];
+                    // hi = value with the 13 low mantissa bits cleared (11 significant bits: exact in fp16 inside the
+                    // range the scale guarantees), lo = value - hi (exact in fp32)
+                    const float h0 = tc::tf32_hi(v0), h1 = tc::tf32_hi(v1);
+                    ah[i] = tc::pack_h2(h0, h1);
+                    al[i] = tc::pack_h2(v0 - h0, v1 - h1);
                 }
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
-                    mma_tf32_16x8x8(acc[nt], al[0], al[1], al[2], al[3], bh[kt][nt][0], bh[kt][nt][1]);
-                    mma_tf32_16x8x8(acc[nt], ah[0], ah[1], ah[2], ah[3], bl[kt][nt][0], bl[kt][nt][1]);
-                    mma_tf32_16x8x8(acc[nt], ah[0], ah[1], ah[2], ah[3], bh[kt][nt][0], bh[kt][nt][1]);
+                    mma_f16_16x8x16(acc[nt], al[0], al[1], al[2], al[3], bh[kt][nt][0], bh[kt][nt][1]);
+                    mma_f16_16x8x16(acc[nt], ah[0], ah[1], ah[2], ah[3], bl[kt][nt][0], bl[kt][nt][1]);
+                    mma_f16_16x8x16(acc[nt], ah[0], ah[1], ah[2], ah[3], bh[kt][nt][0], bh[kt][nt][1]);
                 }
             }
             // bias -> ReLU -> BatchNorm affine (before any max: the scale may be negative)
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 const float2 b = s_bias[4 * nt + t], sc = s_scale[4 * nt + t], sh = s_shift[4 * nt + t];
-                z[2 * m][2 * nt] = fmaf(fmaxf(acc[nt][0] + b.x, 0.f), sc.x, sh.x);
-                z[2 * m][2 * nt + 1] = fmaf(fmaxf(acc[nt][1] + b.y, 0.f), sc.y, sh.y);
-                z[2 * m + 1][2 * nt] = fmaf(fmaxf(acc[nt][2] + b.x, 0.f), sc.x, sh.x);
-                z[2 * m + 1][2 * nt + 1] = fmaf(fmaxf(acc[nt][3] + b.y, 0.f), sc.y, sh.y);
+                z[2 * m][2 * nt] = fmaf(fmaxf(fmaf(acc[nt][0], inv, b.x), 0.f), sc.x, sh.x);
+                z[2 * m][2 * nt + 1] = fmaf(fmaxf(fmaf(acc[nt][1], inv, b.y), 0.f), sc.y, sh.y);
+                z[2 * m + 1][2 * nt] = fmaf(fmaxf(fmaf(acc[nt][2], inv, b.x), 0.f), sc.x, sh.x);
+                z[2 * m + 1][2 * nt + 1] = fmaf(fmaxf(fmaf(acc[nt][3], inv, b.y), 0.f), sc.y, sh.y);
             }
         }
 #pragma unroll
@@ -475,6 +518,7 @@ extern "C" MORIG_API int morig_edgeconv_fwd(const morig_edge_desc *d, void *stre
         MORIG_CHECK_ARG(d->ldpq % 4 == 0 && d->p_off % 4 == 0 && d->q_off % 4 == 0 && aligned16(d->PQ),
                         "edgeconv_fwd: PQ must be 16B aligned (ldpq, p_off, q_off multiples of 4)");
         MORIG_CHECK_ARG(aligned16(d->col) && aligned16(d->tgt), "edgeconv_fwd: col / tgt must be 16B aligned");
+        MORIG_CHECK_ARG(d->pq_amax, "edgeconv_fwd: the narrow (H <= 32) kernel needs pq_amax");
         return H == 16 ? launch_edge_mma<16>(*d, stream) : launch_edge_mma<32>(*d, stream);
     }
     MORIG_CHECK_ARG(H == 64 || H == 128 || H == 256, "edgeconv_fwd: H=%d unsupported (16,32,64,128,256)", H);

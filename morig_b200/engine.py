@@ -425,8 +425,8 @@ def edgeconv(br: EdgeBranch, pq: torch.Tensor, ldpq: int, p_off: int, q_off: int
     d.out, d.ldo, d.out_off = out.data_ptr(), ldo, out_off
     d.H = br.H
     d.W1tc, d.tc_kind, d.tc_w_inv = _lib.ptr(br.W1tc), br.tc_kind, br.tc_w_inv
-    if br.W1tc is not None and br.tc_kind == KIND_F16:
-        d.pq_amax = _amax_in(pq, 0, ldpq, g.n * n_frames, ldpq)
+    if (br.W1tc is not None and br.tc_kind == KIND_F16) or br.H <= 32:       # split-fp16 kernels need the operand range
+        d.pq_amax = _amax_in(pq, 0, ldpq, g.n * (n_frames if out_repeat == 1 else 1), ldpq)
     d.out_amax = _amax_out(out)
     tok = None
     if _counter is not None or _timer is not None:
