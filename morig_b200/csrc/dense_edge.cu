@@ -297,15 +297,27 @@ __global__ void __launch_bounds__(SKINNY_THREADS) dense_skinny_kernel(const Gemm
     float acc[SKINNY_MAX_M];
 #pragma unroll
     for (int m = 0; m < SKINNY_MAX_M; ++m) acc[m] = 0.f;
-    for (int k4 = 4 * kg; k4 < p.K; k4 += 4 * SKINNY_KG) {      // K % 4 == 0 (checked by the launcher)
-        float w[4];
+    // K % 4 == 0 (checked by the launcher).  The weight values of up to 1024 k-rows are requested before the first
+    // one is used: the kernel's cost is DRAM latency, so it wants all of its loads in flight at once.
+    constexpr int IT = 8;
+    for (int kb = 0; kb < p.K; kb += 4 * SKINNY_KG * IT) {
+        float w[IT][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = n_ok ? p.W[(size_t)(k4 + j) * p.ldw + n] : 0.f;
+        for (int it = 0; it < IT; ++it) {
+            const int k4 = kb + 4 * (kg + SKINNY_KG * it);
 #pragma unroll
-        for (int m = 0; m < SKINNY_MAX_M; ++m) {
-            if (m < p.M) {
-                const float4 a = *reinterpret_cast<const float4 *>(p.A + (size_t)m * p.lda + k4);
-                acc[m] = fmaf(a.x, w[0], fmaf(a.y, w[1], fmaf(a.z, w[2], fmaf(a.w, w[3], acc[m]))));
+            for (int j = 0; j < 4; ++j) w[it][j] = (n_ok && k4 < p.K) ? p.W[(size_t)(k4 + j) * p.ldw + n] : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const int k4 = kb + 4 * (kg + SKINNY_KG * it);
+            if (k4 >= p.K) break;
+#pragma unroll
+            for (int m = 0; m < SKINNY_MAX_M; ++m) {
+                if (m < p.M) {
+                    const float4 a = *reinterpret_cast<const float4 *>(p.A + (size_t)m * p.lda + k4);
+                    acc[m] = fmaf(a.x, w[it][0], fmaf(a.y, w[it][1], fmaf(a.z, w[it][2], fmaf(a.w, w[it][3], acc[m]))));
+                }
             }
         }
     }

@@ -7,7 +7,7 @@ MORIG_BENCH_PROFILE=graph timeout 900 ncu --metrics gpu__time_duration.sum --clo
     --csv --log-file gpurun_out/launches_graph.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launch.log 2>&1
 tail -1 gpurun_out/ncu_launch.log | cut -c1-200
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
-    -k regex:"gemm_kernel|edge_mma" -o /tmp/prof_kernels python scripts/prof_kernels.py "$@" > gpurun_out/ncu_full.log 2>&1
+    -k regex:"gemm_kernel|edge_mma" -o /tmp/prof_kernels python scripts/prof_kernels.py e256 e128 d840 e32 e16 > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log | cut -c1-200
 ncu -i /tmp/prof_kernels.ncu-rep --page raw --csv > gpurun_out/prof_kernels_raw.csv 2>/dev/null
 ncu -i /tmp/prof_kernels.ncu-rep --page details > gpurun_out/prof_kernels_details.txt 2>/dev/null
