@@ -141,11 +141,16 @@ typedef struct morig_edge_desc {
     int32_t        H;
     const void    *W1tc;                      /* optional tcgen05 image of W1 (n-tile = H <= 256) */
     int32_t        tc_kind;  float   tc_w_inv;/* as in morig_dense_desc                           */
-    const float   *pq_amax;                   /* device scalar >= max|PQ|, required for tc_kind 1 */
+    const float   *pq_amax;                   /* device scalar >= max|PQ|: required for tc_kind 1 and for H <= 32 */
     float         *out_amax;                  /* optional, raised to max |edge value| before the max */
 } morig_edge_desc;
 
 MORIG_API int morig_edgeconv_fwd(const morig_edge_desc *d, void *stream);
+
+/* `count` (1..4) narrow branches (H in {16, 32}, the same for all) on the same graph and key-frame count in ONE launch:
+ * the pos branches of the three GCUs of a GCNRig (models/rignet.py:59-61 -> basic_modules.py:215-216) are independent
+ * of the GCU chain -- they only read pos -- and each is too small to fill the machine. */
+MORIG_API int morig_edgeconv_fwd_batch(const morig_edge_desc *d, int32_t count, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Per-vertex cls-token attention over key-frames.  Replaces TemporalAttn.forward up to and

@@ -161,7 +161,8 @@ class GCUMotion(FusedModule):
         out = torch.empty(n, gp.out, device=dev, dtype=torch.float32)
         with engine.forward_scope(self._ws, dev):
             engine.dense(pq_pos, pos, 0, pos.shape[1], n, C=pqpos, ldc=pq_pos.N)
-            engine.run_gcu(self._ws, "gcu", gp, x, 0, x.shape[1], x.shape[1], pqpos, gt, gg, n, 1, out, 0, gp.out)
+            engine.run_pos_branches(self._ws, ["gcu"], [gp], pqpos, gt, gg, n, 1)
+            engine.run_gcu(self._ws, "gcu", gp, x, 0, x.shape[1], x.shape[1], gt, gg, n, 1, out, 0, gp.out)
         return out
 
 

@@ -5,6 +5,8 @@
 
 namespace morig {
 
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 // ---- narrow EdgeConv branch (H = 16 / 32) --------------------------------------------------------
 // Warp-level tensor-core kernel for the layers that are too small for the tcgen05 tile engine (gcu_1's x branch and
 // every pos branch of the joint / mask networks: 2 E H^2 FLOPs on 16- or 32-wide rows, bound by the gathers and the
@@ -29,9 +31,14 @@ __device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], uint32_t a0, uint
 }
 
 constexpr int EDGE_MMA_THREADS = 128;
+constexpr int EDGE_BATCH_MAX = 4;
+// several branches of the same width on the same graph (e.g. the pos branches of the three GCUs of a GCNRig, which
+// all read the one pqpos buffer) share a launch: blockIdx.y selects the branch
+struct EdgeBatch { morig_edge_desc d[EDGE_BATCH_MAX]; };
 
 template <int H>
-__global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const morig_edge_desc d) {
+__global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const __grid_constant__ EdgeBatch batch) {
+    const morig_edge_desc &d = batch.d[blockIdx.y];
     constexpr int KT = H / 16, NT = H / 8;          // k-tiles and n-tiles of the m16n8k16 shape
     constexpr int KPL = H / 4;                      // contraction values of one row held by one lane
     constexpr int CPL = 2 * NT;                     // output columns held by one lane: 8 nt + 2 t + {0, 1}
@@ -265,17 +272,33 @@ __global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const morig_
 }
 
 template <int H>
-static int launch_edge_mma(const morig_edge_desc &d, cudaStream_t stream) {
+static int launch_edge_mma(const morig_edge_desc *descs, int count, cudaStream_t stream) {
     static thread_local int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         MORIG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, edge_mma_kernel<H>, EDGE_MMA_THREADS, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
+    EdgeBatch b;
+    for (int i = 0; i < EDGE_BATCH_MAX; ++i) b.d[i] = descs[i < count ? i : 0];
+    const morig_edge_desc &d = descs[0];
     const long long tiles = (long long)ceil_div(d.E_max, 32) * d.n_frames;          // upper bound (E' <= E_max)
     const long long want = ceil_div64(tiles, EDGE_MMA_THREADS / 32);
-    const long long cap = (long long)sm_count() * blocks_per_sm;                    // persistent: warps stride over tiles
-    edge_mma_kernel<H><<<(unsigned)(want < cap ? want : cap), EDGE_MMA_THREADS, 0, stream>>>(d);
+    long long cap = (long long)sm_count() * blocks_per_sm / count;                  // persistent: warps stride over tiles
+    if (cap < 1) cap = 1;
+    edge_mma_kernel<H><<<dim3((unsigned)(want < cap ? want : cap), (unsigned)count), EDGE_MMA_THREADS, 0, stream>>>(b);
     MORIG_LAUNCH_CHECK("edge_mma_kernel");
+    return 0;
+}
+
+static int check_narrow(const morig_edge_desc *d) {
+    MORIG_CHECK_ARG(d && d->PQ && d->rowptr && d->col && d->tgt && d->W1 && d->b1 && d->scale && d->shift && d->out,
+                    "edgeconv_fwd: null operand");
+    MORIG_CHECK_ARG(d->N > 0 && d->E_max >= d->N && d->n_frames >= 1 && d->out_repeat >= 1, "edgeconv_fwd: bad sizes");
+    MORIG_CHECK_ARG(d->out_repeat == 1 || d->n_frames == 1, "edgeconv_fwd: out_repeat needs n_frames == 1");
+    MORIG_CHECK_ARG(d->ldpq % 4 == 0 && d->p_off % 4 == 0 && d->q_off % 4 == 0 && aligned16(d->PQ),
+                    "edgeconv_fwd: PQ must be 16B aligned (ldpq, p_off, q_off multiples of 4)");
+    MORIG_CHECK_ARG(aligned16(d->col) && aligned16(d->tgt), "edgeconv_fwd: col / tgt must be 16B aligned");
+    MORIG_CHECK_ARG(d->pq_amax, "edgeconv_fwd: the narrow (H <= 32) kernel needs pq_amax");
     return 0;
 }
 
@@ -297,27 +320,15 @@ __global__ void __launch_bounds__(SKINNY_THREADS) dense_skinny_kernel(const Gemm
     float acc[SKINNY_MAX_M];
 #pragma unroll
     for (int m = 0; m < SKINNY_MAX_M; ++m) acc[m] = 0.f;
-    // K % 4 == 0 (checked by the launcher).  The weight values of up to 1024 k-rows are requested before the first
-    // one is used: the kernel's cost is DRAM latency, so it wants all of its loads in flight at once.
-    constexpr int IT = 8;
-    for (int kb = 0; kb < p.K; kb += 4 * SKINNY_KG * IT) {
-        float w[IT][4];
+    for (int k4 = 4 * kg; k4 < p.K; k4 += 4 * SKINNY_KG) {      // K % 4 == 0 (checked by the launcher)
+        float w[4];
 #pragma unroll
-        for (int it = 0; it < IT; ++it) {
-            const int k4 = kb + 4 * (kg + SKINNY_KG * it);
+        for (int j = 0; j < 4; ++j) w[j] = n_ok ? p.W[(size_t)(k4 + j) * p.ldw + n] : 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) w[it][j] = (n_ok && k4 < p.K) ? p.W[(size_t)(k4 + j) * p.ldw + n] : 0.f;
-        }
-#pragma unroll
-        for (int it = 0; it < IT; ++it) {
-            const int k4 = kb + 4 * (kg + SKINNY_KG * it);
-            if (k4 >= p.K) break;
-#pragma unroll
-            for (int m = 0; m < SKINNY_MAX_M; ++m) {
-                if (m < p.M) {
-                    const float4 a = *reinterpret_cast<const float4 *>(p.A + (size_t)m * p.lda + k4);
-                    acc[m] = fmaf(a.x, w[it][0], fmaf(a.y, w[it][1], fmaf(a.z, w[it][2], fmaf(a.w, w[it][3], acc[m]))));
-                }
+        for (int m = 0; m < SKINNY_MAX_M; ++m) {
+            if (m < p.M) {
+                const float4 a = *reinterpret_cast<const float4 *>(p.A + (size_t)m * p.lda + k4);
+                acc[m] = fmaf(a.x, w[0], fmaf(a.y, w[1], fmaf(a.z, w[2], fmaf(a.w, w[3], acc[m]))));
             }
         }
     }
@@ -357,7 +368,6 @@ static int launch_gemm(const GemmP &p, dim3 grid, cudaStream_t stream, const cha
     return 0;
 }
 
-static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static long long *g_trace = nullptr;      // debug timeline buffer (device), set by morig_debug_set_trace
 
@@ -527,11 +537,8 @@ extern "C" MORIG_API int morig_edgeconv_fwd(const morig_edge_desc *d, void *stre
     MORIG_CHECK_ARG(d->out_repeat == 1 || d->n_frames == 1, "edgeconv_fwd: out_repeat needs n_frames == 1");
     const int H = d->H;
     if (H == 16 || H == 32) {
-        MORIG_CHECK_ARG(d->ldpq % 4 == 0 && d->p_off % 4 == 0 && d->q_off % 4 == 0 && aligned16(d->PQ),
-                        "edgeconv_fwd: PQ must be 16B aligned (ldpq, p_off, q_off multiples of 4)");
-        MORIG_CHECK_ARG(aligned16(d->col) && aligned16(d->tgt), "edgeconv_fwd: col / tgt must be 16B aligned");
-        MORIG_CHECK_ARG(d->pq_amax, "edgeconv_fwd: the narrow (H <= 32) kernel needs pq_amax");
-        return H == 16 ? launch_edge_mma<16>(*d, stream) : launch_edge_mma<32>(*d, stream);
+        if (int rc = check_narrow(d)) return rc;
+        return H == 16 ? launch_edge_mma<16>(d, 1, stream) : launch_edge_mma<32>(d, 1, stream);
     }
     MORIG_CHECK_ARG(H == 64 || H == 128 || H == 256, "edgeconv_fwd: H=%d unsupported (16,32,64,128,256)", H);
     MORIG_CHECK_ARG(d->out_repeat == 1, "edgeconv_fwd: out_repeat only for H<=32");
@@ -568,4 +575,19 @@ extern "C" MORIG_API int morig_edgeconv_fwd(const morig_edge_desc *d, void *stre
     }
     dim3 grid(ceil_div(d->E_max, 128), H / 128, d->n_frames);
     return launch_gemm<128, 128, AMODE_GATHER, EPI_SEGMAX>(p, grid, stream, "edge<128,128>");
+}
+
+extern "C" MORIG_API int morig_edgeconv_fwd_batch(const morig_edge_desc *d, int32_t count, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MORIG_CHECK_ARG(d && count >= 1 && count <= EDGE_BATCH_MAX, "edgeconv_fwd_batch: count=%d unsupported (1..%d)", count,
+                    EDGE_BATCH_MAX);
+    const int H = d[0].H;
+    MORIG_CHECK_ARG(H == 16 || H == 32, "edgeconv_fwd_batch: H=%d unsupported (16, 32)", H);
+    for (int i = 0; i < count; ++i) {
+        if (int rc = check_narrow(d + i)) return rc;
+        MORIG_CHECK_ARG(d[i].H == H && d[i].rowptr == d[0].rowptr && d[i].col == d[0].col && d[i].tgt == d[0].tgt &&
+                        d[i].N == d[0].N && d[i].E_max == d[0].E_max && d[i].n_frames == d[0].n_frames,
+                        "edgeconv_fwd_batch: branch %d differs in width, graph or key-frame count", i);
+    }
+    return H == 16 ? launch_edge_mma<16>(d, count, stream) : launch_edge_mma<32>(d, count, stream);
 }

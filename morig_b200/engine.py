@@ -412,11 +412,8 @@ def dense(layer: DenseLayer, A: torch.Tensor, a_off: int, lda: int, M: int, *, K
     _end(tok)
 
 
-def edgeconv(br: EdgeBranch, pq: torch.Tensor, ldpq: int, p_off: int, q_off: int, g: Graph, n_frames: int,
-             out: torch.Tensor, ldo: int, out_off: int, out_repeat: int = 1) -> None:
-    lib = _lib.load()
-    g.join()
-    d = _lib.EdgeDesc()
+def _edge_desc(d, br: EdgeBranch, pq: torch.Tensor, ldpq: int, p_off: int, q_off: int, g: Graph, n_frames: int,
+               out: torch.Tensor, ldo: int, out_off: int, out_repeat: int) -> None:
     d.PQ, d.ldpq, d.p_off, d.q_off = pq.data_ptr(), ldpq, p_off, q_off
     d.rowptr, d.col, d.tgt = g.rowptr.data_ptr(), g.col.data_ptr(), g.tgt.data_ptr()
     d.N, d.E_max, d.n_frames, d.out_repeat = g.n, g.e_max, n_frames, out_repeat
@@ -428,12 +425,38 @@ def edgeconv(br: EdgeBranch, pq: torch.Tensor, ldpq: int, p_off: int, q_off: int
     if (br.W1tc is not None and br.tc_kind == KIND_F16) or br.H <= 32:       # split-fp16 kernels need the operand range
         d.pq_amax = _amax_in(pq, 0, ldpq, g.n * (n_frames if out_repeat == 1 else 1), ldpq)
     d.out_amax = _amax_out(out)
+
+
+def _edge_label(br: EdgeBranch, g: Graph, n_frames: int, out_repeat: int, count: int = 1):
+    H, e = br.H, g.e_max
+    return (f"edgeconv H={H} E={e} N={g.n} frames={n_frames}" + (f" x{count}" if count > 1 else ""), 1,
+            count * 2.0 * e * H * H * n_frames,
+            count * (n_frames * 4.0 * g.n * 2 * H + 8.0 * e + 4.0 * g.n * H * n_frames * out_repeat + 4.0 * (H * H + 3 * H)))
+
+
+def edgeconv(br: EdgeBranch, pq: torch.Tensor, ldpq: int, p_off: int, q_off: int, g: Graph, n_frames: int,
+             out: torch.Tensor, ldo: int, out_off: int, out_repeat: int = 1) -> None:
+    lib = _lib.load()
+    g.join()
+    d = _lib.EdgeDesc()
+    _edge_desc(d, br, pq, ldpq, p_off, q_off, g, n_frames, out, ldo, out_off, out_repeat)
+    tok = _begin(*_edge_label(br, g, n_frames, out_repeat)) if (_counter is not None or _timer is not None) else None
+    _lib.check(lib.morig_edgeconv_fwd(ctypes.byref(d), _lib.stream_ptr()), "morig_edgeconv_fwd")
+    _end(tok)
+
+
+def edgeconv_batch(items, g: Graph, n_frames: int, out_repeat: int = 1) -> None:
+    """Up to four narrow (H <= 32, equal width) EdgeConv branches on the same graph in one launch.
+    items: (br, pq, ldpq, p_off, q_off, out, ldo, out_off) per branch."""
+    lib = _lib.load()
+    g.join()
+    descs = (_lib.EdgeDesc * len(items))()
+    for d, (br, pq, ldpq, p_off, q_off, out, ldo, out_off) in zip(descs, items):
+        _edge_desc(d, br, pq, ldpq, p_off, q_off, g, n_frames, out, ldo, out_off, out_repeat)
     tok = None
     if _counter is not None or _timer is not None:
-        H, e = br.H, g.e_max
-        tok = _begin(f"edgeconv H={H} E={e} N={g.n} frames={n_frames}", 1, 2.0 * e * H * H * n_frames,
-                     n_frames * 4.0 * g.n * 2 * H + 8.0 * e + 4.0 * g.n * H * n_frames * out_repeat + 4.0 * (H * H + 3 * H))
-    _lib.check(lib.morig_edgeconv_fwd(ctypes.byref(d), _lib.stream_ptr()), "morig_edgeconv_fwd")
+        tok = _begin(*_edge_label(items[0][0], g, n_frames, out_repeat, len(items)))
+    _lib.check(lib.morig_edgeconv_fwd_batch(descs, len(items), _lib.stream_ptr()), "morig_edgeconv_fwd_batch")
     _end(tok)
 
 
@@ -464,28 +487,53 @@ def row_normalize(x: torch.Tensor, ldx: int, rows: int, c: int, dst2: Optional[t
 
 # ---- layer sequences -------------------------------------------------------------------------------
 
+def _gcu_buffers(ws: Workspace, tag: str, gp: GCUPack, R: int, dev):
+    H, Dp = gp.H, gp.Dp
+    return ws.get(tag + ".pq", (R, 4 * H), dev), ws.get(tag + ".ec", (R, 2 * (H + Dp)), dev)
+
+
+def run_pos_branches(ws: Workspace, tags, gps, pqpos: torch.Tensor, gt: Graph, gg: Graph, n: int, n_frames: int) -> None:
+    """The pos branches of several GCUs (models/basic_modules.py:194, one per edge set and GCU) only read `pos`, so
+    they do not take part in the GCU chain: the EdgeConv outputs of all GCUs are initialised and, per edge set, the
+    pos branches of all GCUs run as ONE launch (narrow branches) before the chain starts."""
+    dev = pqpos.device
+    R = n * n_frames
+    ldpp = pqpos.shape[1]
+    ecs = []
+    for tag, gp in zip(tags, gps):
+        _, ec = _gcu_buffers(ws, tag, gp, R, dev)
+        fill(ec, NEG_INF)       # edge tiles merge the segments they cut with an (exact, ordered-int) atomic max
+        ecs.append(ec)
+    for s, g in enumerate((gt, gg)):
+        items = []
+        for gp, ec in zip(gps, ecs):
+            H, Dp = gp.H, gp.Dp
+            wec = 2 * (H + Dp)
+            bp = gp.pos_geo if s else gp.pos_tpl
+            pc = gp.pos_col + 2 * s * Dp
+            items.append((bp, pqpos, ldpp, pc, pc + Dp, ec, wec, s * (H + Dp) + H))
+        narrow = all(it[0].H == items[0][0].H and it[0].H <= 32 for it in items)
+        if narrow and 1 < len(items) <= 4:
+            edgeconv_batch(items, g, 1, out_repeat=n_frames)
+        else:
+            for bp, pq_, ld_, po, qo, ec, wec, off in items:
+                if bp.H >= 64:      # wide pos branch (skinning net): key-frame count is 1 there
+                    edgeconv(bp, pq_, ld_, po, qo, g, 1, ec, wec, off)
+                else:
+                    edgeconv(bp, pq_, ld_, po, qo, g, 1, ec, wec, off, out_repeat=n_frames)
+
+
 def run_gcu(ws: Workspace, tag: str, gp: GCUPack, x: torch.Tensor, x_off: int, ldx: int, k_x: int,
-            pqpos: torch.Tensor, gt: Graph, gg: Graph, n: int, n_frames: int,
-            out: torch.Tensor, out_off: int, ldo: int) -> None:
-    """One GCUMotion (models/basic_modules.py:205-219): both EdgeConvMotion branches on both edge sets,
-    then the vertex mlp, written to out[:, out_off : out_off + gp.out]."""
-    dev = x.device
+            gt: Graph, gg: Graph, n: int, n_frames: int, out: torch.Tensor, out_off: int, ldo: int) -> None:
+    """One GCUMotion (models/basic_modules.py:205-219) after `run_pos_branches`: the x branch of both
+    EdgeConvMotion layers, then the vertex mlp, written to out[:, out_off : out_off + gp.out]."""
     R = n * n_frames
     H, Dp = gp.H, gp.Dp
     wec = 2 * (H + Dp)
-    pq = ws.get(tag + ".pq", (R, 4 * H), dev)
-    ec = ws.get(tag + ".ec", (R, wec), dev)
+    pq, ec = _gcu_buffers(ws, tag, gp, R, x.device)
     dense(gp.pq_x, x, x_off, ldx, R, K=k_x, C=pq, ldc=4 * H)
-    fill(ec, NEG_INF)           # edge tiles merge the segments they cut with an (exact, ordered-int) atomic max
-    ldpp = pqpos.shape[1]
-    for s, (g, bx, bp) in enumerate(((gt, gp.x_tpl, gp.pos_tpl), (gg, gp.x_geo, gp.pos_geo))):
-        base = s * (H + Dp)
-        edgeconv(bx, pq, 4 * H, 2 * s * H, 2 * s * H + H, g, n_frames, ec, wec, base)
-        pc = gp.pos_col + 2 * s * Dp
-        if Dp >= 64:            # wide pos branch (skinning net): key-frame count is 1 there
-            edgeconv(bp, pqpos, ldpp, pc, pc + Dp, g, 1, ec, wec, base + H)
-        else:
-            edgeconv(bp, pqpos, ldpp, pc, pc + Dp, g, 1, ec, wec, base + H, out_repeat=n_frames)
+    for s, (g, bx) in enumerate(((gt, gp.x_tpl), (gg, gp.x_geo))):
+        edgeconv(bx, pq, 4 * H, 2 * s * H, 2 * s * H + H, g, n_frames, ec, wec, s * (H + Dp))
     dense(gp.mlp, ec, 0, wec, R, C=out, c_off=out_off, ldc=ldo)
 
 
@@ -507,9 +555,10 @@ def run_gcn_rig(ws: Workspace, tag: str, pk: GCNRigPack, pos: torch.Tensor, feat
     dense(pk.pq_pos, pos, 0, 3, n, C=pqpos, ldc=pk.pq_pos.N)
     # GCU chain: input of gcu_1 is the feature block, of gcu_2 / gcu_3 the previous output block
     srcs = [(pk.feat_off, pk.gcus[0].pq_x.K), (pk.x_off[0], pk.gcus[1].pq_x.K), (pk.x_off[1], pk.gcus[2].pq_x.K)]
+    tags = [f"{tag}.gcu{k}" for k in range(len(pk.gcus))]
+    run_pos_branches(ws, tags, pk.gcus, pqpos, gt, gg, n, n_frames)
     for k, gp in enumerate(pk.gcus):
-        run_gcu(ws, f"{tag}.gcu{k}", gp, feat, srcs[k][0], ldf, srcs[k][1], pqpos, gt, gg, n, n_frames,
-                feat, pk.x_off[k], ldf)
+        run_gcu(ws, tags[k], gp, feat, srcs[k][0], ldf, srcs[k][1], gt, gg, n, n_frames, feat, pk.x_off[k], ldf)
     xg = ws.get(tag + ".xg", (G, pk.glb.N), dev)
     fill(xg, NEG_INF)
     dense(pk.glb, feat, 0, ldf, R, pool=xg, binfo=binfo, n_vtx=n)                     # x_4 is never stored
@@ -565,15 +614,16 @@ def run_skin(ws: Workspace, tag: str, pk: SkinPack, pos: torch.Tensor, skin_inpu
     dense(pk.pq_pos, raw, 0, pk.k_pos, n, C=pqpos, ldc=pk.pq_pos.N)
     c = pk.gcus[0].out
     xs = [ws.get(f"{tag}.x{k}", (n, c), dev) for k in range(3)]
-    run_gcu(ws, tag + ".gcu0", pk.gcus[0], motion, 0, motion.shape[1], pk.gcus[0].pq_x.K, pqpos, gt, gg, n, 1,
-            xs[0], 0, c)
+    tags = [f"{tag}.gcu{k}" for k in range(3)]
+    run_pos_branches(ws, tags, pk.gcus, pqpos, gt, gg, n, 1)
+    run_gcu(ws, tags[0], pk.gcus[0], motion, 0, motion.shape[1], pk.gcus[0].pq_x.K, gt, gg, n, 1, xs[0], 0, c)
     g0 = ws.get(tag + ".g0", (n, pk.g0.N), dev)
     dense(pk.g0, xs[0], 0, c, n, C=g0, ldc=pk.g0.N)
     xg = ws.get(tag + ".xg", (B, pk.g1.N), dev)
     fill(xg, NEG_INF)
     dense(pk.g1, g0, 0, pk.g0.N, n, pool=xg, binfo=binfo, n_vtx=n)
-    run_gcu(ws, tag + ".gcu1", pk.gcus[1], xs[0], 0, c, c, pqpos, gt, gg, n, 1, xs[1], 0, c)
-    run_gcu(ws, tag + ".gcu2", pk.gcus[2], xs[1], 0, c, c, pqpos, gt, gg, n, 1, xs[2], 0, c)
+    run_gcu(ws, tags[1], pk.gcus[1], xs[0], 0, c, c, gt, gg, n, 1, xs[1], 0, c)
+    run_gcu(ws, tags[2], pk.gcus[2], xs[1], 0, c, c, gt, gg, n, 1, xs[2], 0, c)
     gb = ws.get(tag + ".gb", (B, pk.c0_global.N), dev)
     dense(pk.c0_global, xg, 0, pk.g1.N, B, C=gb, ldc=pk.c0_global.N)
     h1 = ws.get(tag + ".h1", (n, pk.c0.N), dev)

@@ -70,6 +70,11 @@ def edgeconv(br, pq, ldpq, p_off, q_off, g, n_frames, out, ldo, out_off, out_rep
             _view(out, (f + r) * n * ldo + out_off, n, H, ldo).copy_(m)
 
 
+def edgeconv_batch(items, g, n_frames, out_repeat=1):
+    for br, pq, ldpq, p_off, q_off, out, ldo, out_off in items:
+        edgeconv(br, pq, ldpq, p_off, q_off, g, n_frames, out, ldo, out_off, out_repeat)
+
+
 def fill(t, value):
     t.fill_(value)
 
@@ -110,7 +115,7 @@ def _require(t, name, dtype=torch.float32):
 
 
 def install(monkeypatch):
-    for name in ("graph_prep", "dense", "edgeconv", "fill", "gather_cols", "row_normalize", "temporal_attn",
+    for name in ("graph_prep", "dense", "edgeconv", "edgeconv_batch", "fill", "gather_cols", "row_normalize", "temporal_attn",
                  "frame_reduce"):
         monkeypatch.setattr(engine, name, globals()[name])
     monkeypatch.setattr(_lib, "require_cuda", _require)

