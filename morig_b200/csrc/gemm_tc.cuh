@@ -260,6 +260,28 @@ __device__ __forceinline__ void operand_scales(const GemmP &p, bool gather, floa
         inv = __uint_as_float((uint32_t)(127 - sh) << 23) * p.w_inv;
     }
 }
+// packed fp32 pairs (sm_100 FADD2 / FMUL2): one instruction for two lanes of the producers' element-wise work
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<const uint64_t *>(&a)), "l"(*reinterpret_cast<const uint64_t *>(&b)));
+    return *reinterpret_cast<const float2 *>(&r);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<const uint64_t *>(&a)), "l"(*reinterpret_cast<const uint64_t *>(&b)));
+    return *reinterpret_cast<const float2 *>(&r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<const uint64_t *>(&a)), "l"(*reinterpret_cast<const uint64_t *>(&b)));
+    return *reinterpret_cast<const float2 *>(&r);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<const uint64_t *>(&a)),
+        "l"(*reinterpret_cast<const uint64_t *>(&b)), "l"(*reinterpret_cast<const uint64_t *>(&c)));
+    return *reinterpret_cast<const float2 *>(&r);
+}
 __device__ __forceinline__ uint32_t pack_h2(float lo_k, float hi_k) {
     const __half2 h = __floats2half2_rn(lo_k, hi_k);    // lower k in the low half (K-major, little endian)
     return *reinterpret_cast<const uint32_t *>(&h);
@@ -402,25 +424,29 @@ __device__ __forceinline__ void producer_role(const GemmP &p, float a_scale, uin
         uint8_t *a_lo = a_hi + A_HALF_BYTES;
 #pragma unroll
         for (int ps = 0; ps < RPT; ++ps) {
-            float4 v = pd[ps];
+            // two packed halves of the thread's four k-columns
+            float2 va = make_float2(pd[ps].x, pd[ps].y), vb = make_float2(pd[ps].z, pd[ps].w);
             if (GATHER) {
-                v.x = fmaxf(v.x + qd[ps].x, 0.f); v.y = fmaxf(v.y + qd[ps].y, 0.f);
-                v.z = fmaxf(v.z + qd[ps].z, 0.f); v.w = fmaxf(v.w + qd[ps].w, 0.f);
+                va = add2(va, make_float2(qd[ps].x, qd[ps].y));
+                vb = add2(vb, make_float2(qd[ps].z, qd[ps].w));
+                va.x = fmaxf(va.x, 0.f); va.y = fmaxf(va.y, 0.f); vb.x = fmaxf(vb.x, 0.f); vb.y = fmaxf(vb.y, 0.f);
             }
-            if (KIND == KIND_F16) { v.x *= a_scale; v.y *= a_scale; v.z *= a_scale; v.w *= a_scale; }
+            if (KIND == KIND_F16) {
+                const float2 s2 = make_float2(a_scale, a_scale);
+                va = mul2(va, s2); vb = mul2(vb, s2);
+            }
             // hi = x with the 13 low mantissa bits cleared: 11 significant bits, exact both as TF32 and (inside the
             // normal range the scale guarantees) as FP16; lo = x - hi is exact in fp32 and |lo| < 2^-10 |x|, so
             // hi*hi + hi*lo + lo*hi reproduces x*y to ~2^-21.
-            float4 h, l;
-            h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
-            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+            const float2 ha = make_float2(tf32_hi(va.x), tf32_hi(va.y)), hb = make_float2(tf32_hi(vb.x), tf32_hi(vb.y));
+            const float2 la = sub2(va, ha), lb = sub2(vb, hb);
             if (KIND == KIND_F16) {
                 const uint32_t off = soff[ps] ^ (us ? 64u : 0u);     // unit 1 = the other half of the swizzled row
-                *reinterpret_cast<uint2 *>(a_hi + off) = make_uint2(pack_h2(h.x, h.y), pack_h2(h.z, h.w));
-                *reinterpret_cast<uint2 *>(a_lo + off) = make_uint2(pack_h2(l.x, l.y), pack_h2(l.z, l.w));
+                *reinterpret_cast<uint2 *>(a_hi + off) = make_uint2(pack_h2(ha.x, ha.y), pack_h2(hb.x, hb.y));
+                *reinterpret_cast<uint2 *>(a_lo + off) = make_uint2(pack_h2(la.x, la.y), pack_h2(lb.x, lb.y));
             } else {
-                *reinterpret_cast<float4 *>(a_hi + soff[ps]) = h;
-                *reinterpret_cast<float4 *>(a_lo + soff[ps]) = l;
+                *reinterpret_cast<float4 *>(a_hi + soff[ps]) = make_float4(ha.x, ha.y, hb.x, hb.y);
+                *reinterpret_cast<float4 *>(a_lo + soff[ps]) = make_float4(la.x, la.y, lb.x, lb.y);
             }
         }
         if (us == UPS - 1) {
@@ -600,9 +626,15 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_
                 // Straight-line code (32 independent rows give the FP pipes their instruction-level parallelism; a
                 // branch per row made every row its own dependent chain): bias -> ReLU -> BatchNorm affine, then the
                 // running max restarts at segment heads; the value after the last row of a segment is its maximum.
+                const float2 inv2 = make_float2(inv, inv), bias2 = make_float2(bias_l, bias_l);
+                const float2 scale2 = make_float2(scale_l, scale_l), shift2 = make_float2(shift_l, shift_l);
 #pragma unroll
-                for (int r = 0; r < 32; ++r)
-                    w[r] = fmaf(fmaxf(fmaf(__uint_as_float(v[r]), inv, bias_l), 0.f), scale_l, shift_l);
+                for (int r = 0; r < 32; r += 2) {             // two rows per packed FFMA2
+                    float2 x = fma2(make_float2(__uint_as_float(v[r]), __uint_as_float(v[r + 1])), inv2, bias2);
+                    x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f);
+                    x = fma2(x, scale2, shift2);
+                    w[r] = x.x; w[r + 1] = x.y;
+                }
 #pragma unroll
                 for (int r = 1; r < 32; ++r) w[r] = ((heads >> r) & 1u) ? w[r] : fmaxf(w[r - 1], w[r]);
                 for (uint32_t tl = tails; tl; tl &= tl - 1) {
@@ -613,11 +645,16 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_
                 // dense layer, one segment (graph) in the block: straight-line stores, one pooled max at the end
                 const float b_cur = bias_l + (has_rb ? head_bias(0) : 0.f);
                 float am0 = 0.f, am1 = 0.f;
+                const float2 inv2 = make_float2(inv, inv), bias2 = make_float2(b_cur, b_cur);
+                const float2 scale2 = make_float2(scale_l, scale_l), shift2 = make_float2(shift_l, shift_l);
 #pragma unroll
-                for (int r = 0; r < 32; ++r) {
-                    w[r] = fmaf(fmaxf(fmaf(__uint_as_float(v[r]), inv, b_cur), relu_floor), scale_l, shift_l);
-                    if (r & 1) am1 = fmaxf(am1, fabsf(w[r])); else am0 = fmaxf(am0, fabsf(w[r]));
-                    if (crow) crow[(size_t)r * p.ldc] = w[r];
+                for (int r = 0; r < 32; r += 2) {             // two rows per packed FFMA2
+                    float2 x = fma2(make_float2(__uint_as_float(v[r]), __uint_as_float(v[r + 1])), inv2, bias2);
+                    x.x = fmaxf(x.x, relu_floor); x.y = fmaxf(x.y, relu_floor);
+                    x = fma2(x, scale2, shift2);
+                    w[r] = x.x; w[r + 1] = x.y;
+                    am0 = fmaxf(am0, fabsf(x.x)); am1 = fmaxf(am1, fabsf(x.y));
+                    if (crow) { crow[(size_t)r * p.ldc] = x.x; crow[(size_t)(r + 1) * p.ldc] = x.y; }
                 }
                 if (nl_ok) amax_l = fmaxf(amax_l, fmaxf(am0, am1));
                 if (want_max) {
