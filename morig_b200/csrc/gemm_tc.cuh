@@ -84,7 +84,8 @@ template <int BN> struct Cfg {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_CHUNK_BYTES;
     static constexpr int STAGES = PIPE_BYTES / STAGE_BYTES;                  // 2 / 3 for BN = 256 / 128
     static constexpr int NH = BN / 128;                                      // 128-channel accumulators per buffer
-    static constexpr int TMEM_COLS = 2 * BN;                                 // two accumulator buffers
+    static constexpr int NBUF = 512 / BN;                                    // accumulator buffers: all 512 TMEM columns
+    static constexpr int TMEM_COLS = NBUF * BN;                              // (4 for BN = 128, 2 for BN = 256)
     // resident-B mode (all k-chunks of the weight image stay in shared memory for the whole kernel):
     // possible when the CTA only ever sees one n-tile and the image leaves room for >= 2 A stages
     static constexpr int res_stages(int nK) {
@@ -95,8 +96,8 @@ template <int BN> struct Cfg {
 };
 
 // aux block layout (byte offsets): barriers are 8 bytes each
-constexpr uint32_t AUX_A_FULL = 0, AUX_B_FULL = 64, AUX_MMA_DONE = 128, AUX_ACC_FULL = 192, AUX_ACC_EMPTY = 208,
-                   AUX_TMEM_PTR = 224, AUX_B_PEER = 232, AUX_KEYS = 320;
+constexpr uint32_t AUX_A_FULL = 0, AUX_B_FULL = 64, AUX_MMA_DONE = 128, AUX_ACC_FULL = 192, AUX_ACC_EMPTY = 224,
+                   AUX_TMEM_PTR = 256, AUX_B_PEER = 264;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -506,6 +507,8 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_
     constexpr int NRB = (CTAS == 1) ? 4 : 8;         // 32-row blocks per tile (128 rows, or the 256 rows of a pair)
     constexpr int RBW = NRB / 2;                     // row blocks per warp
     constexpr int BUF_COLS = (CTAS == 1) ? BN : 256; // TMEM columns per accumulator buffer
+    constexpr int NBUF = 512 / BUF_COLS;             // accumulator buffers in flight (4 or 2)
+    constexpr int NBUF_LOG = (NBUF == 4) ? 2 : 1;
     const int e = warp - PRODUCER_WARPS;             // epilogue warp 0..7
     const int q = warp & 3;                          // TMEM lane quarter this warp may read (hardware: warp id % 4)
     const int half = e >> 2;
@@ -546,7 +549,7 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_
     int li = 0;
     for (int t = tm.first; t < tm.total; t += tm.step, ++li) {
         const TileCoord tcd = tm.decode(t);
-        const int buf = li & 1;
+        const int buf = li & (NBUF - 1);
         const int row0 = tcd.m0 - (CTAS == 2 ? rank * BM : 0);
         const int n0 = tcd.n_tile * ((CTAS == 1) ? BN : 256) + (CTAS == 2 ? rank * 128 : 0) + q * 32 + lane;
         if (need_keys) {
@@ -563,7 +566,7 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_
         const uint32_t frame_base = (EPI == EPI_SEGMAX) ? (uint32_t)(tcd.frame * p.n_vtx_frame) : 0u;
 
         tr(10);
-        mbar_wait(aux_addr + AUX_ACC_FULL + 8u * buf, (uint32_t)((li >> 1) & 1));
+        mbar_wait(aux_addr + AUX_ACC_FULL + 8u * buf, (uint32_t)((li >> NBUF_LOG) & 1));
         tr(11);
         tc_fence_after();
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BUF_COLS);
@@ -694,7 +697,7 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_
         tr(17);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) release(buf);             // buffer may be overwritten by tile li + 2
+        if (lane == 0) release(buf);             // buffer may be overwritten by tile li + NBUF
         tr(12);
     }
     if (EPI == EPI_SEGMAX || p.C) amax_commit(p.amax_out, amax_l);
@@ -746,7 +749,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
                 mbar_init(bar_b(s), 1);
                 mbar_init(bar_m(s), 1);
             }
-            for (int b = 0; b < 2; ++b) {
+            for (int b = 0; b < C::NBUF; ++b) {
                 mbar_init(bar_accf(b), 1);
                 mbar_init(bar_acce(b), EPILOGUE_WARPS);      // every epilogue warp releases the buffer
             }
@@ -806,9 +809,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
             uint32_t ph = 0, prev_ph = 0;
             bool first = true;
             for (int li = 0; li < my_tiles; ++li) {
-                const int buf = li & 1;
+                const int buf = li & (C::NBUF - 1);
                 tr(20);
-                mbar_wait(bar_acce(buf), ((li >> 1) & 1) ^ 1);     // accumulator buffer drained by the epilogue
+                mbar_wait(bar_acce(buf), ((li / C::NBUF) & 1) ^ 1);     // accumulator buffer drained by the epilogue
                 tr(21);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
