@@ -191,6 +191,16 @@ MORIG_API int morig_fill_f32(float *dst, int64_t n, float value, void *stream);
  * c_amax arguments above keep it up to date for everything that was). */
 MORIG_API int morig_absmax_f32(const float *x, int32_t ldx, int32_t R, int32_t C, float *amax, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * One weighted mean-shift iteration of the joint-extraction post-process (SURVEY.md section 8(f) #4:
+ * utils/cluster_utils.py:14-35 `meanshift_cluster`, called on the shifted vertices right after the
+ * jointnet / masknet forward, evaluate/eval_rigging.py:91).  fp64 like the reference's numpy code.
+ *   pts, pts_out [N,3] (must not alias), weights [N] or NULL, d2_scratch [N],
+ *   diff_sq: device scalar receiving sum_j |p'_j - p_j|^2 (the host loop stops when its sqrt <= 1e-3).
+ * ------------------------------------------------------------------------------------------- */
+MORIG_API int morig_meanshift_step(const double *pts, const double *weights, double bandwidth, int32_t N,
+                                   double *pts_out, double *d2_scratch, double *diff_sq, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

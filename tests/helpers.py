@@ -17,7 +17,8 @@ TOL = 1e-4
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """network fixtures (jointnet_* / masknet_* / skinnet_*); other fixtures are loaded by the tests that use them"""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*net_*.npz")))
 
 
 def load_golden(name: str):

@@ -1,5 +1,7 @@
 """GPU parity tests proper: the CUDA path (through the C-ABI) against the oracle and the golden
 fixtures produced by the unmodified reference.  Run with `pytest -m gpu` on a B200."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -497,3 +499,55 @@ def test_host_pipeline_slot_discipline():
     with pytest.raises(TypeError):
         d = b.to(DEV)
         pipe.submit(d, d.pred_flow)
+
+
+# ---- joint-extraction post-process: weighted mean-shift on the GPU -------------------------------
+def _cluster_points(n_half, seed, n_centres=6):
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-0.4, 0.4, size=(n_centres, 3))
+    pts = c[rng.integers(0, n_centres, n_half)] + rng.normal(0, 0.02, size=(n_half, 3))
+    pts = np.concatenate([pts, pts * np.array([[-1, 1, 1]])], axis=0)
+    w = np.tile(rng.uniform(0.05, 1.0, size=(n_half, 1)).astype(np.float32), (2, 1))
+    return pts, w
+
+
+def test_meanshift_matches_golden_fixture():
+    """fixture produced by the unmodified reference function (oracle/gen_golden_cluster.py); fp64, so the only
+    difference is the summation order of the N-term sums: 1e-9 absolute, same number of iterations"""
+    from morig_b200 import cluster_utils
+    from oracle import cluster_port
+    z = np.load(os.path.join(helpers.GOLDEN_DIR, "meanshift_n300.npz"))
+    got, iters = cluster_utils.meanshift_cluster(z["pts"], float(z["bandwidth"]), z["attn"], int(z["max_iter"]),
+                                                 return_iters=True)
+    _, ref_iters = cluster_port.meanshift_cluster(z["pts"], float(z["bandwidth"]), z["attn"], int(z["max_iter"]),
+                                                  return_iters=True)
+    assert isinstance(got, np.ndarray) and got.dtype == np.float64 and iters == ref_iters
+    assert np.abs(got - z["out"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("n_half,seed,weighted,max_iter", [(1, 0, True, 20), (17, 1, False, 20), (700, 2, True, 30),
+                                                           (1500, 3, True, 5)])
+def test_meanshift_matches_oracle(n_half, seed, weighted, max_iter):
+    from morig_b200 import cluster_utils
+    from oracle import cluster_port
+    pts, w = _cluster_points(n_half, seed)
+    w = w if weighted else None
+    ref, ref_iters = cluster_port.meanshift_cluster(pts, 0.05, w, max_iter, return_iters=True)
+    got, iters = cluster_utils.meanshift_cluster(torch.from_numpy(pts).to(DEV), 0.05,
+                                                 None if w is None else torch.from_numpy(w).to(DEV), max_iter,
+                                                 return_iters=True)
+    assert got.is_cuda and iters == ref_iters
+    assert np.abs(got.cpu().numpy() - ref).max() < 1e-9
+
+
+def test_meanshift_full_size_properties():
+    """8192 points (a 4K-vertex mesh reflected): modes are fixed points (a second run from the result stops after one
+    step), points never leave the bounding box of the input, and the result is deterministic"""
+    from morig_b200 import cluster_utils
+    pts, w = _cluster_points(4096, 9, n_centres=20)
+    a, it_a = cluster_utils.meanshift_cluster(pts, 0.05, w, 30, return_iters=True)
+    b = cluster_utils.meanshift_cluster(pts, 0.05, w, 30)
+    assert np.array_equal(a, b) and 1 < it_a <= 29
+    assert (a.min(0) >= pts.min(0) - 1e-12).all() and (a.max(0) <= pts.max(0) + 1e-12).all()
+    _, it_c = cluster_utils.meanshift_cluster(a, 0.05, w, 30, return_iters=True)
+    assert it_c <= 2

@@ -152,3 +152,33 @@ def test_skin_column_selection_matches_reference_slicing():
             s = s[:, np.arange(s.shape[1]) % 7 != 6][:, 0:6 * 5]
         assert s[0].long().tolist() == packing.skin_columns(160, 5, dg, lf)
         assert s[0].long().tolist() == rignet_port.skin_columns(160, 5, dg, lf).tolist()
+
+
+# ---- joint-extraction post-process: weighted mean-shift ------------------------------------------
+def _meanshift_fixture():
+    z = np.load(os.path.join(helpers.GOLDEN_DIR, "meanshift_n300.npz"))
+    return z["pts"], z["attn"], float(z["bandwidth"]), int(z["max_iter"]), z["out"]
+
+
+def test_meanshift_port_reproduces_golden():
+    from oracle import cluster_port
+    pts, attn, bw, it, out = _meanshift_fixture()
+    got = cluster_port.meanshift_cluster(pts, bw, attn, it)
+    assert np.array_equal(got, out)                  # same numpy operations in the same order: bit-identical
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("n_half,seed,weighted", [(40, 1, True), (150, 2, False), (333, 3, True)])
+def test_meanshift_port_is_bit_identical_to_unmodified_reference(n_half, seed, weighted):
+    import importlib.util
+    from oracle import cluster_port
+    spec = importlib.util.spec_from_file_location("ref_cluster_utils",
+                                                  os.path.join(pyg_shim.REFERENCE_ROOT, "utils", "cluster_utils.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-0.4, 0.4, size=(5, 3))
+    pts = c[rng.integers(0, 5, n_half)] + rng.normal(0, 0.02, size=(n_half, 3))
+    pts = np.concatenate([pts, pts * np.array([[-1, 1, 1]])], axis=0)
+    w = np.tile(rng.uniform(0.05, 1.0, size=(n_half, 1)).astype(np.float32), (2, 1)) if weighted else None
+    assert np.array_equal(cluster_port.meanshift_cluster(pts, 0.05, w, 30), ref.meanshift_cluster(pts.copy(), 0.05, w, max_iter=30))
