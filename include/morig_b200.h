@@ -201,6 +201,20 @@ MORIG_API int morig_absmax_f32(const float *x, int32_t ldx, int32_t R, int32_t C
 MORIG_API int morig_meanshift_step(const double *pts, const double *weights, double bandwidth, int32_t N,
                                    double *pts_out, double *d2_scratch, double *diff_sq, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Surface-geodesic graph build from surface samples + normals:
+ * data_proc/common_ops.py:182-208 (`calc_surface_geodesic` after open3d's sampling) and :214-226
+ * (`get_geo_edges`).  fp64; the all-pairs distances equal scipy's Dijkstra bit for bit.
+ *   pts, normals [S,3]; verts [V,3]; out [V,V] = surface_geodesic; ws from ..._workspace(S, V).
+ *   geo_ball_edges: edges [V, max_nn, 2] int64 rows (i, j) (first degree[i] rows of vertex i valid):
+ *   ball members in ascending index order when they fit, else the max_nn nearest.
+ * ------------------------------------------------------------------------------------------- */
+MORIG_API size_t morig_surface_geodesic_workspace(int32_t S, int32_t V);
+MORIG_API int    morig_surface_geodesic(const double *pts, const double *normals, int32_t S, const double *verts,
+                                        int32_t V, double *out, void *ws, size_t ws_bytes, void *stream);
+MORIG_API int    morig_geo_ball_edges(const double *geodesic, int32_t V, double radius, int32_t max_nn,
+                                      int64_t *edges, int32_t *degree, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

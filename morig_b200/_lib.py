@@ -63,6 +63,10 @@ _SIGNATURES = {
     "morig_dense_fwd": (C.c_int, [C.POINTER(DenseDesc), C.c_void_p]),
     "morig_edgeconv_fwd": (C.c_int, [C.POINTER(EdgeDesc), C.c_void_p]),
     "morig_edgeconv_fwd_batch": (C.c_int, [C.POINTER(EdgeDesc), C.c_int32, C.c_void_p]),
+    "morig_surface_geodesic_workspace": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "morig_surface_geodesic": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                         C.c_size_t, C.c_void_p]),
+    "morig_geo_ball_edges": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "morig_meanshift_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
     "morig_temporal_attn_fwd": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

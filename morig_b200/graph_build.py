@@ -1,0 +1,68 @@
+"""Surface-geodesic graph build on the GPU: `calc_surface_geodesic` / `get_geo_edges` of the
+reference (`data_proc/common_ops.py:176-226`; offline pre-processing and `evaluate/joint2rig.py:505`) from the point
+where the surface samples and their normals exist.  The Poisson-disk sampling and normal estimation are open3d's
+(`mesh.sample_points_poisson_disk`, `estimate_normals`, :178-179) and are not rebuilt: pass their output in.
+
+    geo = surface_geodesic(np.asarray(samples.points), np.asarray(samples.normals), np.asarray(mesh.vertices))
+    geo_edge_index = geo_ball_edges(geo, radius=0.06, max_nn=15)          # rows [i, j] like the reference
+
+numpy in -> numpy out, CUDA tensors in -> CUDA tensors out.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _to_dev(x, dev):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+    return x.to(dev, torch.float64).contiguous()
+
+
+def _device_of(x):
+    if isinstance(x, np.ndarray):
+        return torch.device("cuda", torch.cuda.current_device()), True
+    if not x.is_cuda:
+        raise RuntimeError("morig_b200.graph_build: CUDA tensors (or numpy arrays) expected")
+    return x.device, False
+
+
+def surface_geodesic(pts, pts_normal, verts):
+    """`calc_surface_geodesic` (common_ops.py:182-208) after the sampling: pts, pts_normal [S,3], verts [V,3] ->
+    surface_geodesic [V,V] float64, bit-identical to the reference's numpy + scipy Dijkstra result."""
+    lib = _lib.load()
+    dev, as_numpy = _device_of(pts)
+    p, nrm, v = _to_dev(pts, dev), _to_dev(pts_normal, dev), _to_dev(verts, dev)
+    if p.dim() != 2 or p.shape[1] != 3 or nrm.shape != p.shape or v.dim() != 2 or v.shape[1] != 3:
+        raise ValueError("surface_geodesic: pts / pts_normal must be [S,3] and verts [V,3]")
+    s, nv = p.shape[0], v.shape[0]
+    out = torch.empty(nv, nv, dtype=torch.float64, device=dev)
+    ws_bytes = lib.morig_surface_geodesic_workspace(s, nv)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.morig_surface_geodesic(p.data_ptr(), nrm.data_ptr(), s, v.data_ptr(), nv, out.data_ptr(),
+                                              ws.data_ptr(), ws_bytes, _lib.stream_ptr()), "morig_surface_geodesic")
+    return out.cpu().numpy() if as_numpy else out
+
+
+def geo_ball_edges(surface_geodesic_matrix, radius=0.06, max_nn=15):
+    """`get_geo_edges` (common_ops.py:214-226) after the geodesic matrix: [E,2] int64 rows (i, j), vertices in
+    ascending order.  A vertex with more than `max_nn` neighbours inside the ball keeps the `max_nn` nearest (the
+    reference draws a random subset there, :221)."""
+    lib = _lib.load()
+    dev, as_numpy = _device_of(surface_geodesic_matrix)
+    g = _to_dev(surface_geodesic_matrix, dev)
+    if g.dim() != 2 or g.shape[0] != g.shape[1]:
+        raise ValueError("geo_ball_edges: square matrix expected")
+    nv = g.shape[0]
+    edges = torch.empty(nv, max_nn, 2, dtype=torch.int64, device=dev)
+    deg = torch.empty(nv, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.morig_geo_ball_edges(g.data_ptr(), nv, float(radius), int(max_nn), edges.data_ptr(),
+                                            deg.data_ptr(), _lib.stream_ptr()), "morig_geo_ball_edges")
+    keep = torch.arange(max_nn, device=dev).unsqueeze(0) < deg.unsqueeze(1)      # compaction of the padded rows
+    out = edges[keep]
+    return out.cpu().numpy() if as_numpy else out

@@ -551,3 +551,54 @@ def test_meanshift_full_size_properties():
     assert (a.min(0) >= pts.min(0) - 1e-12).all() and (a.max(0) <= pts.max(0) + 1e-12).all()
     _, it_c = cluster_utils.meanshift_cluster(a, 0.05, w, 30, return_iters=True)
     assert it_c <= 2
+
+
+# ---- surface-geodesic graph build on the GPU: fp64, bit-exact --------------------------------------
+def test_surface_geodesic_matches_golden_fixture():
+    """fixture produced by the unmodified reference (numpy + scipy Dijkstra); two components -> unreachable pairs"""
+    from morig_b200 import graph_build
+    z = np.load(os.path.join(helpers.GOLDEN_DIR, "geodesic_s400_v150.npz"))
+    got = graph_build.surface_geodesic(z["pts"], z["normals"], z["verts"])
+    assert isinstance(got, np.ndarray) and np.array_equal(got, z["surface_geodesic"])
+
+
+@pytest.mark.parametrize("s,v,seed,two", [(2, 1, 0, False), (7, 30, 1, False), (500, 200, 2, False), (1500, 700, 3, True)])
+def test_surface_geodesic_matches_oracle_bit_exact(s, v, seed, two):
+    from morig_b200 import graph_build
+    from oracle import gen_golden_geodesic as gg
+    from oracle import geodesic_port
+    pts, nrm, verts = gg.make_inputs(s, v, seed, two_parts=two)
+    ref = geodesic_port.surface_geodesic_from_samples(pts, nrm, verts)
+    got = graph_build.surface_geodesic(torch.from_numpy(pts).to(DEV), torch.from_numpy(nrm).to(DEV),
+                                       torch.from_numpy(verts).to(DEV))
+    assert got.is_cuda and np.array_equal(got.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("radius,max_nn", [(0.06, 15), (0.15, 15), (0.3, 4), (100.0, 3)])
+def test_geo_ball_edges_bit_exact(radius, max_nn):
+    from morig_b200 import graph_build
+    from oracle import gen_golden_geodesic as gg
+    from oracle import geodesic_port
+    pts, nrm, verts = gg.make_inputs(600, 300, 4)
+    geo = geodesic_port.surface_geodesic_from_samples(pts, nrm, verts)
+    ref = geodesic_port.geo_ball_edges(geo, radius, max_nn)
+    got = graph_build.geo_ball_edges(geo, radius, max_nn)
+    assert got.dtype == np.int64 and np.array_equal(got, ref)
+    assert np.bincount(got[:, 0], minlength=300).max() <= max_nn and (got[:, 0] != got[:, 1]).all()
+
+
+def test_surface_geodesic_full_size_properties():
+    """the reference's size (4000 samples, a 4096-vertex mesh): symmetric, zero diagonal for vertices sharing a sample,
+    triangle inequality on sampled triples, never shorter than the Euclidean distance of the samples, deterministic"""
+    from morig_b200 import graph_build
+    from oracle import gen_golden_geodesic as gg
+    pts, nrm, verts = gg.make_inputs(4000, 4096, 6)
+    a = graph_build.surface_geodesic(pts, nrm, verts)
+    assert np.array_equal(a, graph_build.surface_geodesic(pts, nrm, verts))
+    assert np.array_equal(a, a.T) and (a >= 0).all() and np.isfinite(a).all()
+    nn = np.argmin(np.sqrt(((verts[None] - pts[:, None]) ** 2).sum(2)), axis=0)
+    euc = np.sqrt(((pts[nn][None] - pts[nn][:, None]) ** 2).sum(2))
+    assert (a >= euc - 1e-6).all()
+    rng = np.random.default_rng(0)
+    i, j, k = rng.integers(0, 4096, (3, 20000))
+    assert (a[i, j] <= a[i, k] + a[k, j] + 1e-9).all()

@@ -182,3 +182,51 @@ def test_meanshift_port_is_bit_identical_to_unmodified_reference(n_half, seed, w
     pts = np.concatenate([pts, pts * np.array([[-1, 1, 1]])], axis=0)
     w = np.tile(rng.uniform(0.05, 1.0, size=(n_half, 1)).astype(np.float32), (2, 1)) if weighted else None
     assert np.array_equal(cluster_port.meanshift_cluster(pts, 0.05, w, 30), ref.meanshift_cluster(pts.copy(), 0.05, w, max_iter=30))
+
+
+# ---- surface-geodesic graph build -------------------------------------------------------------------
+def test_geodesic_port_reproduces_golden():
+    from oracle import geodesic_port
+    z = np.load(os.path.join(helpers.GOLDEN_DIR, "geodesic_s400_v150.npz"))
+    got = geodesic_port.surface_geodesic_from_samples(z["pts"], z["normals"], z["verts"])
+    assert np.array_equal(got, z["surface_geodesic"])        # same numpy / scipy calls: bit-identical
+    assert (got > 8.0).any()                                 # the fixture has unreachable pairs (two components)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("s,v,seed,two", [(60, 25, 1, False), (300, 120, 2, True)])
+def test_geodesic_port_is_bit_identical_to_unmodified_reference(s, v, seed, two):
+    """the unmodified `calc_surface_geodesic` / `get_geo_edges` run on a stand-in mesh that hands out pre-drawn samples"""
+    from oracle import gen_golden_geodesic as gg
+    from oracle import geodesic_port
+    co = gg.load_reference()
+    pts, nrm, verts = gg.make_inputs(s, v, seed, two_parts=two)
+    ref = co.calc_surface_geodesic(gg.FakeMesh(verts, pts, nrm))
+    assert np.array_equal(geodesic_port.surface_geodesic_from_samples(pts, nrm, verts), ref)
+    # get_geo_edges: deterministic whenever no ball exceeds max_nn (here: max_nn = number of vertices)
+    class Remeshed(gg.FakeMesh):
+        pass
+    ref_edges = co.get_geo_edges(Remeshed(verts, pts, nrm), radius=0.1, max_nn=v)
+    assert np.array_equal(geodesic_port.geo_ball_edges(ref, 0.1, v), ref_edges)
+
+
+def test_geodesic_port_against_floyd_warshall():
+    """independent check of the shortest-path part on a tiny sample set"""
+    from oracle import gen_golden_geodesic as gg
+    from oracle import geodesic_port
+    pts, nrm, _ = gg.make_inputs(24, 5, 5)
+    geo = geodesic_port.surface_geodesic_from_samples(pts, nrm, pts)          # vertices = the samples themselves
+    n = len(pts)
+    d = np.sqrt(((pts[None] - pts[:, None]) ** 2).sum(2))
+    w = np.full((n, n), np.inf)
+    order = np.argsort(d, axis=1)
+    for p in range(n):
+        for q in order[p, 1:6]:
+            cs = nrm[q] @ nrm[p] / (np.linalg.norm(nrm[q]) * np.linalg.norm(nrm[p]) + 1e-10)
+            if cs > -0.5:
+                w[p, q] = w[q, p] = min(w[p, q], float(np.float32(d[p, q])))
+    np.fill_diagonal(w, 0.0)
+    for k in range(n):
+        w = np.minimum(w, w[:, k:k + 1] + w[k:k + 1, :])
+    w[np.isinf(w)] = (8.0 + d)[np.isinf(w)]
+    assert np.allclose(geo, w, rtol=0, atol=1e-12)
