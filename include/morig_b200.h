@@ -215,6 +215,13 @@ MORIG_API int    morig_surface_geodesic(const double *pts, const double *normals
 MORIG_API int    morig_geo_ball_edges(const double *geodesic, int32_t V, double radius, int32_t max_nn,
                                       int64_t *edges, int32_t *degree, void *stream);
 
+/* Topological edges from the triangle list: data_proc/common_ops.py:15-32 (`get_tpl_edges`).
+ *   faces [F,3] int64 -> edges [<= 6F, 2] int64 rows (v, n): per vertex its distinct face neighbours, ascending
+ *   (the reference lists them in python-set order; the edge set is identical).  *count = rows written. */
+MORIG_API size_t morig_tpl_edges_workspace(int64_t F);
+MORIG_API int    morig_tpl_edges(const int64_t *faces, int64_t F, int64_t *edges, int64_t *count, void *ws,
+                                 size_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -299,3 +299,70 @@ extern "C" MORIG_API int morig_geo_ball_edges(const double *geodesic, int32_t V,
     MORIG_LAUNCH_CHECK("geo_ball_kernel");
     return 0;
 }
+
+// ---- topological edges from the triangle list (data_proc/common_ops.py:15-32 `get_tpl_edges`) -------------------------
+// The reference scans the whole face array once per vertex (O(V F) in python).  Here every face emits its six directed
+// half-edges as 64-bit keys (v << 32 | n); a radix sort and a unique pass leave, per vertex, its distinct neighbours in
+// ascending order.  (The reference lists a vertex's neighbours in python-set iteration order; the edge SET is the same,
+// and the networks' max-aggregation does not depend on edge order.)
+#include <cub/cub.cuh>
+
+namespace morig {
+
+__global__ void tpl_emit_kernel(const int64_t *__restrict__ faces, int64_t F, uint64_t *keys) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const uint64_t a = (uint64_t)faces[3 * f], b = (uint64_t)faces[3 * f + 1], c = (uint64_t)faces[3 * f + 2];
+    const uint64_t SKIP = ~0ull;                                 // degenerate corner pairs (n == v) are not neighbours
+    uint64_t *k = keys + 6 * f;
+    k[0] = a != b ? (a << 32 | b) : SKIP; k[1] = a != c ? (a << 32 | c) : SKIP;
+    k[2] = b != a ? (b << 32 | a) : SKIP; k[3] = b != c ? (b << 32 | c) : SKIP;
+    k[4] = c != a ? (c << 32 | a) : SKIP; k[5] = c != b ? (c << 32 | b) : SKIP;
+}
+
+__global__ void tpl_unpack_kernel(const uint64_t *__restrict__ keys, const int32_t *__restrict__ n_unique, int64_t cap,
+                                  int64_t *edges, int64_t *count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t n = *n_unique;
+    if (n > 0 && keys[n - 1] == ~0ull) --n;                      // the SKIP key sorts last
+    if (i == 0) *count = n;
+    if (i >= n || i >= cap) return;
+    edges[2 * i] = (int64_t)(keys[i] >> 32);
+    edges[2 * i + 1] = (int64_t)(keys[i] & 0xffffffffull);
+}
+
+}  // namespace morig
+
+extern "C" MORIG_API size_t morig_tpl_edges_workspace(int64_t F) {
+    if (F <= 0) return 0;
+    const int64_t n = 6 * F;
+    size_t sort_bytes = 0, uniq_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int)n);
+    cub::DeviceSelect::Unique(nullptr, uniq_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int32_t *)nullptr, (int)n);
+    const size_t tmp = sort_bytes > uniq_bytes ? sort_bytes : uniq_bytes;
+    return 3 * align256((size_t)n * 8) + align256(tmp) + 256;
+}
+
+// edges [6F, 2] int64 (capacity), count: device int64 receiving the number of rows written
+extern "C" MORIG_API int morig_tpl_edges(const int64_t *faces, int64_t F, int64_t *edges, int64_t *count, void *ws,
+                                         size_t ws_bytes, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MORIG_CHECK_ARG(faces && edges && count && ws && F > 0 && 6 * F < (1ll << 31), "tpl_edges: bad argument");
+    MORIG_CHECK_ARG(ws_bytes >= morig_tpl_edges_workspace(F), "tpl_edges: workspace too small");
+    const int64_t n = 6 * F;
+    uint8_t *w = reinterpret_cast<uint8_t *>(ws);
+    uint64_t *k0 = reinterpret_cast<uint64_t *>(w); w += align256((size_t)n * 8);
+    uint64_t *k1 = reinterpret_cast<uint64_t *>(w); w += align256((size_t)n * 8);
+    uint64_t *k2 = reinterpret_cast<uint64_t *>(w); w += align256((size_t)n * 8);
+    int32_t *n_unique = reinterpret_cast<int32_t *>(w); w += 256;
+    size_t sort_bytes = 0, uniq_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, k0, k1, (int)n);
+    cub::DeviceSelect::Unique(nullptr, uniq_bytes, k1, k2, n_unique, (int)n);
+    tpl_emit_kernel<<<(unsigned)ceil_div64(F, 256), 256, 0, stream>>>(faces, F, k0);
+    MORIG_LAUNCH_CHECK("tpl_emit_kernel");
+    MORIG_CUDA(cub::DeviceRadixSort::SortKeys(w, sort_bytes, k0, k1, (int)n, 0, 64, stream));
+    MORIG_CUDA(cub::DeviceSelect::Unique(w, uniq_bytes, k1, k2, n_unique, (int)n, stream));
+    tpl_unpack_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, stream>>>(k2, n_unique, n, edges, count);
+    MORIG_LAUNCH_CHECK("tpl_unpack_kernel");
+    return 0;
+}

@@ -66,3 +66,30 @@ def geo_ball_edges(surface_geodesic_matrix, radius=0.06, max_nn=15):
     keep = torch.arange(max_nn, device=dev).unsqueeze(0) < deg.unsqueeze(1)      # compaction of the padded rows
     out = edges[keep]
     return out.cpu().numpy() if as_numpy else out
+
+
+def tpl_edges(obj_v, obj_f):
+    """`get_tpl_edges(obj_v, obj_f)` (common_ops.py:15-32): [E,2] int64 rows (v, n) for every vertex v and each of its
+    distinct neighbours n over the faces it belongs to.  Rows are sorted by (v, n); the reference emits a vertex's
+    neighbours in python-set iteration order, the edge set is the same.  `obj_v` is only used for its type."""
+    lib = _lib.load()
+    as_numpy = isinstance(obj_f, np.ndarray)
+    dev = torch.device("cuda", torch.cuda.current_device()) if as_numpy else obj_f.device
+    if dev.type != "cuda":
+        raise RuntimeError("morig_b200.graph_build: CUDA tensors (or numpy arrays) expected")
+    f = (torch.from_numpy(np.ascontiguousarray(obj_f, dtype=np.int64)) if as_numpy else obj_f).to(dev, torch.int64).contiguous()
+    if f.dim() != 2 or f.shape[1] != 3:
+        raise ValueError("tpl_edges: faces must be [F, 3]")
+    nf = f.shape[0]
+    if nf == 0:
+        out = torch.empty(0, 2, dtype=torch.int64, device=dev)
+        return out.cpu().numpy() if as_numpy else out
+    edges = torch.empty(6 * nf, 2, dtype=torch.int64, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws_bytes = lib.morig_tpl_edges_workspace(nf)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.morig_tpl_edges(f.data_ptr(), nf, edges.data_ptr(), count.data_ptr(), ws.data_ptr(), ws_bytes,
+                                       _lib.stream_ptr()), "morig_tpl_edges")
+    out = edges[: int(count.item())]
+    return out.cpu().numpy() if as_numpy else out

@@ -50,3 +50,27 @@ def geo_ball_edges(surface_geodesic, radius=0.06, max_nn=15):
             ball = ball[order[:max_nn]]
         edge_index.append(np.concatenate((np.repeat(i, len(ball))[:, np.newaxis], ball[:, np.newaxis]), axis=1))   # :223
     return np.concatenate(edge_index, axis=0)
+
+
+def tpl_edges(obj_v, obj_f):
+    """`get_tpl_edges` (data_proc/common_ops.py:15-32), statement for statement"""
+    edge_index = []
+    for v in range(len(obj_v)):                                                               # :17
+        face_ids = np.argwhere(obj_f == v)[:, 0]                                              # :18
+        neighbor_ids = []
+        for face_id in face_ids:                                                              # :20-23
+            for v_id in range(3):
+                if obj_f[face_id, v_id] != v:
+                    neighbor_ids.append(obj_f[face_id, v_id])
+        neighbor_ids = list(set(neighbor_ids))                                                # :24
+        neighbor_ids = [np.array([v, n])[np.newaxis, :] for n in neighbor_ids]                # :25
+        if len(neighbor_ids) > 0:
+            edge_index.append(np.concatenate(neighbor_ids, axis=0))                           # :27-28
+    return np.concatenate(edge_index, axis=0)                                                 # :31
+
+
+def sorted_rows(e):
+    """rows in (v, n) order: the canonical form in which edge lists are compared (a vertex's neighbours come out of
+    the reference in python-set iteration order)"""
+    e = np.asarray(e, dtype=np.int64)
+    return e[np.lexsort((e[:, 1], e[:, 0]))]

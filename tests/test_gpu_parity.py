@@ -602,3 +602,16 @@ def test_surface_geodesic_full_size_properties():
     rng = np.random.default_rng(0)
     i, j, k = rng.integers(0, 4096, (3, 20000))
     assert (a[i, j] <= a[i, k] + a[k, j] + 1e-9).all()
+
+
+@pytest.mark.parametrize("nu,nv", [(2, 2), (7, 9), (64, 64)])
+def test_tpl_edges_bit_exact(nu, nv):
+    """topological edges from the face list against the statement-for-statement port of get_tpl_edges
+    (compared as (v, n)-sorted rows; the reference's order inside a vertex is python-set order)"""
+    from morig_b200 import graph_build
+    from oracle import geodesic_port
+    from test_oracle_pinning import _grid_faces
+    verts, faces = _grid_faces(nu, nv, nu)
+    got = graph_build.tpl_edges(verts, faces)
+    ref = geodesic_port.sorted_rows(geodesic_port.tpl_edges(verts, faces))
+    assert got.dtype == np.int64 and np.array_equal(got, ref)

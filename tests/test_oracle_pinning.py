@@ -230,3 +230,24 @@ def test_geodesic_port_against_floyd_warshall():
         w = np.minimum(w, w[:, k:k + 1] + w[k:k + 1, :])
     w[np.isinf(w)] = (8.0 + d)[np.isinf(w)]
     assert np.allclose(geo, w, rtol=0, atol=1e-12)
+
+
+def _grid_faces(nu, nv, seed):
+    """triangulated open grid with a few isolated vertices, one degenerate and one duplicated face"""
+    rng = np.random.default_rng(seed)
+    vid = np.arange(nu * nv).reshape(nu, nv)
+    a, b, c, d = vid[:-1, :-1].ravel(), vid[1:, :-1].ravel(), vid[:-1, 1:].ravel(), vid[1:, 1:].ravel()
+    f = np.concatenate([np.stack([a, b, c], 1), np.stack([b, d, c], 1)])
+    f = f[rng.permutation(len(f))]
+    f = np.concatenate([f, f[:1], np.array([[0, 0, 5]])])
+    verts = np.zeros((nu * nv + 3, 3))                       # three vertices without faces
+    return verts, f.astype(np.int64)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference only exists in the build container")
+def test_tpl_edges_port_is_identical_to_unmodified_reference():
+    from oracle import gen_golden_geodesic as gg
+    from oracle import geodesic_port
+    co = gg.load_reference()
+    verts, faces = _grid_faces(7, 9, 0)
+    assert np.array_equal(geodesic_port.tpl_edges(verts, faces), co.get_tpl_edges(verts, faces))   # incl. set order
