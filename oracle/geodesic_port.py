@@ -53,20 +53,16 @@ def geo_ball_edges(surface_geodesic, radius=0.06, max_nn=15):
 
 
 def tpl_edges(obj_v, obj_f):
-    """`get_tpl_edges` (data_proc/common_ops.py:15-32), statement for statement"""
-    edge_index = []
-    for v in range(len(obj_v)):                                                               # :17
-        face_ids = np.argwhere(obj_f == v)[:, 0]                                              # :18
-        neighbor_ids = []
-        for face_id in face_ids:                                                              # :20-23
-            for v_id in range(3):
-                if obj_f[face_id, v_id] != v:
-                    neighbor_ids.append(obj_f[face_id, v_id])
-        neighbor_ids = list(set(neighbor_ids))                                                # :24
-        neighbor_ids = [np.array([v, n])[np.newaxis, :] for n in neighbor_ids]                # :25
-        if len(neighbor_ids) > 0:
-            edge_index.append(np.concatenate(neighbor_ids, axis=0))                           # :27-28
-    return np.concatenate(edge_index, axis=0)                                                 # :31
+    """`get_tpl_edges` (data_proc/common_ops.py:15-32): for every vertex, the distinct other corners of the faces it
+    belongs to, as rows (v, n); neighbours of a vertex in python-set iteration order, vertices without faces skipped"""
+    rows = []
+    for v in range(len(obj_v)):
+        faces_of_v = np.argwhere(obj_f == v)[:, 0]                                            # :18
+        others = [obj_f[f, c] for f in faces_of_v for c in range(3) if obj_f[f, c] != v]      # :20-23
+        uniq = list(set(others))                                                              # :24 (set order kept)
+        if uniq:
+            rows.append(np.array([[v, n] for n in uniq]))                                     # :25-28
+    return np.concatenate(rows, axis=0)                                                       # :31
 
 
 def sorted_rows(e):
