@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MORIG_ABI_VERSION 2
+#define MORIG_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define MORIG_API __attribute__((visibility("default")))

@@ -84,7 +84,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 
