@@ -352,6 +352,42 @@ __global__ void __launch_bounds__(SKINNY_THREADS) dense_skinny_kernel(const Gemm
     amax_commit(p.amax_out, am);
 }
 
+// ---- tiny-K dense layer (K <= 8: the first Linear on 3-D positions / flows) -----------------------------------
+// [M, K] x [K, N] with K of 3 or 4 is a streaming write of M x N outputs: one thread per (row, 4 consecutive
+// columns), weights through L1, float4 stores.
+constexpr int SMALLK_MAX = 8;
+
+__global__ void __launch_bounds__(256) dense_smallk_kernel(const GemmP p) {
+    const int nq = p.N >> 2;                                    // N % 4 == 0 (checked by the launcher)
+    const long long total = (long long)p.M * nq, stride = (long long)gridDim.x * blockDim.x;
+    float am = 0.f;
+    // grid-stride: the operand-range atomic at the end is one per warp of a bounded grid, not one per 32 outputs
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int m = (int)(idx / nq), n = (int)(idx - (long long)m * nq) * 4;
+        float a[SMALLK_MAX];
+#pragma unroll
+        for (int k = 0; k < SMALLK_MAX; ++k) a[k] = k < p.K ? p.A[(size_t)m * p.lda + k] : 0.f;
+        float4 acc = p.bias ? *reinterpret_cast<const float4 *>(p.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < SMALLK_MAX; ++k) {
+            if (k < p.K) {
+                const float4 w = *reinterpret_cast<const float4 *>(p.W + (size_t)k * p.ldw + n);
+                acc.x = fmaf(a[k], w.x, acc.x); acc.y = fmaf(a[k], w.y, acc.y);
+                acc.z = fmaf(a[k], w.z, acc.z); acc.w = fmaf(a[k], w.w, acc.w);
+            }
+        }
+        if (p.relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+        if (p.scale) {
+            const float4 sc = *reinterpret_cast<const float4 *>(p.scale + n), sh = *reinterpret_cast<const float4 *>(p.shift + n);
+            acc.x = fmaf(acc.x, sc.x, sh.x); acc.y = fmaf(acc.y, sc.y, sh.y);
+            acc.z = fmaf(acc.z, sc.z, sh.z); acc.w = fmaf(acc.w, sc.w, sh.w);
+        }
+        *reinterpret_cast<float4 *>(p.C + (size_t)m * p.ldc + n) = acc;
+        am = fmaxf(am, fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w))));
+    }
+    amax_commit(p.amax_out, am);
+}
+
 template <int BM, int BN, int AMODE, int EPI>
 static int launch_gemm(const GemmP &p, dim3 grid, cudaStream_t stream, const char *name) {
     auto kern = gemm_simt_kernel<BM, BN, AMODE, EPI>;
@@ -499,6 +535,13 @@ extern "C" MORIG_API int morig_dense_fwd(const morig_dense_desc *d, void *stream
     p.pool = d->pool; p.ldpool = d->ldpool;
     p.M = d->M; p.N = d->N; p.K = d->K; p.relu = d->relu;
     p.amax_in = d->a_amax; p.amax_out = d->c_amax; p.w_inv = 1.f;
+    if (d->K <= SMALLK_MAX && d->N % 4 == 0 && p.c_vec && d->C && !d->pool && !d->rowbias && aligned16(d->W) &&
+        (!d->bias || aligned16(d->bias)) && (!d->scale || (d->shift && aligned16(d->scale) && aligned16(d->shift)))) {
+        const long long blocks = ceil_div64((long long)d->M * (d->N / 4), 256), cap = (long long)sm_count() * 8;
+        dense_smallk_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(p);
+        MORIG_LAUNCH_CHECK("dense_smallk_kernel");
+        return 0;
+    }
     if (d->M <= SKINNY_MAX_M && d->K >= 64 && p.a_vec && d->C && !d->pool && !d->rowbias) {
         const size_t smem = (size_t)SKINNY_KG * d->M * SKINNY_COLS * sizeof(float);
         dense_skinny_kernel<<<ceil_div(d->N, SKINNY_COLS), SKINNY_THREADS, smem, stream>>>(p);

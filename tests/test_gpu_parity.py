@@ -62,7 +62,8 @@ def test_knn_graph_bit_exact(n, b):
 
 # ---- kernels against straightforward torch fp32 references -------------------------------------------
 @pytest.mark.parametrize("M,K,N", [(1, 3, 5), (130, 36, 64), (257, 838, 1024), (1000, 256, 3), (4099, 544, 512),
-                                   (20, 1024, 1024), (4, 1024, 1024), (32, 64, 9), (1, 1024, 1021)])   # last four: skinny kernel
+                                   (20, 1024, 1024), (4, 1024, 1024), (32, 64, 9), (1, 1024, 1021),    # skinny kernel
+                                   (1000, 3, 192), (257, 4, 128), (5, 8, 12), (4099, 3, 64)])          # tiny-K kernel
 def test_dense_fwd(M, K, N):
     g = torch.Generator().manual_seed(M + K + N)
     A = torch.randn(M, K, generator=g)
