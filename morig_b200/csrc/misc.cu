@@ -114,17 +114,19 @@ __global__ void frame_reduce_kernel(const float *__restrict__ x, int N, int T, i
 __global__ void gather_cols_kernel(const float *__restrict__ src, int lds, int src_off, int frame_stride,
                                    const int32_t *__restrict__ cols, int C, int N, int n_frames, float *dst, int ldd,
                                    int dst_off, float *dst_amax) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    float val = 0.f;
-    if (idx < (int64_t)N * n_frames * C) {
+    // grid-stride over a bounded grid: the operand-range atomic below is per warp, all on one address
+    const int64_t total = (int64_t)N * n_frames * C;
+    float am = 0.f;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(idx % C);
         const int64_t r = idx / C;
         const int f = (int)(r / N), v = (int)(r % N);
         const int sc = src_off + f * frame_stride + (cols ? cols[c] : c);
-        val = src[(size_t)v * lds + sc];
+        const float val = src[(size_t)v * lds + sc];
         dst[(size_t)r * ldd + dst_off + c] = val;
+        am = fmaxf(am, fabsf(val));
     }
-    amax_commit(dst_amax, fabsf(val));
+    amax_commit(dst_amax, am);
 }
 
 // grid-stride max |x| of a strided [R, C] block
@@ -190,8 +192,9 @@ extern "C" MORIG_API int morig_gather_cols(const float *src, int32_t lds, int32_
     cudaStream_t stream = (cudaStream_t)stream_;
     MORIG_CHECK_ARG(src && dst && C > 0 && N > 0 && n_frames > 0, "gather_cols: bad argument");
     const int64_t total = (int64_t)N * n_frames * C;
-    gather_cols_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(src, lds, src_off, frame_stride, cols, C, N,
-                                                                            n_frames, dst, ldd, dst_off, dst_amax);
+    const int64_t blocks = ceil_div64(total, 256), cap = (int64_t)sm_count() * 8;
+    gather_cols_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(src, lds, src_off, frame_stride, cols, C, N,
+                                                                                   n_frames, dst, ldd, dst_off, dst_amax);
     MORIG_LAUNCH_CHECK("gather_cols_kernel");
     return 0;
 }
