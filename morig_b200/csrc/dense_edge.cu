@@ -304,51 +304,87 @@ static int check_narrow(const morig_edge_desc *d) {
 
 // ---- skinny dense layer (M <= 32 rows) -------------------------------------------------------------
 // The per-graph layers (e.g. the [B, 1024] x [1024, 1024] bias derived from the pooled global feature,
-// models/rignet.py:64-65) have a handful of rows: the cost is streaming the weight matrix once.  A tile engine
-// would put that on N / 256 CTAs; here N / 8 CTAs each own 8 output columns, 32 thread groups split K, every
-// thread keeps the M partial sums of its column in registers, and one shared-memory pass adds the groups.
+// models/rignet.py:64-65) have a handful of rows: the cost is streaming the weight matrix once, i.e. DRAM latency,
+// so the work is spread over as many CTAs as possible while every weight read stays a full 128-byte line.
+// A cluster of 8 CTAs owns 32 output columns; CTA r of the cluster takes every 8th group of 8 k-rows (split-K), its
+// eight k-lanes keep the M partial sums of their column in registers, and the partials are added in a fixed order:
+// first across the k-lanes through shared memory, then across the cluster through distributed shared memory by
+// rank 0, which applies the epilogue.  Deterministic, no workspace.
 constexpr int SKINNY_MAX_M = 32;
-constexpr int SKINNY_COLS = 8;
-constexpr int SKINNY_THREADS = 256;
-constexpr int SKINNY_KG = SKINNY_THREADS / SKINNY_COLS;
+constexpr int SKINNY_COLS = 32;
+constexpr int SKINNY_KL = 8;                        // k-lanes per CTA
+constexpr int SKINNY_SPLIT = 8;                     // CTAs per cluster (split-K)
+constexpr int SKINNY_THREADS = SKINNY_COLS * SKINNY_KL;
 
-__global__ void __launch_bounds__(SKINNY_THREADS) dense_skinny_kernel(const GemmP p) {
-    extern __shared__ float s_part[];               // [KG][M][COLS]
-    const int col = threadIdx.x % SKINNY_COLS, kg = threadIdx.x / SKINNY_COLS;
+__global__ void __cluster_dims__(1, SKINNY_SPLIT, 1) __launch_bounds__(SKINNY_THREADS) dense_skinny_kernel(const GemmP p) {
+    extern __shared__ float s_mem[];                // [KL][M][COLS] k-lane partials; then [M][COLS] CTA partial at the front
+    const int col = threadIdx.x % SKINNY_COLS, kl = threadIdx.x / SKINNY_COLS;
+    const int rank = blockIdx.y;                    // cluster dims (1, 8, 1): rank in the cluster == blockIdx.y
     const int n = blockIdx.x * SKINNY_COLS + col;
     const bool n_ok = n < p.N;
     float acc[SKINNY_MAX_M];
 #pragma unroll
     for (int m = 0; m < SKINNY_MAX_M; ++m) acc[m] = 0.f;
-    for (int k4 = 4 * kg; k4 < p.K; k4 += 4 * SKINNY_KG) {      // K % 4 == 0 (checked by the launcher)
+    // k = 4 * (kl + 8 * (rank + 8 * i)) .. + 3: a warp reads four full 128-byte lines of W per step
+    for (int k4 = 4 * (kl + SKINNY_KL * rank); k4 < p.K; k4 += 4 * SKINNY_KL * SKINNY_SPLIT) {      // K % 4 == 0
         float w[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) w[j] = n_ok ? p.W[(size_t)(k4 + j) * p.ldw + n] : 0.f;
 #pragma unroll
         for (int m = 0; m < SKINNY_MAX_M; ++m) {
             if (m < p.M) {
-                const float4 a = *reinterpret_cast<const float4 *>(p.A + (size_t)m * p.lda + k4);
+                const float4 a = *reinterpret_cast<const float4 *>(p.A + (size_t)m * p.lda + k4);   // warp-uniform address
                 acc[m] = fmaf(a.x, w[0], fmaf(a.y, w[1], fmaf(a.z, w[2], fmaf(a.w, w[3], acc[m]))));
             }
         }
     }
 #pragma unroll
     for (int m = 0; m < SKINNY_MAX_M; ++m)
-        if (m < p.M) s_part[(kg * p.M + m) * SKINNY_COLS + col] = acc[m];
+        if (m < p.M) s_mem[(kl * p.M + m) * SKINNY_COLS + col] = acc[m];
     __syncthreads();
-    float am = 0.f;
-    for (int o = threadIdx.x; o < p.M * SKINNY_COLS; o += SKINNY_THREADS) {
-        const int m = o / SKINNY_COLS, c = o % SKINNY_COLS, nn = blockIdx.x * SKINNY_COLS + c;
+    float part[SKINNY_MAX_M / SKINNY_KL];           // this thread's share of the [M][COLS] CTA partial
+#pragma unroll
+    for (int i = 0; i < SKINNY_MAX_M / SKINNY_KL; ++i) {
+        const int m = kl + SKINNY_KL * i;
         float sum = 0.f;
-        for (int g = 0; g < SKINNY_KG; ++g) sum += s_part[(g * p.M + m) * SKINNY_COLS + c];
-        if (nn < p.N) {
-            float x = sum + (p.bias ? p.bias[nn] : 0.f);
-            if (p.relu) x = fmaxf(x, 0.f);
-            const float z = fmaf(x, p.scale ? p.scale[nn] : 1.f, p.shift ? p.shift[nn] : 0.f);
-            p.C[(size_t)m * p.ldc + nn] = z;
-            am = fmaxf(am, fabsf(z));
+        if (m < p.M)
+            for (int g = 0; g < SKINNY_KL; ++g) sum += s_mem[(g * p.M + m) * SKINNY_COLS + col];      // fixed order
+        part[i] = sum;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SKINNY_MAX_M / SKINNY_KL; ++i) {
+        const int m = kl + SKINNY_KL * i;
+        if (m < p.M) s_mem[m * SKINNY_COLS + col] = part[i];
+    }
+    // cluster barrier (release / acquire): every CTA's partial is visible to rank 0
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    float am = 0.f;
+    if (rank == 0) {
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(s_mem);
+#pragma unroll
+        for (int i = 0; i < SKINNY_MAX_M / SKINNY_KL; ++i) {
+            const int m = kl + SKINNY_KL * i;
+            if (m >= p.M) continue;
+            float sum = 0.f;
+            for (uint32_t r = 0; r < SKINNY_SPLIT; ++r) {                                           // fixed order
+                uint32_t addr;
+                float v;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(addr) : "r"(base + 4u * (m * SKINNY_COLS + col)), "r"(r));
+                asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+                sum += v;
+            }
+            if (n_ok) {
+                float x = sum + (p.bias ? p.bias[n] : 0.f);
+                if (p.relu) x = fmaxf(x, 0.f);
+                const float z = fmaf(x, p.scale ? p.scale[n] : 1.f, p.shift ? p.shift[n] : 0.f);
+                p.C[(size_t)m * p.ldc + n] = z;
+                am = fmaxf(am, fabsf(z));
+            }
         }
     }
+    // no CTA may exit while rank 0 still reads its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     amax_commit(p.amax_out, am);
 }
 
@@ -543,8 +579,8 @@ extern "C" MORIG_API int morig_dense_fwd(const morig_dense_desc *d, void *stream
         return 0;
     }
     if (d->M <= SKINNY_MAX_M && d->K >= 64 && p.a_vec && d->C && !d->pool && !d->rowbias) {
-        const size_t smem = (size_t)SKINNY_KG * d->M * SKINNY_COLS * sizeof(float);
-        dense_skinny_kernel<<<ceil_div(d->N, SKINNY_COLS), SKINNY_THREADS, smem, stream>>>(p);
+        const size_t smem = (size_t)SKINNY_KL * d->M * SKINNY_COLS * sizeof(float);
+        dense_skinny_kernel<<<dim3(ceil_div(d->N, SKINNY_COLS), SKINNY_SPLIT), SKINNY_THREADS, smem, stream>>>(p);
         MORIG_LAUNCH_CHECK("dense_skinny_kernel");
         return 0;
     }
