@@ -82,7 +82,8 @@ KINDS = [pytest.param(packing.KIND_TF32, id="tf32"), pytest.param(packing.KIND_F
 
 @pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("M,K,N", [(128, 32, 64), (300, 96, 64), (1000, 64, 128), (257, 288, 256), (4099, 544, 512),
-                                   (640, 840, 1024), (20, 1024, 1024), (513, 36, 768), (40000, 256, 256)])
+                                   (640, 840, 1024), (20, 1024, 1024), (513, 36, 768), (40000, 256, 256),
+                                   (300, 64, 40), (500, 128, 100), (700, 96, 200), (129, 32, 17), (33, 64, 1000)])
 def test_dense_fwd_tensor_core(M, K, N, kind):
     """tcgen05 split-precision engine (both operand kinds) against an fp64 reference: fp32-class accuracy is
     required (tolerance of the path is 1e-4 absolute after ~20 chained layers, so a single layer must stay near
