@@ -13,13 +13,20 @@ import torch
 from . import _lib
 
 
+def _require_cuda_device() -> torch.device:
+    """numpy inputs are processed on the current CUDA device; there is no CPU path"""
+    if not torch.cuda.is_available():
+        raise RuntimeError("morig_b200: a CUDA device is required (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def meanshift_cluster(pts_in, bandwidth, weights=None, max_iter=20, return_iters=False):
     """`meanshift_cluster(pts_in, bandwidth, weights=None, max_iter=20)` — utils/cluster_utils.py:14.
     pts_in [N,3] and weights [N] / [N,1] as numpy arrays (returns numpy, like the reference) or CUDA tensors
     (returns a CUDA float64 tensor).  There is no CPU path: a CUDA device is required."""
     lib = _lib.load()
     as_numpy = isinstance(pts_in, np.ndarray)
-    dev = torch.device("cuda", torch.cuda.current_device()) if as_numpy else pts_in.device
+    dev = _require_cuda_device() if as_numpy else pts_in.device
     if dev.type != "cuda":
         raise RuntimeError("morig_b200.cluster_utils.meanshift_cluster: CUDA tensors (or numpy arrays) expected")
     pts = (torch.from_numpy(np.ascontiguousarray(pts_in, dtype=np.float64)) if as_numpy else pts_in).to(dev, torch.float64)

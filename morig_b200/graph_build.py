@@ -16,6 +16,13 @@ import torch
 from . import _lib
 
 
+def _require_cuda_device() -> torch.device:
+    """numpy inputs are processed on the current CUDA device; there is no CPU path"""
+    if not torch.cuda.is_available():
+        raise RuntimeError("morig_b200: a CUDA device is required (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def _to_dev(x, dev):
     if isinstance(x, np.ndarray):
         x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
@@ -24,7 +31,7 @@ def _to_dev(x, dev):
 
 def _device_of(x):
     if isinstance(x, np.ndarray):
-        return torch.device("cuda", torch.cuda.current_device()), True
+        return _require_cuda_device(), True
     if not x.is_cuda:
         raise RuntimeError("morig_b200.graph_build: CUDA tensors (or numpy arrays) expected")
     return x.device, False
@@ -74,7 +81,7 @@ def tpl_edges(obj_v, obj_f):
     neighbours in python-set iteration order, the edge set is the same.  `obj_v` is only used for its type."""
     lib = _lib.load()
     as_numpy = isinstance(obj_f, np.ndarray)
-    dev = torch.device("cuda", torch.cuda.current_device()) if as_numpy else obj_f.device
+    dev = _require_cuda_device() if as_numpy else obj_f.device
     if dev.type != "cuda":
         raise RuntimeError("morig_b200.graph_build: CUDA tensors (or numpy arrays) expected")
     f = (torch.from_numpy(np.ascontiguousarray(obj_f, dtype=np.int64)) if as_numpy else obj_f).to(dev, torch.int64).contiguous()

@@ -51,3 +51,24 @@ def test_host_pipeline_refuses_cpu_models():
     model = morig_b200.jointnet_motion(**synth.ARCH_KWARGS["jointnet_motion"]).eval()
     with pytest.raises(RuntimeError):
         morig_b200.HostPipeline(model)
+
+
+def test_post_process_and_graph_build_have_no_cpu_path():
+    """numpy-in / numpy-out helpers run on the GPU; without one they raise instead of falling back"""
+    import numpy as np
+    import pytest
+    import torch
+    from morig_b200 import cluster_utils, graph_build
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    pts = np.zeros((4, 3))
+    with pytest.raises(RuntimeError):
+        cluster_utils.meanshift_cluster(pts, 0.05)
+    with pytest.raises(RuntimeError):
+        graph_build.surface_geodesic(pts, pts, pts)
+    with pytest.raises(RuntimeError):
+        graph_build.geo_ball_edges(np.zeros((4, 4)))
+    with pytest.raises(RuntimeError):
+        graph_build.tpl_edges(pts, np.zeros((2, 3), dtype=np.int64))
+    with pytest.raises(RuntimeError):
+        cluster_utils.meanshift_cluster(torch.zeros(4, 3, dtype=torch.float64), 0.05)
