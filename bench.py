@@ -97,7 +97,16 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def cpu_reference_run(steps: int, warmup: int, n_meshes: int = 1):
+def workload_config(world: int, meshes_per_gpu: int) -> dict:
+    """`config` of the bench line -- the same object in both arms (ours and `--impl reference`)"""
+    return {"workload": f"{ARCH} forward, batch={meshes_per_gpu} x {N_VTX}-vertex synthetic meshes per GPU "
+                        "(BASELINE.json configs[1]), graph preparation included every step",
+            "arch": ARCH, "n_vtx": N_VTX, "meshes_per_gpu": meshes_per_gpu,
+            "l2": "256 MiB flush write between timed steps; per-step workspace ~1 GB >> L2",
+            "parallelism": f"dp{world}: whole meshes per rank, no forward collective"}
+
+
+def cpu_reference_run(steps: int, warmup: int, n_meshes: int = 1, n_vtx: int = N_VTX):
     """Reference CPU path (oracle port = op-for-op restatement of models/rignet.py pinned to the unmodified
     reference) on all host threads.  One step = forward of `n_meshes` 4096-vertex meshes."""
     from morig_b200 import synth
@@ -108,7 +117,7 @@ def cpu_reference_run(steps: int, warmup: int, n_meshes: int = 1):
     kw = synth.ARCH_KWARGS[ARCH]
     model = getattr(morig_b200, ARCH)(**kw).eval()
     sd = synth.seeded_state_dict(model, 1)
-    data = synth.make_batch(n_meshes, N_VTX, seed=0)
+    data = synth.make_batch(n_meshes, n_vtx, seed=0)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
@@ -120,7 +129,7 @@ def cpu_reference_run(steps: int, warmup: int, n_meshes: int = 1):
                 times.append(dt)
     total = sum(times)
     return dict(value=n_meshes * len(times) / total, unit=UNIT, cores=cores, kind="port",
-                sample=f"{len(times)} timed forwards of {n_meshes} x {N_VTX}-vertex mesh after {warmup} warm-up, "
+                sample=f"{len(times)} timed forwards of {n_meshes} x {n_vtx}-vertex mesh after {warmup} warm-up, "
                        f"torch {torch.__version__} CPU fp32, {cores} threads",
                 ms_per_step=1e3 * total / len(times))
 
@@ -129,13 +138,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps, args.warmup, n_meshes=1)
+    # one step = the same batch our arm steps at N=1 (4 x 4096 vertices, ~3 s of CPU work): a bounded sample of the
+    # N-GPU workload, which is N such batches
+    r = cpu_reference_run(args.steps, args.warmup, n_meshes=args.meshes_per_gpu)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{ARCH} forward, batch={MESHES_PER_GPU} x {N_VTX}-vertex synthetic meshes per GPU "
-                                   "(BASELINE.json configs[1]); reference arm step = bounded sample of 1 mesh",
-                       "arch": ARCH, "n_vtx": N_VTX, "meshes_per_step": 1},
+            "config": workload_config(args.gpus, args.meshes_per_gpu),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -155,10 +164,7 @@ def run_ours(args):
         # stdout must carry the ONE JSON line only: NCCL prints its version banner (and, with NCCL_DEBUG=INFO in the
         # environment, its whole log) to fd 1 from C, so fd 1 is pointed at stderr for the run and the line goes to
         # the saved descriptor
-        if "MORIG_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["MORIG_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
+        # (NCCL_DEBUG is left as the caller set it: the driver audits the NCCL log for the rank count)
         sys.stdout.flush()
         json_fd = os.dup(1)
         os.dup2(2, 1)
@@ -172,6 +178,7 @@ def run_ours(args):
     model = getattr(morig_b200, ARCH)(**kw).eval()
     model.load_state_dict(synth.seeded_state_dict(model, 1))
     model = model.to(dev)
+    MESHES_PER_GPU = args.meshes_per_gpu
     host = synth.make_batch(MESHES_PER_GPU, N_VTX, seed=rank * MESHES_PER_GPU).pin_memory()
     resident = host.to(dev)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -304,14 +311,19 @@ def run_ours(args):
                         "note": "86 FLOP/B and 1.39 M random 128-byte gathers per launch: bound by L2 gather latency and the "
                                 "warp-level MMAs, not by HBM"}
         cpu = cpu_reference_run(steps=3, warmup=1, n_meshes=1) if world == 1 else None
+        # BASELINE.json configs[0] (1 x 1024 vertices, the reference's own CPU-runnable case): both sides, informational
+        cfg0 = None
+        if world == 1:
+            small = synth.make_batch(1, 1024, seed=0).to(dev)
+            ms0 = timed(lambda: model(small, small.pred_flow), args.steps, max(args.warmup, 3))
+            c0 = cpu_reference_run(steps=5, warmup=1, n_meshes=1, n_vtx=1024)
+            cfg0 = {"workload": "jointnet_motion forward, 1 x 1024-vertex mesh (BASELINE.json configs[0])",
+                    "gpu_ms_per_forward": ms0 / args.steps, "gpu_meshes_per_s": args.steps / (ms0 / 1e3),
+                    "cpu_ms_per_forward": c0["ms_per_step"], "cpu_meshes_per_s": c0["value"], "cpu_cores": c0["cores"]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{ARCH} forward, batch={MESHES_PER_GPU} x {N_VTX}-vertex synthetic meshes "
-                                       "per GPU (BASELINE.json configs[1]), graph preparation included every step",
-                           "arch": ARCH, "n_vtx": N_VTX, "meshes_per_gpu": MESHES_PER_GPU,
-                           "l2": "256 MiB flush write between timed steps; per-step workspace ~1 GB >> L2",
-                           "parallelism": f"dp{world}: whole meshes per rank, no forward collective"},
+                "config": workload_config(world, MESHES_PER_GPU),
                 "clocks": clocks,
                 "e2e": {"value": meshes / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
@@ -331,6 +343,8 @@ def run_ours(args):
                 "kernels": kstats}
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if cfg0 is not None:
+            line["config0_1x1024"] = cfg0
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
@@ -343,6 +357,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--meshes-per-gpu", type=int, default=MESHES_PER_GPU,
+                    help="meshes in one step's batch per GPU (4 = BASELINE.json configs[1]; 8 at --gpus 8 = configs[4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -111,8 +111,10 @@ def check(code: int, what: str) -> None:
         raise RuntimeError(f"{what} failed (code {code}): {msg}")
 
 
-def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def stream_ptr(device=None) -> int:
+    """raw handle of torch's current stream on `device` (default: the current device -- every top-level forward of
+    this package runs under `torch.cuda.device(<device of its inputs>)`, see FusedModule.__call__)"""
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def ptr(t) -> int:

@@ -25,20 +25,45 @@ def MLP(channels: List[int], batch_norm: bool = True) -> nn.Sequential:
     return nn.Sequential(*blocks)
 
 
+def _check_rows(who: str, n: int, **tensors) -> None:
+    for name, t in tensors.items():
+        if t.dim() < 1 or t.shape[0] != n:
+            raise ValueError(f"{who}: `{name}` must have {n} rows, got shape {tuple(t.shape)}")
+
+
+def _check_width(who: str, **pairs) -> None:
+    """the reference raises a shape error from `Linear`; raw kernels would read out of bounds instead"""
+    for name, (t, want) in pairs.items():
+        if t.dim() != 2 or t.shape[1] != want:
+            raise ValueError(f"{who}: `{name}` must be [N, {want}], got shape {tuple(t.shape)}")
+
+
 # bumped whenever any module's parameters may have changed; captured CUDA graphs remember the epoch they
 # were built in and are rebuilt when it moved (they bake packed-weight pointers)
 WEIGHTS_EPOCH = [0]
 
 
+def _cuda_device_of(args):
+    """device of the first CUDA tensor among a forward's arguments (tensors, or batch objects with `.pos`)"""
+    for a in args:
+        t = a if torch.is_tensor(a) else getattr(a, "pos", None)
+        if torch.is_tensor(t) and t.is_cuda:
+            return t.device
+    return None
+
+
 class FusedModule(nn.Module):
     """Common behaviour of the drop-in modules: lazily packed device weights that are dropped whenever
-    the parameters may have changed (`load_state_dict`, `.to()`, `.train()`), a reusable workspace and
-    loud failure outside the supported regime."""
+    the parameters may have changed (`load_state_dict`, `.to()`, `.train()`, or any tracked in-place edit of a
+    parameter / buffer: optimizer steps, `nn.init`, `load_state_dict` on a plain child container), a reusable
+    workspace and loud failure outside the supported regime."""
 
     def __init__(self):
         super().__init__()
         self._packed = None
         self._packed_key = None
+        self._packed_fp = None
+        self._fp_tensors = None
         self._ws = engine.Workspace()
         self._graphs = engine.GraphCache()
         self._batches = engine.BatchCache()
@@ -54,6 +79,26 @@ class FusedModule(nn.Module):
             if isinstance(m, FusedModule):
                 m._packed = None
                 m._packed_key = None
+                m._packed_fp = None
+                m._fp_tensors = None
+
+    def __call__(self, *args, **kwargs):
+        # raw kernel launches go to the current stream of the CURRENT device: make that the inputs' device, as
+        # PyTorch ops do implicitly (a model on cuda:1 must work while cuda:0 is current)
+        dev = _cuda_device_of(args)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return super().__call__(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return super().__call__(*args, **kwargs)
+
+    def weights_fingerprint(self):
+        """(storage address, in-place version) of every parameter and buffer below this module: changes with
+        optimizer steps, `nn.init.*_`, `load_state_dict` (also on children), `.to()`.  Untracked writes through
+        `.data` are the one thing it cannot see -- call `invalidate_packed()` after those."""
+        ts = self._fp_tensors
+        if ts is None:
+            ts = self._fp_tensors = list(self.state_dict(keep_vars=True).values())
+        return tuple((t.data_ptr(), t._version) for t in ts)
 
     def _apply(self, fn, *args, **kwargs):
         self.invalidate_packed()
@@ -79,10 +124,14 @@ class FusedModule(nn.Module):
                 raise RuntimeError(f"morig_b200 runs on CUDA tensors only (got {t.device}); there is no CPU path")
 
     def _packed_for(self, key, builder):
-        if self._packed is None or self._packed_key != key:
+        fp = self.weights_fingerprint()
+        if self._packed is None or self._packed_key != key or self._packed_fp != fp:
+            if self._packed is not None and self._packed_fp != fp:
+                WEIGHTS_EPOCH[0] += 1          # captured CUDA graphs bake pointers of the old pack
             with torch.no_grad():
                 self._packed = builder()
             self._packed_key = key
+            self._packed_fp = fp
         return self._packed
 
 
@@ -115,6 +164,8 @@ class EdgeConvMotion(FusedModule):
             return pq_x, br_x, pq_p, br_p
 
         pq_x, br_x, pq_p, br_p = self._packed_for("edge", build)
+        _check_rows("EdgeConvMotion", n, pos=pos)
+        _check_width("EdgeConvMotion", x=(x, pq_x.K), pos=(pos, pq_p.K))
         g = self._graphs.get(edge_index, n)
         H, Dp = br_x.H, br_p.H
         out = torch.empty(n, H + Dp, device=dev, dtype=torch.float32)
@@ -155,6 +206,8 @@ class GCUMotion(FusedModule):
             return gp, packing.fuse_pos_pq(parts)
 
         gp, pq_pos = self._packed_for("gcu", build)
+        _check_rows("GCUMotion", n, pos=pos)
+        _check_width("GCUMotion", x=(x, gp.pq_x.K), pos=(pos, pq_pos.K))
         gt = self._graphs.get(tpl_edge_index, n)
         gg = self._graphs.get(geo_edge_index, n)
         pqpos = self._ws.get("pqpos", (n, pq_pos.N), dev)
@@ -187,6 +240,7 @@ class EdgeConv(FusedModule):
 
     def run(self, x: torch.Tensor, g: engine.Graph, out: torch.Tensor, ldo: int, out_off: int) -> None:
         pq, br = self._packed_for("edge", self._pack)
+        _check_width("EdgeConv", x=(x, pq.K))
         n = x.shape[0]
         buf = self._ws.get("pq", (n, pq.N), x.device)
         engine.dense(pq, x, 0, x.shape[1], n, C=buf, ldc=pq.N)
@@ -196,7 +250,8 @@ class EdgeConv(FusedModule):
         self._guard(x, edge_index)
         x = _lib.require_cuda(x.unsqueeze(-1) if x.dim() == 1 else x, "x")
         n = x.shape[0]
-        _, br = self._packed_for("edge", self._pack)
+        pq, br = self._packed_for("edge", self._pack)
+        _check_width("EdgeConv", x=(x, pq.K))
         out = torch.empty(n, br.H, device=x.device, dtype=torch.float32)
         with engine.forward_scope(self._ws, x.device):
             engine.fill(out, engine.NEG_INF)

@@ -115,11 +115,17 @@ class forward_scope:
 
     def __init__(self, ws: "Workspace", device):
         self.ws, self.device, self.outer = ws, device, False
+        self.guard = None
 
     def __enter__(self):
         global _tracker
         if _tracker is None:
             self.outer = True
+            # every launch helper enqueues on torch's current stream of the CURRENT device: make that the device
+            # the tensors live on (PyTorch ops guard implicitly; raw launches have to do it themselves)
+            if torch.device(self.device).type == "cuda":
+                self.guard = torch.cuda.device(self.device)
+                self.guard.__enter__()
             _tracker = self.ws.tracker
             _tracker.begin(self.device)
         return self
@@ -128,6 +134,9 @@ class forward_scope:
         global _tracker
         if self.outer:
             _tracker = None
+            if self.guard is not None:
+                self.guard.__exit__(*exc)
+                self.guard = None
         return False
 
 
@@ -173,7 +182,7 @@ class Graph:
     n: int
     e_max: int
     ready: Optional[torch.cuda.Event] = None     # set while the CSR is still being built on a side stream
-    scratch: Optional[torch.Tensor] = None       # keeps the builder's workspace alive until then
+    scratch: Optional[tuple] = None              # keeps the builder's workspace (and edge-list copy) alive until then
 
     def join(self) -> None:
         """make the current stream wait for a CSR that is being built on a side stream (no-op afterwards)"""
@@ -219,7 +228,7 @@ def graph_prep(edge_index: torch.Tensor, n: int, overlap: bool = False) -> Graph
                                         ws.data_ptr(), ws_bytes, side.cuda_stream), "morig_graph_prep")
         g.ready = torch.cuda.Event()
         g.ready.record(side)
-        g.scratch = ws
+        g.scratch = (ws, ei)     # `ei` may be a contiguous temporary: it must outlive the side-stream kernels too
         return g
     tok = _begin(f"graph_prep E={e} N={n}", 5, 0.0, 16.0 * e + 8.0 * (e + n)) if (_counter is not None or _timer is not None) else None
     _lib.check(lib.morig_graph_prep(ei.data_ptr(), e, n, rowptr.data_ptr(), col.data_ptr(), tgt.data_ptr(),
@@ -262,7 +271,12 @@ class BatchCache:
             return ent[2]
         b = _lib.require_cuda(batch, "batch", torch.int64)
         ng = getattr(data, "num_graphs", None) if data is not None else None
+        if ng is None and data is not None and torch.is_tensor(getattr(data, "ptr", None)):
+            ng = data.ptr.numel() - 1          # PyG `Batch.ptr` [B + 1]
         if ng is None:
+            # plain `Data` with a hand-made batch vector (evaluate/joint2rig.py:261-263) and no `num_graphs`: the one
+            # place that has to read 8 bytes back, once per batch tensor -- exactly what the reference's
+            # `scatter_max(x_4, batch)` does for dim_size (models/rignet.py:63).  Set `data.num_graphs` to avoid it.
             ng = int(b[-1].item()) + 1         # `batch` is sorted (PyG collation): last id = B - 1
         info = BatchInfo(batch32=b.to(torch.int32), n_graphs=int(ng))
         self._ent = (batch, batch._version, info)
@@ -386,6 +400,9 @@ def dense(layer: DenseLayer, A: torch.Tensor, a_off: int, lda: int, M: int, *, K
           pool: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None,
           binfo: Optional[BatchInfo] = None, n_vtx: int = 0) -> None:
     lib = _lib.load()
+    kk = layer.K if K is None else K
+    if kk > layer.W.shape[0] or lda < kk:
+        raise ValueError(f"dense: K={kk} exceeds the packed weight rows ({layer.W.shape[0]}) or the row stride ({lda})")
     d = _lib.DenseDesc()
     d.A = A.data_ptr() + 4 * a_off
     d.lda = lda

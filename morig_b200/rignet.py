@@ -74,6 +74,13 @@ class GCNRig(FusedModule):
         feature = feature.unsqueeze(-1) if feature.dim() == 1 else feature
         feature = _lib.require_cuda(feature, "feature")
         n = pos.shape[0]
+        pk = self._packed_for("rig", self.pack)
+        if pos.dim() != 2 or pos.shape[1] != 3:
+            raise ValueError(f"GCNRig: `pos` must be [N, 3], got {tuple(pos.shape)}")
+        if feature.dim() != 2 or feature.shape != (n, pk.F):
+            raise ValueError(f"GCNRig: `feature` must be [{n}, {pk.F}], got {tuple(feature.shape)}")
+        if batch.dim() != 1 or batch.shape[0] != n:
+            raise ValueError(f"GCNRig: `batch` must be [{n}], got {tuple(batch.shape)}")
         gt = self._graphs.get(tpl_edge_index, n)
         gg = self._graphs.get(geo_edge_index, n)
         binfo = self._batches.get(batch)
@@ -89,7 +96,6 @@ class _GraphReplay:
 
     def __init__(self, model, data, input_flow, num_graphs):
         import types
-        self.epoch = WEIGHTS_EPOCH[0]
         self.static = types.SimpleNamespace(num_graphs=num_graphs)
         for f in self._FIELDS:
             v = getattr(data, f, None)
@@ -105,9 +111,13 @@ class _GraphReplay:
             model._forward_impl(self.static, self.flow, self.ws, engine.GraphCache(), engine.BatchCache())
         cur.wait_stream(side)
         torch.cuda.synchronize()
+        self.epoch = WEIGHTS_EPOCH[0]              # after the warm-up (which may have re-packed the weights)
+        self.fingerprint = model.weights_fingerprint()
         self.graph = torch.cuda.CUDAGraph()
         self.caches = (engine.GraphCache(), engine.BatchCache())      # fresh: graph prep is captured too
-        with torch.cuda.graph(self.graph), torch.no_grad():
+        # thread_local: CUDA calls of OTHER threads (a DataLoader's pin-memory thread, another model) must not
+        # invalidate the capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"), torch.no_grad():
             self.outs = model._forward_impl(self.static, self.flow, self.ws, *self.caches)
 
     def run(self, data, input_flow):
@@ -160,14 +170,24 @@ class _MotionNet(FusedModule):
         seen = self.__dict__.setdefault("_seen", {})
         key = self._shape_key(data, input_flow)
         ent = replays.get(key)
-        if ent is not None and ent.epoch != WEIGHTS_EPOCH[0]:
+        if ent is not None and (ent.epoch != WEIGHTS_EPOCH[0] or ent.fingerprint != self.weights_fingerprint()):
             replays.pop(key)
             ent = None
         if ent is None:
             seen[key] = seen.get(key, 0) + 1
             if seen[key] < 2:                        # first sight of this shape: plain launches
                 return self._forward_impl(data, input_flow, self._ws, self._graphs, self._batches)
-            ent = _GraphReplay(self, data, input_flow, key[5])
+            try:
+                ent = _GraphReplay(self, data, input_flow, key[5])
+            except RuntimeError as exc:              # capture failed: plain launches for this shape from now on
+                import warnings
+                warnings.warn(f"morig_b200: CUDA-graph capture failed ({exc}); using plain launches for this batch shape")
+                try:
+                    torch.cuda.synchronize()
+                except RuntimeError:
+                    pass
+                seen[key] = -(1 << 60)
+                return self._forward_impl(data, input_flow, self._ws, self._graphs, self._batches)
             while len(replays) >= self._GRAPH_SLOTS:
                 replays.pop(next(iter(replays)))
             replays[key] = ent

@@ -617,3 +617,128 @@ def test_tpl_edges_bit_exact(nu, nv):
     got = graph_build.tpl_edges(verts, faces)
     ref = geodesic_port.sorted_rows(geodesic_port.tpl_edges(verts, faces))
     assert got.dtype == np.int64 and np.array_equal(got, ref)
+
+
+# ---- parity against the oracle at the sizes BASELINE.json is quoted on ----------------------------------------------------
+@pytest.mark.parametrize("arch,b,n", [("jointnet_motion", 4, 4096),      # configs[1]
+                                      ("masknet_motion", 8, 4096),       # configs[2]
+                                      ("skinnet_motion", 4, 8192)])      # configs[3]
+def test_models_match_oracle_at_baseline_configs(arch, b, n):
+    """CUDA path vs the CPU oracle (oracle/rignet_port.py) on the full BASELINE.json batches: the fp16-split operand
+    scales depend on data-dependent max|value|, so parity is checked at the quoted sizes, not only on small meshes"""
+    kw = synth.ARCH_KWARGS[arch]
+    data = synth.make_batch(b, n, seed=0, with_skin=(arch == "skinnet_motion"))
+    model = helpers.build_model(arch, kw, 1, DEV)
+    expect = helpers.oracle_forward(arch, kw, model, data, data.pred_flow)
+    with torch.no_grad():
+        out = model(data.to(DEV), data.pred_flow.to(DEV))
+    for o, e, k in zip(out, expect, helpers.OUT_KEYS):
+        assert o.shape == e.shape
+        assert helpers.max_abs_diff(o, e) < helpers.TOL, k
+
+
+@pytest.mark.parametrize("use_Dg,use_Lf", [(True, False), (False, True), (True, True)])
+def test_skinnet_column_selections(use_Dg, use_Lf):
+    """the three other branches of the skin_input column selection (models/rignet.py:159-171)"""
+    kw = dict(synth.ARCH_KWARGS["skinnet_motion"], use_Dg=use_Dg, use_Lf=use_Lf)
+    data = synth.make_batch(2, 512, seed=60, with_skin=True)
+    model = helpers.build_model("skinnet_motion", kw, 23, DEV)
+    expect = helpers.oracle_forward("skinnet_motion", kw, model, data, data.pred_flow)
+    with torch.no_grad():
+        out = model(data.to(DEV), data.pred_flow.to(DEV))
+    for o, e, k in zip(out, expect, helpers.OUT_KEYS):
+        assert helpers.max_abs_diff(o, e) < helpers.TOL, k
+
+
+def _outlier_state_dict(model, seed):
+    """a 'trained-like' weight set: a few BatchNorm scales x1000 (edge MLPs and vertex MLPs), one hidden channel of a
+    wide layer x1e4 and one first-layer row x100 -- channels whose magnitude is far from the rest of their tensor"""
+    sd = synth.seeded_state_dict(model, seed)
+    for key, idx, f in (("motionNet.gcu_2.edge_conv_geo.nn_x.0.2.weight", 5, 1e3),
+                        ("motionNet.gcu_3.edge_conv_tpl.nn_x.1.2.weight", 17, 1e3),
+                        ("motionNet.gcu_1.mlp.0.2.weight", 3, 1e3),
+                        ("motionNet.mlp_transform.0.0.0.weight", 7, 1e4),
+                        ("motionNet.gcu_1.edge_conv_tpl.nn_pos.0.0.weight", 2, 1e2)):
+        if key in sd:
+            sd[key][idx] = sd[key][idx] * f
+    for head in ("jointnet", "masknet", "skinNet"):
+        for key, idx, f in ((f"{head}.gcu_3.edge_conv_geo.nn_x.0.2.weight", 9, 1e3), (f"{head}.mlp_glb.0.2.weight", 100, 1e3),
+                            (f"{head}.gcu2.edge_conv_tpl.nn_x.1.2.weight", 11, 1e3), (f"{head}.gcu3.mlp.0.0.weight", 4, 1e4)):
+            if key in sd:
+                sd[key][idx] = sd[key][idx] * f
+    return sd
+
+
+@pytest.mark.parametrize("kind", ["f16", "tf32"])
+@pytest.mark.parametrize("arch", ["jointnet_motion", "skinnet_motion"])
+def test_outlier_channels_through_whole_networks(arch, kind, monkeypatch):
+    """dynamic range of the split-operand arithmetic: one max|value| per buffer scales the fp16 operands, so a
+    checkpoint with outlier channels (BN scale x1e3, one hidden channel x1e4) must still meet the tolerance --
+    1e-4 absolute on the unit-norm embeddings, 1e-4 of the output range on the (now large) predictions"""
+    monkeypatch.setenv("MORIG_TC_KIND", kind)
+    kw = synth.ARCH_KWARGS[arch]
+    data = synth.make_batch(2, 1024, seed=70, with_skin=(arch == "skinnet_motion"))
+    model = getattr(__import__("morig_b200"), arch)(**kw).eval()
+    model.load_state_dict(_outlier_state_dict(model, 29))
+    model = model.to(DEV)
+    expect = helpers.oracle_forward(arch, kw, model, data, data.pred_flow)
+    with torch.no_grad():
+        out = model(data.to(DEV), data.pred_flow.to(DEV))
+    for o, e, k in zip(out, expect, helpers.OUT_KEYS):
+        assert torch.isfinite(o).all(), k
+        assert helpers.max_abs_diff(o, e) < helpers.TOL * max(1.0, float(e.abs().max())), k
+
+
+# ---- integer-exact known-answer test (SURVEY.md 8(c) item 3) ---------------------------------------------------------------
+def _integer_state_dict(model, seed):
+    """small-integer weights (sparse, in {-1, 0, 1}), integer biases, BatchNorm = exact integer affine
+    (running_var = 1 - eps so that 1/sqrt(var + eps) rounds to exactly 1, gamma = +-1, integer
+    beta / running_mean): every fp32 sum of the forward is then an exact integer whatever the summation order"""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for key, ref in sorted(model.state_dict().items()):
+        leaf = key.rsplit(".", 1)[-1]
+        shape = tuple(ref.shape)
+        if leaf == "num_batches_tracked":
+            v = torch.zeros(shape, dtype=ref.dtype)
+        elif leaf == "running_var":
+            v = torch.full(shape, 1.0 - 1e-5)
+        elif leaf == "running_mean":
+            v = torch.randint(-1, 2, shape, generator=g).float()
+        elif ref.dim() == 2:
+            dense_ = torch.randint(-1, 2, shape, generator=g).float()
+            keep = torch.rand(shape, generator=g) < min(1.0, 8.0 / shape[1])      # ~8 non-zeros per output row
+            v = dense_ * keep
+        elif leaf == "weight":                                                     # BatchNorm gamma
+            v = torch.ones(shape)
+            v = torch.where(torch.rand(shape, generator=g) < 0.2, -v, v)
+        else:
+            v = torch.randint(-1, 2, shape, generator=g).float()
+        sd[key] = v.to(ref.dtype)
+    return sd
+
+
+@pytest.mark.parametrize("kind", ["f16", "tf32"])
+@pytest.mark.parametrize("F,O", [(3, 32), (64, 3)])
+def test_integer_exact_kat_gcn_rig(F, O, kind, monkeypatch):
+    """GCNRig (3 GCUMotion + pooled global feature + head, models/rignet.py:50-67) on integer data: the CUDA path
+    (factorised first Linear, folded BatchNorm, split-operand tensor-core GEMMs, segmented / pooled max) must
+    reproduce the oracle BIT FOR BIT -- any dropped low-order term, mis-scaled operand or wrong segment shows"""
+    import morig_b200
+    from oracle import rignet_port
+    monkeypatch.setenv("MORIG_TC_KIND", kind)
+    data = synth.make_batch(2, 400, seed=5)
+    n = data.pos.shape[0]
+    g = torch.Generator().manual_seed(F)
+    pos = torch.randint(-2, 3, (n, 3), generator=g).float()
+    feat = torch.randint(-2, 3, (n, F), generator=g).float()
+    rig = morig_b200.GCNRig(F, O).eval()
+    rig.load_state_dict(_integer_state_dict(rig, 31 + F))
+    sd = {"r." + k: v for k, v in rig.state_dict().items()}
+    with torch.no_grad():
+        want = rignet_port.gcn_rig(sd, "r", pos, feat, data.tpl_edge_index, data.geo_edge_index, data.batch)
+    assert torch.equal(want, want.round()) and float(want.abs().max()) < 2 ** 21     # the KAT is integer-valued
+    assert float(want.abs().max()) > 0
+    got = rig.to(DEV)(pos.to(DEV), feat.to(DEV), data.tpl_edge_index.to(DEV), data.geo_edge_index.to(DEV),
+                      data.batch.to(DEV))
+    assert torch.equal(got.cpu(), want)

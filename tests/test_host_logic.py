@@ -261,3 +261,55 @@ def test_c_abi_argument_validation_without_gpu():
     e = _lib.EdgeDesc()
     assert lib.morig_edgeconv_fwd(ctypes.byref(e), None) == 1001
     assert lib.morig_graph_prep(None, 10, 0, None, None, None, None, 0, None) == 1001
+
+
+def test_packed_weights_follow_in_place_parameter_edits(emulated):
+    """stale-pack protection (weights_fingerprint): optimizer-style in-place updates, nn.init and load_state_dict on a
+    plain nn.Sequential child / nested module must all be seen by the next forward"""
+    from oracle import rignet_port
+    import morig_b200
+    data = synth.make_batch(1, 100, seed=5)
+    x = torch.randn(100, 64, generator=torch.Generator().manual_seed(0))
+    rig = morig_b200.GCNRig(64, 3).eval()
+    rig.load_state_dict(synth.seeded_state_dict(rig, 2))
+
+    def check():
+        sd = {"r." + k: v for k, v in rig.state_dict().items()}
+        want = rignet_port.gcn_rig(sd, "r", data.pos, x, data.tpl_edge_index, data.geo_edge_index, data.batch)
+        got = rig(data.pos, x, data.tpl_edge_index, data.geo_edge_index, data.batch)
+        assert helpers.max_abs_diff(got, want) < 5e-6 * max(1.0, float(want.abs().max()))
+        return got
+
+    a = check()
+    with torch.no_grad():
+        for p in rig.parameters():
+            p.add_(0.01 * torch.ones_like(p))                                  # what an optimizer step does
+    b = check()
+    assert not torch.equal(a, b)
+    torch.nn.init.constant_(rig.mlp_transform[1].bias, 0.5)
+    check()
+    child = rig.mlp_glb                                                         # plain nn.Sequential, no hooks of ours
+    child.load_state_dict({k: v * 1.5 for k, v in child.state_dict().items()})
+    check()
+    nested = rig.gcu_2                                                          # the pack lives on the parent GCNRig
+    nested.load_state_dict({k: (v * 0.5 if v.is_floating_point() else v) for k, v in nested.state_dict().items()})
+    check()
+
+
+def test_standalone_forwards_validate_shapes(emulated):
+    import morig_b200
+    data = synth.make_batch(1, 64, seed=1)
+    rig = morig_b200.GCNRig(64, 3).eval()
+    good = torch.zeros(64, 64)
+    with pytest.raises(ValueError):
+        rig(data.pos, torch.zeros(64, 32), data.tpl_edge_index, data.geo_edge_index, data.batch)
+    with pytest.raises(ValueError):
+        rig(data.pos[:, :2].contiguous(), good, data.tpl_edge_index, data.geo_edge_index, data.batch)
+    with pytest.raises(ValueError):
+        rig(data.pos, good, data.tpl_edge_index, data.geo_edge_index, data.batch[:10])
+    gcu = morig_b200.GCUMotion(64, 256).eval()
+    with pytest.raises(ValueError):
+        gcu(data.pos, torch.zeros(64, 60), data.tpl_edge_index, data.geo_edge_index)
+    ec = morig_b200.EdgeConvMotion(morig_b200.MLP([6, 32, 32]), morig_b200.MLP([6, 16, 16])).eval()
+    with pytest.raises(ValueError):
+        ec(torch.zeros(64, 4), torch.zeros(64, 3), data.tpl_edge_index)

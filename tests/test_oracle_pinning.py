@@ -251,3 +251,13 @@ def test_tpl_edges_port_is_identical_to_unmodified_reference():
     co = gg.load_reference()
     verts, faces = _grid_faces(7, 9, 0)
     assert np.array_equal(geodesic_port.tpl_edges(verts, faces), co.get_tpl_edges(verts, faces))   # incl. set order
+
+
+def test_synth_generator_is_pinned_by_input_carrying_fixtures():
+    """output-only fixtures (jointnet_b1_n4096_outputs) rely on `synth.make_batch` being deterministic: the fixtures
+    that do carry their inputs must be reproduced bit for bit by the generator"""
+    z = np.load(os.path.join(helpers.GOLDEN_DIR, "jointnet_b1_n1024.npz"))
+    data = synth.make_batch(int(z["graphs"]), int(z["n_vtx"]), seed=int(z["data_seed"]))
+    assert np.array_equal(data.pos.numpy(), z["pos"]) and np.array_equal(data.pred_flow.numpy(), z["pred_flow"])
+    assert np.array_equal(data.tpl_edge_index.numpy(), z["tpl_edge_index"])
+    assert np.array_equal(data.geo_edge_index.numpy(), z["geo_edge_index"])
