@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MORIG_ABI_VERSION 3
+#define MORIG_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define MORIG_API __attribute__((visibility("default")))
@@ -221,6 +221,91 @@ MORIG_API int    morig_geo_ball_edges(const double *geodesic, int32_t V, double 
 MORIG_API size_t morig_tpl_edges_workspace(int64_t F);
 MORIG_API int    morig_tpl_edges(const int64_t *faces, int64_t F, int64_t *edges, int64_t *count, void *ws,
                                  size_t ws_bytes, void *stream);
+
+/* =============================================================================================
+ * Training path.  The reference trains these networks with torch autograd
+ * (training/train_rig.py:136-195, training/train_skin.py:139-183): train-mode BatchNorm1d inside every MLP block
+ * (models/basic_modules.py:33), scatter-max whose gradient goes to the FIRST maximal edge (torch_scatter), cuBLAS
+ * GEMMs for the Linear gradients.  The entry points below are what the autograd functions of
+ * morig_b200/autograd_ops.py bind; forward GEMMs and the input-gradient GEMMs (dX = dY W) go through
+ * morig_dense_fwd.  fp32 data, fp64 accumulation for every reduction over rows, fixed summation order except the
+ * scatter-add of morig_edge_gather_relu_bwd's dQ (fp32 atomics).  Matrices are row-major with explicit row strides.
+ * ============================================================================================= */
+
+/* dst [cols, ldd] = src [rows, cols]^T, columns rows..ldd-1 zeroed: a Linear weight [out, in] -> the packed [K, ldw]
+ * operand of morig_dense_fwd (weights change every optimisation step) */
+MORIG_API int morig_transpose_pad_f32(const float *src, int32_t rows, int32_t cols, int32_t lds, float *dst, int32_t ldd,
+                                      void *stream);
+
+/* Linear weight / bias gradient:  dW [N, K] (+)= dY^T (X * x_scale + x_shift),  dbias [N] (+)= column sums of dY
+ * (x_scale / x_shift [K] optional; dbias optional; accumulate != 0 adds to the existing contents).
+ * ws: morig_wgrad_workspace(M, N, K) bytes. */
+MORIG_API size_t morig_wgrad_workspace(int32_t M, int32_t N, int32_t K);
+MORIG_API int    morig_wgrad_f32(const float *dY, int32_t lddy, const float *X, int32_t ldx, int32_t M, int32_t N, int32_t K,
+                                 const float *x_scale, const float *x_shift, float *dW, int32_t lddw, float *dbias,
+                                 int32_t accumulate, void *ws, size_t ws_bytes, void *stream);
+
+/* train-mode BatchNorm1d over the R rows of x [R, C] (torch semantics, models/basic_modules.py:33): batch mean and
+ * biased variance normalise, running_mean / running_var (optional) move by `momentum` towards the batch mean / unbiased
+ * variance.  Writes mean, invstd, scale = gamma * invstd, shift = beta - mean * scale [C] and, if y != NULL,
+ * y = x * scale + shift.  ws: morig_colstats_workspace(R, C) bytes. */
+MORIG_API size_t morig_colstats_workspace(int32_t R, int32_t C);
+MORIG_API int    morig_bn_train_fwd(const float *x, int32_t ldx, int32_t R, int32_t C, const float *gamma, const float *beta,
+                                    float eps, float momentum, float *running_mean, float *running_var, float *mean,
+                                    float *invstd, float *scale, float *shift, float *y, int32_t ldy, void *ws,
+                                    size_t ws_bytes, void *stream);
+
+/* backward of [ReLU ->] BatchNorm(train) given dy and the saved BatchNorm input x (= ReLU output):
+ *   dgamma = sum dy * xhat, dbeta = sum dy, dz = [x > 0 or !relu] * gamma * invstd * (dy - mean(dy) - xhat * mean(dy * xhat))
+ * coef: scratch [3 C].  dz may alias dy. */
+MORIG_API int    morig_bn_relu_bwd(const float *dy, int32_t lddy, const float *x, int32_t ldx, int32_t R, int32_t C,
+                                   const float *gamma, const float *mean, const float *invstd, int32_t relu, float *dz,
+                                   int32_t lddz, float *dgamma, float *dbeta, float *coef, void *ws, size_t ws_bytes,
+                                   void *stream);
+/* dz = [y > 0] * dy */
+MORIG_API int    morig_relu_bwd(const float *dy, int32_t lddy, const float *y, int32_t ldy, int32_t R, int32_t C, float *dz,
+                                int32_t lddz, void *stream);
+
+/* first edge layer after factorisation, materialised for training: h [E, C] = relu(P[tgt[e]] + Q[col[e]]) over the E
+ * valid CSR slots (models/basic_modules.py:193-194); backward: dP[v] = sum over v's in-edges, dQ[u] = sum over u's
+ * out-edges of [h > 0] * dh (both overwritten) */
+MORIG_API int    morig_edge_gather_relu(const float *P, int32_t ldp, const float *Q, int32_t ldq, const int32_t *tgt,
+                                        const int32_t *col, int32_t E, int32_t C, float *h, int32_t ldh, void *stream);
+MORIG_API int    morig_edge_gather_relu_bwd(const float *dh, int32_t lddh, const float *h, int32_t ldh, const int32_t *rowptr,
+                                            const int32_t *col, int32_t N, int32_t E, int32_t C, float *dP, int32_t ldp,
+                                            float *dQ, int32_t ldq, void *stream);
+
+/* segmented max over contiguous row segments ptr[s]..ptr[s+1] of y [R, C] with argmax = the FIRST maximal row
+ * (torch_scatter.scatter_max; PyG aggr='max', models/basic_modules.py:180-181; models/rignet.py:63,176); empty
+ * segment -> 0 / arg -1.  Backward: dy [R, C] overwritten with zeros and dy[arg[s, c], c] = dout[s, c]. */
+MORIG_API int    morig_segmax_fwd(const float *y, int32_t ldy, const int32_t *ptr, int32_t S, int32_t C, float *out, int32_t ldo,
+                                  int32_t *arg, int32_t lda, void *stream);
+MORIG_API int    morig_segmax_bwd(const float *dout, int32_t lddo, const int32_t *arg, int32_t lda, int32_t S, int32_t C,
+                                  float *dy, int32_t lddy, int32_t R, void *stream);
+/* ptr [S + 1] of a sorted key vector (PyG `batch`) */
+MORIG_API int    morig_seg_ptr(const int32_t *keys, int32_t N, int32_t S, int32_t *ptr, void *stream);
+/* out[r] = src[idx[r]] (repeat_interleave of the pooled feature, models/rignet.py:64) and its gradient, the per-segment sum */
+MORIG_API int    morig_row_gather(const float *src, int32_t lds, const int32_t *idx, int32_t R, int32_t C, float *out,
+                                  int32_t ldo, void *stream);
+MORIG_API int    morig_seg_sum(const float *x, int32_t ldx, const int32_t *ptr, int32_t S, int32_t C, float *out, int32_t ldo,
+                               void *stream);
+
+/* F.normalize(dim=1) out of place, and its gradient */
+MORIG_API int    morig_normalize_fwd(const float *x, int32_t ldx, int32_t R, int32_t C, float *y, int32_t ldy, void *stream);
+MORIG_API int    morig_normalize_bwd(const float *x, int32_t ldx, const float *dy, int32_t lddy, int32_t R, int32_t C, float *dx,
+                                     int32_t lddx, void *stream);
+
+/* cls-query attention over the key-frames with explicit projections (TemporalAttn, models/rignet.py:36-45, training
+ * form): q0 / kc / vc [HD] = projected cls token, Kx / Vx [N, T, HD] = projected key-frame tokens, HD = heads * d.
+ * out [N, HD]; att [N, heads, T + 1] saved for the backward (slot 0 = cls).  Backward writes dq0 / dkc / dvc [HD]
+ * (sums over vertices, fixed order) and dKx / dVx.  ws: morig_attn_cls_bwd_workspace(N, HD) bytes. */
+MORIG_API int    morig_attn_cls_fwd(const float *q0, const float *kc, const float *vc, const float *Kx, const float *Vx,
+                                    int32_t N, int32_t T, int32_t HD, int32_t d, float *out, float *att, void *stream);
+MORIG_API size_t morig_attn_cls_bwd_workspace(int32_t N, int32_t HD);
+MORIG_API int    morig_attn_cls_bwd(const float *q0, const float *kc, const float *vc, const float *Kx, const float *Vx,
+                                    const float *att, const float *dout, int32_t N, int32_t T, int32_t HD, int32_t d,
+                                    float *dq0, float *dkc, float *dvc, float *dKx, float *dVx, void *ws, size_t ws_bytes,
+                                    void *stream);
 
 #ifdef __cplusplus
 }

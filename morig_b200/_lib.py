@@ -52,6 +52,8 @@ class EdgeDesc(C.Structure):
     ]
 
 
+_P, _I = C.c_void_p, C.c_int32
+
 _SIGNATURES = {
     "morig_version": (C.c_int, []),
     "morig_last_error": (C.c_char_p, []),
@@ -81,10 +83,31 @@ _SIGNATURES = {
                                     C.c_int32, c_f32p, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
     "morig_fill_f32": (C.c_int, [c_f32p, C.c_int64, C.c_float, C.c_void_p]),
     "morig_absmax_f32": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
+    # ---- training path ----
+    "morig_transpose_pad_f32": (C.c_int, [_P, _I, _I, _I, _P, _I, _P]),
+    "morig_wgrad_workspace": (C.c_size_t, [_I, _I, _I]),
+    "morig_wgrad_f32": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _I, _P, C.c_size_t, _P]),
+    "morig_colstats_workspace": (C.c_size_t, [_I, _I]),
+    "morig_bn_train_fwd": (C.c_int, [_P, _I, _I, _I, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P, _I, _P,
+                                     C.c_size_t, _P]),
+    "morig_bn_relu_bwd": (C.c_int, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P, C.c_size_t, _P]),
+    "morig_relu_bwd": (C.c_int, [_P, _I, _P, _I, _I, _I, _P, _I, _P]),
+    "morig_edge_gather_relu": (C.c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _P, _I, _P]),
+    "morig_edge_gather_relu_bwd": (C.c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _P, _I, _P]),
+    "morig_segmax_fwd": (C.c_int, [_P, _I, _P, _I, _I, _P, _I, _P, _I, _P]),
+    "morig_segmax_bwd": (C.c_int, [_P, _I, _P, _I, _I, _I, _P, _I, _I, _P]),
+    "morig_seg_ptr": (C.c_int, [_P, _I, _I, _P, _P]),
+    "morig_row_gather": (C.c_int, [_P, _I, _P, _I, _I, _P, _I, _P]),
+    "morig_seg_sum": (C.c_int, [_P, _I, _P, _I, _I, _P, _I, _P]),
+    "morig_normalize_fwd": (C.c_int, [_P, _I, _I, _I, _P, _I, _P]),
+    "morig_normalize_bwd": (C.c_int, [_P, _I, _P, _I, _I, _I, _P, _I, _P]),
+    "morig_attn_cls_fwd": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "morig_attn_cls_bwd_workspace": (C.c_size_t, [_I, _I]),
+    "morig_attn_cls_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
-ABI_VERSION = 3
+ABI_VERSION = 4
 _lib = None
 
 

@@ -2,7 +2,8 @@
 same constructor arguments, same `forward` signatures, same `state_dict` keys — but `forward` runs
 the fused sm_100a kernels of `libmorig_b200.so`.  Parameters live in ordinary torch containers purely
 so that reference checkpoints load unchanged (`training/train_rig.py:95`); the containers themselves
-are never executed.  Inference (eval-mode BatchNorm, no autograd) only in this round.
+are never executed.  `model.eval()` runs the fused inference kernels (no autograd); `model.train()` runs the training
+path (train-mode BatchNorm, autograd functions of `autograd_ops.py`, see `train_forward.py`).
 """
 from __future__ import annotations
 
@@ -114,10 +115,6 @@ class FusedModule(nn.Module):
         return {k: v for k, v in self.state_dict(keep_vars=True).items()}
 
     def _guard(self, *tensors: torch.Tensor):
-        if self.training:
-            raise NotImplementedError(
-                "morig_b200 implements the inference forward (model.eval(), as training/train_rig.py:200); "
-                "train-mode BatchNorm / backward are not built yet")
         _lib.load()
         for t in tensors:
             if not t.is_cuda:
@@ -152,6 +149,10 @@ class EdgeConvMotion(FusedModule):
         pos = _lib.require_cuda(pos, "pos")
         x = _lib.require_cuda(x, "x")
         n, dev = x.shape[0], x.device
+        if self.training:                            # train-mode BatchNorm + autograd (train_forward.py)
+            from . import autograd_ops, train_forward
+            g = train_forward.graph_for_training(self._graphs, edge_index, n)
+            return autograd_ops.ConcatCols.apply(*train_forward.edge_conv_motion_parts(self, pos, x, g))
 
         def build():
             sd = self._device_state()
@@ -198,6 +199,10 @@ class GCUMotion(FusedModule):
         pos = _lib.require_cuda(pos, "pos")
         x = _lib.require_cuda(x, "x")
         n, dev = x.shape[0], x.device
+        if self.training:
+            from . import train_forward
+            return train_forward.gcu_motion(self, pos, x, train_forward.graph_for_training(self._graphs, tpl_edge_index, n),
+                                            train_forward.graph_for_training(self._graphs, geo_edge_index, n))
 
         def build():
             parts: list = []
@@ -250,6 +255,9 @@ class EdgeConv(FusedModule):
         self._guard(x, edge_index)
         x = _lib.require_cuda(x.unsqueeze(-1) if x.dim() == 1 else x, "x")
         n = x.shape[0]
+        if self.training:
+            from . import train_forward
+            return train_forward.edge_branch(x, self.nn_pos, train_forward.graph_for_training(self._graphs, edge_index, n))
         pq, br = self._packed_for("edge", self._pack)
         _check_width("EdgeConv", x=(x, pq.K))
         out = torch.empty(n, br.H, device=x.device, dtype=torch.float32)
@@ -274,6 +282,10 @@ class GCU(FusedModule):
         self._guard(pos, tpl_edge_index, geo_edge_index)
         x = _lib.require_cuda(pos.unsqueeze(-1) if pos.dim() == 1 else pos, "pos")
         n, dev = x.shape[0], x.device
+        if self.training:
+            from . import train_forward
+            return train_forward.gcu(self, x, train_forward.graph_for_training(self._graphs, tpl_edge_index, n),
+                                     train_forward.graph_for_training(self._graphs, geo_edge_index, n))
         mlp = self._packed_for("gcu", lambda: packing.pack_mlp_layer(
             {"m." + k: v for k, v in self.mlp.state_dict(keep_vars=True).items()}, "m.0"))
         half = mlp.K // 2

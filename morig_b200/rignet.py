@@ -6,7 +6,8 @@ swapped into `training/train_rig.py:83`, `training/train_skin.py:83` and `evalua
 
 Every forward launches the fused sm_100a kernels of `libmorig_b200.so` through `engine.py`; the five
 key-frame passes of the motion encoder (same weights, same graph: models/rignet.py:85-86) run as one
-5x-row batch.  Inference only (eval BatchNorm, no autograd) in this round.
+5x-row batch in eval mode.  In train mode (`model.train()`) the forward builds an autograd graph of this package's
+kernels with train-mode BatchNorm (`train_forward.py`), so `loss.backward()` works as in training/train_rig.py:190.
 """
 from __future__ import annotations
 
@@ -40,6 +41,9 @@ class TemporalAttn(FusedModule):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         self._guard(x)
         x = _lib.require_cuda(x, "x")
+        if self.training:
+            from . import train_forward
+            return train_forward.temporal_attn(self, x)
         pk = self._packed_for("attn", self.pack)
         out = torch.empty(x.shape[0], pk.ff1.N, device=x.device, dtype=torch.float32)
         with engine.forward_scope(self._ws, x.device):
@@ -74,6 +78,12 @@ class GCNRig(FusedModule):
         feature = feature.unsqueeze(-1) if feature.dim() == 1 else feature
         feature = _lib.require_cuda(feature, "feature")
         n = pos.shape[0]
+        if self.training:
+            from . import train_forward
+            return train_forward.gcn_rig(self, pos, feature,
+                                         train_forward.graph_for_training(self._graphs, tpl_edge_index, n),
+                                         train_forward.graph_for_training(self._graphs, geo_edge_index, n),
+                                         self._batches.get(batch))
         pk = self._packed_for("rig", self.pack)
         if pos.dim() != 2 or pos.shape[1] != 3:
             raise ValueError(f"GCNRig: `pos` must be [N, 3], got {tuple(pos.shape)}")
@@ -163,7 +173,10 @@ class _MotionNet(FusedModule):
         self.__dict__.get("_seen", {}).clear()
 
     def forward(self, data, input_flow):
-        if not (self.use_cuda_graph and not engine.hooks_active() and not self.training
+        if self.training:
+            self._guard(data.pos, input_flow, data.tpl_edge_index, data.geo_edge_index, data.batch)
+            return self._train_forward(data, input_flow)
+        if not (self.use_cuda_graph and not engine.hooks_active()
                 and torch.is_tensor(data.pos) and data.pos.is_cuda):
             return self._forward_impl(data, input_flow, self._ws, self._graphs, self._batches)
         replays = self.__dict__.setdefault("_replays", {})
@@ -254,6 +267,11 @@ class _JointMaskBase(_MotionNet):
         return motion_all, motion_aggr, pred.clone()
 
 
+    def _train_forward(self, data, input_flow):
+        from . import train_forward
+        return train_forward.joint_mask_forward(self, data, input_flow)
+
+
 class JointNetMotion(_JointMaskBase):
     """models/rignet.py:70-100 — returns (motion_all [N,T,32], motion_aggr [N,64|32], pred_shift [N,chn_output])."""
     _head_name = "jointnet"
@@ -297,6 +315,12 @@ class SkinNet_inner(FusedModule):
         pos = _lib.require_cuda(data.pos, "data.pos")
         motion = _lib.require_cuda(motion, "motion")
         n = pos.shape[0]
+        if self.training:
+            from . import train_forward
+            return train_forward.skin_inner(self, data, pos, motion,
+                                            train_forward.graph_for_training(self._graphs, data.tpl_edge_index, n),
+                                            train_forward.graph_for_training(self._graphs, data.geo_edge_index, n),
+                                            self._batches.get(data.batch, data))
         gt = self._graphs.get(data.tpl_edge_index, n)
         gg = self._graphs.get(data.geo_edge_index, n)
         binfo = self._batches.get(data.batch, data)
@@ -318,6 +342,10 @@ class SkinMotion(_MotionNet):
         self.skinNet = SkinNet_inner(nearest_bone, use_Dg, use_Lf, motion_dim, use_motion, aggr)
 
     _needs_skin = True
+
+    def _train_forward(self, data, input_flow):
+        from . import train_forward
+        return train_forward.skin_forward(self, data, input_flow)
 
     def _forward_impl(self, data, input_flow, ws, graphs, batches):
         pos, flow, n, gt, gg, binfo = self._inputs(data, input_flow, graphs, batches)

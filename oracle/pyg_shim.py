@@ -16,7 +16,8 @@ Semantics restated from the published behaviour of those releases (their sources
   `*_i = t[ei[1]]`, `message(...)`, then scatter-max over `ei[1]` with `dim_size=N`,
   empty segments -> 0, then `update(...)`  (call site `:190`)
 * `scatter_max(src, index, dim=0)` -> (max per index, argmax); first maximal element wins,
-  untouched rows -> 0 / argmax = src.size(0)  (call sites `models/rignet.py:63,176`)
+  untouched rows -> 0 / argmax = src.size(0)  (call sites `models/rignet.py:63,176`); its gradient goes to
+  that first maximal element only (torch_scatter's backward gathers grad_out by argmax)
 """
 from __future__ import annotations
 
@@ -42,18 +43,25 @@ def scatter_max(src, index, dim=0, out=None, dim_size=None):
     assert dim == 0 and src.dim() == 2 and index.dim() == 1
     n = (int(index.max()) + 1 if index.numel() else 0) if dim_size is None else int(dim_size)
     lowest = torch.finfo(src.dtype).min
-    res = torch.full((n, src.shape[1]), lowest, dtype=src.dtype, device=src.device)
     idx2 = index.unsqueeze(1).expand_as(src)
-    res = res.scatter_reduce(0, idx2, src, reduce="amax", include_self=True)
-    # argmax: first row (in src order) attaining the max of its segment
-    hit = src == res[index]
-    rows = torch.arange(src.shape[0], device=src.device).unsqueeze(1).expand_as(src)
-    cand = torch.where(hit, rows, torch.full_like(rows, src.shape[0]))
-    arg = torch.full((n, src.shape[1]), src.shape[0], dtype=torch.long, device=src.device)
-    arg = arg.scatter_reduce(0, idx2, cand, reduce="amin", include_self=True)
-    touched = torch.zeros(n, dtype=torch.bool, device=src.device)
-    touched[index] = True
-    res = torch.where(touched.unsqueeze(1), res, torch.zeros_like(res))
+    with torch.no_grad():
+        res = torch.full((n, src.shape[1]), lowest, dtype=src.dtype, device=src.device)
+        res = res.scatter_reduce(0, idx2, src, reduce="amax", include_self=True)
+        # argmax: first row (in src order) attaining the max of its segment
+        hit = src == res[index]
+        rows = torch.arange(src.shape[0], device=src.device).unsqueeze(1).expand_as(src)
+        cand = torch.where(hit, rows, torch.full_like(rows, src.shape[0]))
+        arg = torch.full((n, src.shape[1]), src.shape[0], dtype=torch.long, device=src.device)
+        arg = arg.scatter_reduce(0, idx2, cand, reduce="amin", include_self=True)
+        touched = torch.zeros(n, dtype=torch.bool, device=src.device)
+        touched[index] = True
+        res = torch.where(touched.unsqueeze(1), res, torch.zeros_like(res))
+    if torch.is_grad_enabled() and src.requires_grad and src.shape[0] > 0:
+        # torch_scatter's backward sends the gradient of out[s, c] to src[arg[s, c], c] only (the first maximal
+        # element) -- unlike torch's scatter_reduce('amax'), which splits it evenly among ties.  Same values,
+        # re-expressed as a gather so that autograd follows that rule.
+        picked = src.gather(0, arg.clamp(max=src.shape[0] - 1))
+        res = torch.where(arg < src.shape[0], picked, torch.zeros_like(picked))
     return res, arg
 
 

@@ -13,7 +13,8 @@ vectors for this path, so that is the strongest pin available.
 
 The op sequence deliberately mirrors the reference step for step (per-edge gathers, explicit
 concatenations, Linear -> ReLU -> BatchNorm, scatter-max) so that its CPU timing is
-representative of the reference's CPU path.  Eval-mode only (running BatchNorm statistics).
+representative of the reference's CPU path.  Eval-mode by default (running BatchNorm statistics); under
+`with training_mode():` it is the training oracle (batch statistics, running-statistics updates, autograd).
 
 Each function cites the reference lines it follows (paths relative to /root/reference).
 """
@@ -25,6 +26,24 @@ import torch
 import torch.nn.functional as F
 
 
+# Training oracle: with TRAINING set (see `training_mode`) BatchNorm uses batch statistics and moves
+# the running statistics stored in `sd` in place, exactly like the reference's modules in `.train()` mode; gradients
+# come from torch autograd on the `sd` tensors that require grad.
+TRAINING = False
+
+
+class training_mode:
+    def __enter__(self):
+        global TRAINING
+        self.prev, TRAINING = TRAINING, True
+        return self
+
+    def __exit__(self, *exc):
+        global TRAINING
+        TRAINING = self.prev
+        return False
+
+
 def _mlp(sd, prefix: str, x: torch.Tensor) -> torch.Tensor:
     """`MLP(channels)` = stack of (Linear, ReLU, BatchNorm1d) — models/basic_modules.py:31-36.
     Keys `{prefix}.{layer}.0.{weight,bias}` (Linear) and `{prefix}.{layer}.2.*` (BatchNorm)."""
@@ -34,7 +53,7 @@ def _mlp(sd, prefix: str, x: torch.Tensor) -> torch.Tensor:
         x = F.linear(x, sd[p + ".0.weight"], sd[p + ".0.bias"])
         x = F.relu(x)
         x = F.batch_norm(x, sd[p + ".2.running_mean"], sd[p + ".2.running_var"],
-                         sd[p + ".2.weight"], sd[p + ".2.bias"], training=False, momentum=0.1, eps=1e-5)
+                         sd[p + ".2.weight"], sd[p + ".2.bias"], training=TRAINING, momentum=0.1, eps=1e-5)
         layer += 1
     return x
 
@@ -43,11 +62,22 @@ def _segment_max(msg: torch.Tensor, dst: torch.Tensor, n: int) -> torch.Tensor:
     """PyG `aggr='max'` -> torch_scatter max over the target index; empty segment -> 0
     (models/basic_modules.py:180-181,190; third-party semantics restated in oracle/pyg_shim.py)."""
     lowest = torch.finfo(msg.dtype).min
-    out = torch.full((n, msg.shape[1]), lowest, dtype=msg.dtype)
-    out = out.scatter_reduce(0, dst.unsqueeze(1).expand_as(msg), msg, reduce="amax", include_self=True)
-    seen = torch.zeros(n, dtype=torch.bool)
-    seen[dst] = True
-    return torch.where(seen.unsqueeze(1), out, torch.zeros_like(out))
+    idx2 = dst.unsqueeze(1).expand_as(msg)
+    with torch.no_grad():
+        out = torch.full((n, msg.shape[1]), lowest, dtype=msg.dtype)
+        out = out.scatter_reduce(0, idx2, msg, reduce="amax", include_self=True)
+        seen = torch.zeros(n, dtype=torch.bool)
+        seen[dst] = True
+        out = torch.where(seen.unsqueeze(1), out, torch.zeros_like(out))
+    if torch.is_grad_enabled() and msg.requires_grad and msg.shape[0] > 0:
+        # gradient rule of torch_scatter's max: only the FIRST maximal row of a segment receives it
+        rows = torch.arange(msg.shape[0]).unsqueeze(1).expand_as(msg)
+        cand = torch.where(msg.detach() == out[dst], rows, torch.full_like(rows, msg.shape[0]))
+        arg = torch.full((n, msg.shape[1]), msg.shape[0], dtype=torch.long)
+        arg = arg.scatter_reduce(0, idx2, cand, reduce="amin", include_self=True)
+        picked = msg.gather(0, arg.clamp(max=msg.shape[0] - 1))
+        out = torch.where(arg < msg.shape[0], picked, torch.zeros_like(picked))
+    return out
 
 
 def normalized_edges(edge_index: torch.Tensor, n: int) -> torch.Tensor:

@@ -18,4 +18,5 @@ def emulated(monkeypatch):
     """CPU emulation of the C-ABI launch helpers (tests/emu.py) — host-logic tests only."""
     import emu
     emu.install(monkeypatch)
+    emu.install_train(monkeypatch)
     return emu

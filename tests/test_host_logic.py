@@ -116,10 +116,12 @@ def test_train_mode_and_cpu_tensors_fail_loudly():
     kw = synth.ARCH_KWARGS["jointnet_motion"]
     model = morig_b200.jointnet_motion(**kw)
     data = synth.make_batch(1, 64, seed=0)
-    with pytest.raises(NotImplementedError):
-        model.train()(data, data.pred_flow)
     with pytest.raises(RuntimeError, match="no CPU path"):
-        model.eval()(data, data.pred_flow)                        # CPU tensors and no fallback
+        model.train()(data, data.pred_flow)                       # CPU tensors and no fallback, in either mode
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        model.eval()(data, data.pred_flow)
+    mean_model = morig_b200.jointnet_motion(**dict(kw, aggr_method="mean")).train()
+    assert mean_model.aggr_method == "mean"                       # (training with mean / max aggregation: see train_forward)
 
 
 def test_factories_ignore_extra_kwargs_like_the_reference():
@@ -158,7 +160,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(_lib.EXPORTS) == declared                      # the ctypes table covers the whole header
-    assert _lib.load().morig_version() == _lib.ABI_VERSION == 3
+    assert _lib.load().morig_version() == _lib.ABI_VERSION == 4
 
 
 def test_tensor_core_weight_image_layout():

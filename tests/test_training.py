@@ -1,0 +1,178 @@
+"""Training path.  CPU tier:
+  * the training oracle (oracle/rignet_port.py under `training_mode`) against autograd through the reference's own,
+    unmodified modules in `.train()` mode (build container only);
+  * the HOST logic of this package's training forward / backward (autograd function composition, factorised first
+    edge Linear, running-statistics updates) under the CPU emulation of the C-ABI (tests/emu.py) against that oracle.
+The GPU tier (tests/test_gpu_training.py) runs the real kernels."""
+import os
+
+import pytest
+import torch
+
+import helpers
+from morig_b200 import synth
+from oracle import pyg_shim, rignet_port
+
+HAVE_REF = os.path.isdir(os.path.join(pyg_shim.REFERENCE_ROOT, "models"))
+
+
+def loss_of(outs, pos):
+    """a scalar that exercises all three outputs (stand-in for the reference's losses, training/train_rig.py:168-183)"""
+    motion_all, motion_aggr, pred = outs
+    w1 = torch.linspace(-1, 1, motion_all.numel()).reshape(motion_all.shape)
+    w2 = torch.linspace(1, -1, motion_aggr.numel()).reshape(motion_aggr.shape)
+    return ((motion_all * w1.to(motion_all)).sum() + (motion_aggr * w2.to(motion_aggr)).sum() +
+            torch.tanh(pred).pow(2).sum()) / pos.shape[0]
+
+
+def oracle_train_step(arch, kw, sd0, data, flow, dtype=torch.float32):
+    """forward + backward of the training oracle on a copy of the weights; returns (outs, grads, updated buffers).
+    dtype=torch.float64 runs the same op sequence in double precision: train-mode BatchNorm over few rows with random
+    weights has nearly dead channels (variance ~ eps), which amplify fp32 rounding far beyond 1e-4, so comparisons use
+    the fp64 result as the yardstick and the fp32 oracle's own distance from it as the scale."""
+    sd = {k: (v.clone().to(dtype) if v.is_floating_point() else v.clone()) for k, v in sd0.items()}
+    if dtype != torch.float32:
+        data = synth.Batch(**{k: (v.to(dtype) if torch.is_tensor(v) and v.is_floating_point() else v)
+                              for k, v in data.__dict__.items()})
+        flow = flow.to(dtype)
+    params = {k for k in sd if sd[k].is_floating_point() and not k.endswith(("running_mean", "running_var"))}
+    for k in params:
+        sd[k].requires_grad_(True)
+    args = dict(num_keyframes=kw["num_keyframes"])
+    if arch == "skinnet_motion":
+        args.update(nearest_bone=kw["nearest_bone"], use_Dg=kw["use_Dg"], use_Lf=kw["use_Lf"])
+    else:
+        args.update(aggr_method=kw["aggr_method"])
+    with rignet_port.training_mode():
+        outs = rignet_port.FORWARDS[arch](sd, data, flow, **args)
+    loss_of(outs, data.pos).backward()
+    grads = {k: sd[k].grad for k in params}
+    bufs = {k: sd[k].detach() for k in sd if k.endswith(("running_mean", "running_var"))}
+    return [o.detach() for o in outs], grads, bufs
+
+
+def rel_err(a, b):
+    scale = max(float(b.abs().max()), 1e-6)
+    return float((a.detach().cpu().double() - b.detach().cpu().double()).abs().max()) / scale
+
+
+def grad_l2_errors(named_params, grads32, truth):
+    """relative L2 distance from the fp64 gradients, over all parameters: (this path, fp32 oracle)"""
+    num = num32 = den = 0.0
+    for k, p in named_params.items():
+        g = p.grad if hasattr(p, "grad") else p
+        num += float((g.detach().cpu().double() - truth[k]).pow(2).sum())
+        num32 += float((grads32[k].double() - truth[k]).pow(2).sum())
+        den += float(truth[k].pow(2).sum())
+    return (num / den) ** 0.5, (num32 / den) ** 0.5
+
+
+def close_to_truth(got, ref32, truth, tol=1e-4, slack=4.0):
+    """|got - truth| <= max(tol * range, slack * |fp32 reference - truth|)"""
+    rng = max(1.0, float(truth.abs().max()))
+    err = helpers.max_abs_diff(got, truth)
+    return err <= max(tol * rng, slack * helpers.max_abs_diff(ref32, truth)), err
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("arch", ["jointnet_motion", "skinnet_motion"])
+def test_training_oracle_matches_autograd_through_unmodified_reference(arch):
+    """the reference's own modules in .train() mode (shimmed PyG / torch_scatter, gradient of max to the first maximal
+    edge) vs the travelling training oracle: same outputs, gradients and running statistics"""
+    models = pyg_shim.import_reference_models()
+    kw = synth.ARCH_KWARGS[arch]
+    ref = models.__dict__[arch](**kw).train()
+    ref.load_state_dict(synth.seeded_state_dict(ref, 9))
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    data = synth.make_batch(2, 100, seed=77, with_skin=(arch == "skinnet_motion"))
+    outs = ref(data, data.pred_flow)
+    loss_of(outs, data.pos).backward()
+    o_outs, o_grads, o_bufs = oracle_train_step(arch, kw, sd0, data, data.pred_flow)
+    for a, b in zip(outs, o_outs):
+        assert torch.equal(a.detach(), b)
+    named = dict(ref.named_parameters())
+    assert set(named) == set(o_grads)
+    for k, p in named.items():
+        assert torch.allclose(p.grad, o_grads[k], rtol=0, atol=1e-6 * max(1.0, float(o_grads[k].abs().max()))), k
+    for k, v in ref.state_dict().items():
+        if k in o_bufs:
+            assert torch.equal(v, o_bufs[k]), k
+
+
+@pytest.mark.parametrize("arch,b,n", [("jointnet_motion", 2, 64), ("masknet_motion", 1, 100), ("skinnet_motion", 2, 64)])
+def test_training_host_logic_is_exact_in_double_precision(emulated, arch, b, n):
+    """Whole networks, forward + backward + running statistics, evaluated in fp64 through this package's training
+    path (autograd function composition, factorised first edge Linear, per-key-frame passes; C-ABI emulated on the
+    CPU) against the fp64 training oracle.  In double precision there is no rounding chaos (argmax flips, nearly dead
+    BatchNorm channels), so every parameter gradient must agree to 1e-8 of its range: an exact check of the logic."""
+    kw = synth.ARCH_KWARGS[arch]
+    model = helpers.build_model(arch, kw, 3).double()
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    data = synth.make_batch(b, n, seed=21, with_skin=(arch == "skinnet_motion"))
+    data = synth.Batch(**{k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v)
+                          for k, v in data.__dict__.items()})
+    x_outs, x_grads, x_bufs = oracle_train_step(arch, kw, sd0, data, data.pred_flow, dtype=torch.float64)
+    model.train()
+    outs = model(data, data.pred_flow)
+    for a, x, k in zip(outs, x_outs, helpers.OUT_KEYS):
+        assert a.shape == x.shape and helpers.max_abs_diff(a, x) < 1e-9 * max(1.0, float(x.abs().max())), k
+    loss_of(outs, data.pos).backward()
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        assert rel_err(p.grad, x_grads[k]) < 1e-8, k
+    for k, v in model.state_dict().items():
+        if k in x_bufs:
+            assert helpers.max_abs_diff(v, x_bufs[k]) < 1e-10 * max(1.0, float(x_bufs[k].abs().max())), k
+        if k.endswith("num_batches_tracked"):
+            assert int(v) == (5 if k.startswith("motionNet") else 1), k
+
+
+@pytest.mark.parametrize("arch,b,n", [("jointnet_motion", 2, 64), ("skinnet_motion", 2, 64)])
+def test_training_host_logic_fp32_stays_near_the_fp64_truth(emulated, arch, b, n):
+    """the same in fp32: train-mode BatchNorm over few rows with random weights has nearly dead channels and near-tie
+    maxima, so the fp32 reference itself is ~1e-2 from the fp64 result; this path must stay within a small multiple of
+    that (outputs: max-norm; gradients: relative L2 norm over all parameters)"""
+    kw = synth.ARCH_KWARGS[arch]
+    model = helpers.build_model(arch, kw, 3)
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    data = synth.make_batch(b, n, seed=21, with_skin=(arch == "skinnet_motion"))
+    o_outs, o_grads, _ = oracle_train_step(arch, kw, sd0, data, data.pred_flow)
+    x_outs, x_grads, _ = oracle_train_step(arch, kw, sd0, data, data.pred_flow, dtype=torch.float64)
+    model.train()
+    outs = model(data, data.pred_flow)
+    for a, e, x, k in zip(outs, o_outs, x_outs, helpers.OUT_KEYS):
+        ok, err = close_to_truth(a, e, x)
+        assert ok, (k, err)
+    loss_of(outs, data.pos).backward()
+    ours, ref = grad_l2_errors(dict(model.named_parameters()), o_grads, x_grads)
+    assert ours < max(1e-3, 10.0 * ref), (ours, ref)
+
+
+def test_gradient_of_max_goes_to_first_maximal_edge(emulated):
+    """integer-valued EdgeConvMotion with deliberate ties (duplicate edges, ReLU zeros): the argmax must follow the
+    oracle's first-edge rule, so the gradients are bit-identical integers"""
+    import morig_b200
+    g = torch.Generator().manual_seed(0)
+    n = 40
+    ei = torch.randint(0, n, (2, 300), generator=g)
+    ei = torch.cat([ei, ei[:, :100]], dim=1)                                  # duplicate edges: exact ties
+    mod = morig_b200.EdgeConvMotion(morig_b200.MLP([6, 32, 32]), morig_b200.MLP([6, 16, 16]))
+    with torch.no_grad():
+        for name, p in mod.named_parameters():
+            p.copy_(torch.randint(-1, 2, p.shape, generator=g).float())
+    pos = torch.randint(-2, 3, (n, 3), generator=g).float()
+    x = torch.randint(-2, 3, (n, 3), generator=g).float().requires_grad_(True)
+    xo = x.detach().clone().requires_grad_(True)
+    sd = {"m." + k: v.clone() for k, v in mod.state_dict().items()}
+    mod.eval()      # eval-mode BN in the ORACLE (exact integer affine); this package's train path has batch-stat BN, so
+    #                 compare the aggregation rule through the autograd functions directly instead:
+    from morig_b200 import autograd_ops as A, engine
+    gr = engine.graph_prep(ei, n)
+    gr.e_real = int(gr.rowptr[n])
+    y = (x[gr.tgt[:gr.e_real].long()] * 2 + x[gr.col[:gr.e_real].long()]).round()      # integer per-edge values with ties
+    out, arg = A.SegMax.apply(y, gr.rowptr, n)
+    out.sum().backward()
+    ref = rignet_port.normalized_edges(ei, n)
+    yo = (xo[ref[1]] * 2 + xo[ref[0]]).round()
+    rignet_port._segment_max(yo, ref[1], n).sum().backward()
+    assert torch.equal(x.grad, xo.grad)
