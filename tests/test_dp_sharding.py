@@ -75,3 +75,56 @@ def test_partition_balances_and_is_deterministic():
     loads = [sum(costs[i] for i in b) for b in bins]
     assert max(loads) <= 1.35 * (sum(costs) / 4)
     assert dp.partition([5, 5], 4) == [[0], [1], [], []]
+
+
+def _train_worker(rank, world, port, ret):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here); sys.path.insert(0, os.path.dirname(here))
+    import emu
+    import helpers
+    import test_training as tt
+
+    class MP:
+        def setattr(self, obj, name, val):
+            setattr(obj, name, val)
+    emu.install(MP()); emu.install_train(MP())
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    kw = synth.ARCH_KWARGS["masknet_motion"]
+    model = helpers.build_model("masknet_motion", kw, 4).train()
+    ar = dp.GradAllReduce(model, bucket_mb=8.0)
+    assert len(ar.buckets) >= 2
+    shards = [synth.make_batch(1, 64, seed=300 + r) for r in range(world)]
+    ar.zero_grad()
+    tt.loss_of(model(shards[rank], shards[rank].pred_flow), shards[rank].pos).backward()
+    nbytes = ar.finish()
+    got = {k: p.grad.clone() for k, p in model.named_parameters()}
+    flat_is_grad = all(p.grad.data_ptr() >= ar.flat.data_ptr() for p in model.parameters())
+    if rank == 0:
+        # single-process reference: mean over the two shards of the per-shard gradients (fresh copies of the model:
+        # per-replica BatchNorm statistics, as under DistributedDataParallel)
+        want = None
+        for r in range(world):
+            m = helpers.build_model("masknet_motion", kw, 4).train()
+            tt.loss_of(m(shards[r], shards[r].pred_flow), shards[r].pos).backward()
+            g = {k: p.grad for k, p in m.named_parameters()}
+            want = g if want is None else {k: want[k] + g[k] for k in g}
+        ret["err"] = max(float((got[k] - want[k] / world).abs().max()) / max(1.0, float(want[k].abs().max())) for k in got)
+        ret["bytes"] = nbytes
+        ret["numel"] = sum(p.numel() for p in model.parameters())
+        ret["views"] = flat_is_grad
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_all_reduce_equals_mean_of_shard_gradients():
+    """dp.GradAllReduce under gloo: flat-buffer, bucketed all-reduce launched from post-accumulate hooks during the
+    backward; the result is the mean of the per-rank gradients and the whole parameter set travels once"""
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_train_worker, args=(2, port, ret), nprocs=2, join=True)
+        assert ret["err"] < 1e-6
+        assert ret["bytes"] == 4 * ret["numel"] and ret["views"]

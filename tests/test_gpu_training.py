@@ -53,7 +53,7 @@ def test_kernels_take_column_slices_in_place():
     assert close(T.concat_cols([xs, dy]), torch.cat([xs.cpu(), dy.cpu()], 1), 0)
 
 
-@pytest.mark.parametrize("R,C", [(1, 8), (50, 16), (4096, 64), (100000, 256), (7, 1024)])
+@pytest.mark.parametrize("R,C", [(2, 8), (50, 16), (4096, 64), (100000, 256), (7, 1024)])
 def test_batchnorm_train_forward_and_backward(R, C):
     g = g_(R + C)
     x = torch.relu(torch.randn(R, C, generator=g) * 2 + 0.3)
@@ -272,7 +272,7 @@ def test_optimisation_steps_and_eval_after_training():
         loss = (torch.tanh(pred) - target).pow(2).mean()
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0]
     model.eval()
     with torch.no_grad():
