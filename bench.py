@@ -282,6 +282,46 @@ def run_ours(args):
         return model(resident, resident.pred_flow)
     ms_cached = timed(step_cached, args.steps, args.warmup)
 
+    # training step of the same network and batch: forward + backward through this package's
+    # kernels and ONE flat-buffer gradient all-reduce (NCCL over NVLink at N > 1, dp.GradAllReduce) -- informational,
+    # outside the headline metric
+    train = None
+    if args.train_steps > 0:
+        from morig_b200 import dp
+        tmodel = getattr(morig_b200, ARCH)(**kw)
+        tmodel.load_state_dict(synth.seeded_state_dict(tmodel, 1))
+        tmodel = tmodel.to(dev).train()
+        ar = dp.GradAllReduce(tmodel)
+        target = torch.zeros(resident.pos.shape[0], 3, device=dev)
+
+        def train_step():
+            ar.zero_grad()
+            _, _, pred = tmodel(resident, resident.pred_flow)
+            loss = (torch.tanh(pred) - target).pow(2).mean()       # stand-in for training/train_rig.py:168-183
+            loss.backward()
+            return ar.finish()
+
+        nbytes = train_step()
+        barrier()
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record(stream)
+        for _ in range(args.train_steps):
+            train_step()
+        e_ev.record(stream)
+        barrier()
+        t = torch.tensor([s_ev.elapsed_time(e_ev)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_train = float(t.item()) / args.train_steps
+        train = {"ms_per_step": ms_train, "meshes_per_s": MESHES_PER_GPU * world / (ms_train / 1e3),
+                 "steps": args.train_steps, "allreduce_bytes_per_step": nbytes, "buckets": len(ar.buckets),
+                 "what": "forward + backward (train-mode BatchNorm, fp32 CUDA-core GEMMs) + flat-buffer gradient all-reduce, "
+                         "max over ranks; BatchNorm statistics per replica",
+                 "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+        ar.close()
+        del tmodel, ar
+        torch.cuda.empty_cache()
+
     if rank == 0:
         meshes = MESHES_PER_GPU * world * args.steps
         value = meshes / (ms_total / 1e3)
@@ -345,6 +385,8 @@ def run_ours(args):
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         if cfg0 is not None:
             line["config0_1x1024"] = cfg0
+        if train is not None:
+            line["train_step"] = train
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
@@ -357,6 +399,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--train-steps", type=int, default=3,
+                    help="extra: timed training steps (forward + backward + gradient all-reduce) reported under "
+                         "`train_step`; 0 disables")
     ap.add_argument("--meshes-per-gpu", type=int, default=MESHES_PER_GPU,
                     help="meshes in one step's batch per GPU (4 = BASELINE.json configs[1]; 8 at --gpus 8 = configs[4])")
     args = ap.parse_args()

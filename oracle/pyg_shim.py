@@ -100,6 +100,28 @@ class MessagePassing(torch.nn.Module):
         return aggr_out
 
 
+class Data:
+    """minimal stand-in for `torch_geometric.data.Data` / a collated `Batch`: an attribute bag with `.to(device)`"""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def to(self, device, *a, **k):
+        return Data(**{key: (v.to(device) if torch.is_tensor(v) else v) for key, v in self.__dict__.items()})
+
+
+class InMemoryDataset:
+    def __init__(self, *a, **k):
+        raise NotImplementedError("datasets are external downloads; the oracle shim feeds synthetic batches")
+
+
+class DataLoader(list):
+    """`torch_geometric.loader.DataLoader` stand-in: a list of already collated batches"""
+
+    def __init__(self, batches=(), *a, **k):
+        super().__init__(batches)
+
+
 def _unavailable(*_a, **_k):
     raise NotImplementedError("not on the rignet.py forward path; not provided by the oracle shim")
 
@@ -121,7 +143,10 @@ def install() -> None:
     tg.nn.conv = mod("torch_geometric.nn.conv", MessagePassing=MessagePassing)
     tg.utils = mod("torch_geometric.utils", remove_self_loops=remove_self_loops,
                    add_self_loops=add_self_loops, softmax=_unavailable)
+    tg.loader = mod("torch_geometric.loader", DataLoader=DataLoader)
+    tg.data = mod("torch_geometric.data", Data=Data, InMemoryDataset=InMemoryDataset)
     mod("torch_scatter", scatter_max=scatter_max, scatter_add=scatter_add)
+    mod("torch_cluster", fps=_unavailable, knn=_unavailable, radius=_unavailable)
 
 
 REFERENCE_ROOT = "/root/reference"
