@@ -222,6 +222,40 @@ MORIG_API size_t morig_tpl_edges_workspace(int64_t F);
 MORIG_API int    morig_tpl_edges(const int64_t *faces, int64_t F, int64_t *edges, int64_t *count, void *ws,
                                  size_t ws_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Rest of the joint-extraction post-process and the losses next to it.
+ *
+ * morig_nms_meanshift: utils/cluster_utils.py:38-63 (`nms_meanshift`, run after the mean-shift at
+ *   evaluate/eval_rigging.py:94).  pts [N,3], attn [N] fp64; keep [N] receives 1 for the surviving modes (the caller
+ *   compacts: pts[keep]).  Visiting order: decreasing neighbour count, equal counts from the higher index down
+ *   (= np.argsort(kind="stable")[::-1]; the reference's default argsort leaves ties unspecified).
+ * morig_nn_dist_*: nearest-neighbour distance (and index, first minimum) of every row of A [N,D] among B [M,D], D <= 4:
+ *   both halves of `chamfer_distance_with_average` (models/customized_losses.py:231-251, fp32) and of `chamfer_dist`
+ *   (utils/mst_utils.py:316-321, fp64).  morig_chamfer_bwd_f32: gradient with respect to A of
+ *   g1 * sum_i d1[i] + g2 * sum_j d2[j]  (d1 / n1 = A against B, d2 / n2 = B against A).
+ * morig_info_nce_*: loss[r] = logsumexp_m(A[r] . K[m] / tau) - A[r] . K[label[r]] / tau  (cross entropy of the similarity
+ *   rows: `infoNCE`, models/customized_losses.py:107-135, per direction; `multi_pos_infoNCE` :137-158 after its
+ *   sampling); lse [R] is saved for the backward, which writes dA and accumulates dK (optional).  With sel [R, S] != NULL
+ *   row r only sees its candidate keys K[sel[r, s]] and label[r] is a position in that list (multi_pos_infoNCE: one
+ *   positive + 200 negatives per anchor).
+ * ------------------------------------------------------------------------------------------- */
+MORIG_API size_t morig_nms_meanshift_workspace(int32_t N);
+MORIG_API int    morig_nms_meanshift(const double *pts, const double *attn, int32_t N, double bandwidth, double thrd_density,
+                                     double thrd_attn, uint8_t *keep, void *ws, size_t ws_bytes, void *stream);
+MORIG_API int    morig_nn_dist_f32(const float *A, int32_t N, const float *B, int32_t M, int32_t D, float *dist, int32_t *arg,
+                                   void *stream);
+MORIG_API int    morig_nn_dist_f64(const double *A, int32_t N, const double *B, int32_t M, int32_t D, double *dist, int32_t *arg,
+                                   void *stream);
+MORIG_API int    morig_chamfer_bwd_f32(const float *A, int32_t N, const float *B, int32_t M, int32_t D, const float *d1,
+                                       const int32_t *n1, const float *d2, const int32_t *n2, float g1, float g2, float *dA,
+                                       void *stream);
+MORIG_API int    morig_info_nce_fwd(const float *A, int32_t lda, const float *K, int32_t ldk, const int64_t *label,
+                                    const int64_t *sel, int32_t S, int32_t R, int32_t M, int32_t C, float tau, float *loss,
+                                    float *lse, void *stream);
+MORIG_API int    morig_info_nce_bwd(const float *A, int32_t lda, const float *K, int32_t ldk, const int64_t *label,
+                                    const int64_t *sel, int32_t S, const float *lse, const float *g, int32_t R, int32_t M,
+                                    int32_t C, float tau, float *dA, int32_t ldda, float *dK, int32_t lddk, void *stream);
+
 /* =============================================================================================
  * Training path.  The reference trains these networks with torch autograd
  * (training/train_rig.py:136-195, training/train_skin.py:139-183): train-mode BatchNorm1d inside every MLP block

@@ -83,6 +83,13 @@ _SIGNATURES = {
                                     C.c_int32, c_f32p, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
     "morig_fill_f32": (C.c_int, [c_f32p, C.c_int64, C.c_float, C.c_void_p]),
     "morig_absmax_f32": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
+    "morig_nms_meanshift_workspace": (C.c_size_t, [_I]),
+    "morig_nms_meanshift": (C.c_int, [_P, _P, _I, C.c_double, C.c_double, C.c_double, _P, _P, C.c_size_t, _P]),
+    "morig_nn_dist_f32": (C.c_int, [_P, _I, _P, _I, _I, _P, _P, _P]),
+    "morig_nn_dist_f64": (C.c_int, [_P, _I, _P, _I, _I, _P, _P, _P]),
+    "morig_chamfer_bwd_f32": (C.c_int, [_P, _I, _P, _I, _I, _P, _P, _P, _P, C.c_float, C.c_float, _P, _P]),
+    "morig_info_nce_fwd": (C.c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, C.c_float, _P, _P, _P]),
+    "morig_info_nce_bwd": (C.c_int, [_P, _I, _P, _I, _P, _P, _I, _P, _P, _I, _I, _I, C.c_float, _P, _I, _P, _I, _P]),
     # ---- training path ----
     "morig_transpose_pad_f32": (C.c_int, [_P, _I, _I, _I, _P, _I, _P]),
     "morig_wgrad_workspace": (C.c_size_t, [_I, _I, _I]),

@@ -2,79 +2,54 @@
 // Replaces remove_self_loops/add_self_loops of models/basic_modules.py:188-189 (run 36x per forward
 // by the reference) with one pass per edge set; also a brute-force kNN graph builder used for the
 // synthetic geodesic stand-in.  Integer work: results are bit-exact against oracle/graph_port.py.
+#include <cub/cub.cuh>
 #include "common.cuh"
 
 namespace morig {
 
-__global__ void gp_init_kernel(int32_t *cnt, int32_t n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) cnt[i] = 1;  // the appended self loop
-}
-
-__global__ void gp_count_kernel(const int64_t *__restrict__ ei, int64_t E, int32_t n, int32_t *cnt) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= E) return;
-    int64_t j = ei[e], i = ei[E + e];
-    if (j == i || i < 0 || i >= n || j < 0 || j >= n) return;
-    atomicAdd(&cnt[(int)i], 1);
-}
-
-// single-block exclusive scan; n+1 outputs. cursor[i] = rowptr[i].
-__global__ void gp_scan_kernel(const int32_t *__restrict__ cnt, int32_t n, int32_t *rowptr, int32_t *cursor) {
-    __shared__ int32_t part[1024];
-    const int t = threadIdx.x, nt = blockDim.x;
-    const int per = (n + nt - 1) / nt;
-    const int lo = min(t * per, n), hi = min(lo + per, n);
-    int32_t s = 0;
-    for (int i = lo; i < hi; ++i) s += cnt[i];
-    part[t] = s;
-    __syncthreads();
-    for (int off = 1; off < nt; off <<= 1) {  // Hillis-Steele inclusive scan of the partials
-        int32_t v = (t >= off) ? part[t - off] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
+// Stable target-sorted CSR = a STABLE sort of the normalised edge list by target.  Three steps, all parallel over edges and
+// independent of the in-degree distribution (a hub with 64 K in-edges costs the same as 64 K ordinary edges):
+//   gp_keys_kernel    slot e < E:  key = target (or the sentinel N for dropped edges: self loops, out-of-range ids),
+//                     value = source;  slot E + v: the appended self loop (v, v) -- after all real edges, so the stable
+//                     sort leaves it last inside its target, exactly like add_self_loops' append
+//   cub radix sort    keys -> tgt, values -> col   (LSD radix sort is stable; only ceil(log2(N + 1)) key bits are sorted)
+//   gp_rowptr_kernel  rowptr[v] = first slot whose key >= v (binary search); rowptr[N] = E' = first sentinel
+__global__ void gp_keys_kernel(const int64_t *__restrict__ ei, int64_t E, int32_t n, int32_t *__restrict__ keys,
+                               int32_t *__restrict__ vals) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E + n) return;
+    if (e < E) {
+        const int64_t j = ei[e], i = ei[E + e];
+        const bool drop = (j == i || i < 0 || i >= n || j < 0 || j >= n);
+        keys[e] = drop ? n : (int32_t)i;
+        vals[e] = drop ? 0 : (int32_t)j;
+    } else {
+        keys[e] = vals[e] = (int32_t)(e - E);
     }
-    int32_t run = part[t] - s;
-    for (int i = lo; i < hi; ++i) {
-        rowptr[i] = run;
-        cursor[i] = run;
-        run += cnt[i];
-    }
-    if (t == nt - 1) rowptr[n] = part[t];
 }
 
-__global__ void gp_fill_kernel(const int64_t *__restrict__ ei, int64_t E, int32_t n, int32_t *cursor,
-                               int32_t *col, int32_t *eid) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= E) return;
-    int64_t j = ei[e], i = ei[E + e];
-    if (j == i || i < 0 || i >= n || j < 0 || j >= n) return;
-    int slot = atomicAdd(&cursor[(int)i], 1);
-    col[slot] = (int32_t)j;
-    eid[slot] = (int32_t)e;
+__global__ void gp_rowptr_kernel(const int32_t *__restrict__ tgt, int32_t total, int32_t n, int32_t *__restrict__ rowptr) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > n) return;
+    int lo = 0, hi = total;                          // first slot with tgt[slot] >= v
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tgt[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    rowptr[v] = lo;
 }
 
-// one thread per target: restore input order inside the segment (stable CSR), put the self loop
-// last, expand the target id per slot.
-__global__ void gp_finalize_kernel(const int32_t *__restrict__ rowptr, int32_t n, int32_t *col, int32_t *eid,
-                                   int32_t *tgt) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int lo = rowptr[i], hi = rowptr[i + 1] - 1;  // [lo, hi) real edges, slot hi = self loop
-    for (int a = lo + 1; a < hi; ++a) {                // insertion sort by original edge id
-        int32_t ke = eid[a], kc = col[a];
-        int b = a - 1;
-        while (b >= lo && eid[b] > ke) {
-            eid[b + 1] = eid[b];
-            col[b + 1] = col[b];
-            --b;
-        }
-        eid[b + 1] = ke;
-        col[b + 1] = kc;
-    }
-    col[hi] = i;
-    for (int a = lo; a <= hi; ++a) tgt[a] = i;
+static int key_bits(int32_t n) {                     // bits needed for keys 0..n (n = sentinel)
+    int b = 1;
+    while (((int64_t)1 << b) <= (int64_t)n) ++b;
+    return b;
+}
+
+static size_t sort_temp_bytes(int64_t total, int32_t n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int32_t *)nullptr, (int32_t *)nullptr, (const int32_t *)nullptr,
+                                    (int32_t *)nullptr, (int)total, 0, key_bits(n));
+    return bytes;
 }
 
 // ---- brute-force kNN inside each graph: one warp per query vertex --------------------------------
@@ -141,7 +116,8 @@ __global__ void knn_kernel(const float *__restrict__ pos, const int32_t *__restr
 using namespace morig;
 
 extern "C" MORIG_API size_t morig_graph_prep_workspace(int64_t E, int32_t N) {
-    return sizeof(int32_t) * (size_t)(2 * (int64_t)N + E + N) + 256;
+    const int64_t total = E + N;
+    return sizeof(int32_t) * (size_t)(2 * total) + 512 + sort_temp_bytes(total, N);
 }
 
 extern "C" MORIG_API int morig_graph_prep(const int64_t *edge_index, int64_t E, int32_t N, int32_t *rowptr, int32_t *col,
@@ -154,14 +130,17 @@ extern "C" MORIG_API int morig_graph_prep(const int64_t *edge_index, int64_t E, 
         set_error("graph_prep: workspace %zu < %zu", ws_bytes, morig_graph_prep_workspace(E, N));
         return MORIG_E_WORKSPACE;
     }
-    int32_t *cnt = (int32_t *)ws, *cursor = cnt + N, *eid = cursor + N;
+    const int64_t total = E + N;
+    int32_t *keys = (int32_t *)ws, *vals = keys + total;
+    void *temp = (void *)(((uintptr_t)(vals + total) + 255) & ~(uintptr_t)255);
+    size_t temp_bytes = sort_temp_bytes(total, N);
     const int T = 256;
-    gp_init_kernel<<<ceil_div(N, T), T, 0, stream>>>(cnt, N);
-    if (E > 0) gp_count_kernel<<<(unsigned)ceil_div64(E, T), T, 0, stream>>>(edge_index, E, N, cnt);
-    gp_scan_kernel<<<1, 1024, 0, stream>>>(cnt, N, rowptr, cursor);
-    if (E > 0) gp_fill_kernel<<<(unsigned)ceil_div64(E, T), T, 0, stream>>>(edge_index, E, N, cursor, col, eid);
-    gp_finalize_kernel<<<ceil_div(N, 128), 128, 0, stream>>>(rowptr, N, col, eid, tgt);
-    MORIG_LAUNCH_CHECK("graph_prep");
+    gp_keys_kernel<<<(unsigned)ceil_div64(total, T), T, 0, stream>>>(edge_index, E, N, keys, vals);
+    MORIG_LAUNCH_CHECK("gp_keys_kernel");
+    MORIG_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const int32_t *)keys, tgt, (const int32_t *)vals, col, (int)total, 0,
+                                               key_bits(N), stream));
+    gp_rowptr_kernel<<<ceil_div(N + 1, T), T, 0, stream>>>(tgt, (int32_t)total, N, rowptr);
+    MORIG_LAUNCH_CHECK("gp_rowptr_kernel");
     return 0;
 }
 

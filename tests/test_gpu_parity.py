@@ -35,6 +35,24 @@ def test_graph_prep_bit_exact(n, e, seed):
     assert np.array_equal(g.tgt.cpu().numpy()[:e_real], np.repeat(np.arange(n, dtype=np.int32), np.diff(rowptr)))
 
 
+def test_graph_prep_hub_with_64k_in_edges():
+    """degree robustness: a star whose hub has 65 536 in-edges (plus duplicates and self loops) -- the CSR is a stable
+    radix sort by target, so the cost does not depend on the in-degree distribution; bit-exact vs the oracle"""
+    from oracle import graph_port
+    n = 70000
+    rng = np.random.default_rng(7)
+    src = rng.permutation(n)[:65536]
+    ei = np.stack([src, np.full(65536, 5)]).astype(np.int64)
+    extra = rng.integers(0, n, size=(2, 20000)).astype(np.int64)
+    ei = np.concatenate([ei[:, :30000], extra, ei[:, 30000:], ei[:, :100]], axis=1)
+    g = engine.graph_prep(torch.from_numpy(ei).to(DEV), n)
+    rowptr, col = graph_port.csr_by_target(ei, n)
+    e_real = int(rowptr[-1])
+    assert np.array_equal(g.rowptr.cpu().numpy(), rowptr)
+    assert np.array_equal(g.col.cpu().numpy()[:e_real], col)
+    assert np.array_equal(g.tgt.cpu().numpy()[:e_real], np.repeat(np.arange(n, dtype=np.int32), np.diff(rowptr)))
+
+
 def test_graph_prep_on_dataset_style_input():
     """edge lists as the dataset delivers them (self loops already appended, datasets/dataset_rig.py:121-122)"""
     from oracle import graph_port
