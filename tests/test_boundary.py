@@ -112,6 +112,10 @@ def test_reference_train_and_test_loops_run_unchanged_on_installed_networks(emul
     from morig_b200 import synth
     models = pyg_shim.import_reference_models()
     ref_factories = {k: models.__dict__[k] for k in ("jointnet_motion", "masknet_motion")}
+    names = ("jointnet_motion", "masknet_motion", "skinnet_motion", "JointNetMotion", "MaskNetMotion", "SkinMotion",
+             "SkinNet_inner", "GCNRig", "TemporalAttn")
+    saved = {k: models.__dict__[k] for k in names if k in models.__dict__}
+    saved_sub = {k: models.rignet.__dict__[k] for k in names if k in models.rignet.__dict__}
     import importlib
     if not hasattr(np, "int"):
         np.int = int          # the reference pins numpy 1.2x (environment.yml), where the alias its utils use still exists
@@ -149,7 +153,8 @@ def test_reference_train_and_test_loops_run_unchanged_on_installed_networks(emul
                 for k in a:
                     assert abs(a[k] - b[k]) <= tol * max(1.0, abs(a[k])), (arch, stage, k, a[k], b[k])
             assert results[1][0]["total_loss"] != results[1][2]["total_loss"]  # the optimiser steps took effect
-    finally:
-        for k, v in ref_factories.items():
+    finally:                                   # other tests import the reference's own classes from `models`
+        for k, v in saved.items():
             setattr(models, k, v)
+        for k, v in saved_sub.items():
             setattr(models.rignet, k, v)
