@@ -256,6 +256,52 @@ MORIG_API int    morig_info_nce_bwd(const float *A, int32_t lda, const float *K,
                                     const int64_t *sel, int32_t S, const float *lse, const float *g, int32_t R, int32_t M,
                                     int32_t C, float tau, float *dA, int32_t ldda, float *dK, int32_t lddk, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Point-cloud primitives of the upstream flow producer (CorrNet / DeformNet,
+ * models/corrnet.py:10-77, models/deformnet.py:34-99, PointNet++ modules models/basic_modules.py:66-138) and of the
+ * surface-sampling front-end of the geodesic graph build (section 8(f) #2, data_proc/common_ops.py:175-181).
+ * They replace torch_cluster.fps / radius / knn and PyG's knn_interpolate / PointConv (semantics restated in
+ * oracle/pointops_port.py).  Segments: points of sample b are rows ptr[b] .. ptr[b+1] (sorted `batch` vectors).
+ *
+ * morig_fps            farthest point sampling per segment: out[out_ptr[b] ..] = global indices in selection order, first
+ *                      pick = ptr[b] + start[b] (start == NULL: 0), ties -> lower index; segments <= 16384 points
+ * morig_ball_query     nbr [M, K] = the first K points (index order) of the centre's segment with |x - y|^2 < radius^2,
+ *                      count [M] = number of valid entries (torch_cluster.radius with max_num_neighbors = K)
+ * morig_knn_topk       nbr [M, k] (k <= 8) nearest points of the query's segment, nearest first; metric 0 = squared
+ *                      Euclidean distance, 1 = cosine similarity (torch_cluster.knn(cosine=True)); score optional
+ * morig_knn_interpolate  out[i] = sum_k w_k f[nbr[i,k]] / sum_k w_k, w = 1 / max(|pos_x - pos_y|^2, 1e-16)
+ * morig_sample_surface   S area-weighted uniform samples on a triangle mesh + unit face normals (fp64; splitmix64 hash of
+ *                      (seed, sample) -- reproducible on any device); ws: 2 F doubles
+ * morig_edge_mlp_layer   Linear -> ReLU -> affine on E edge rows of a bipartite neighbourhood graph (PointConv's local MLP,
+ *                      PyG PointNetConv): rows = A [E, K] or relu(P[tgt[e]] + Q[col[e]]) (factorised first Linear on
+ *                      cat[x_j, pos_j - pos_i]); result stored per edge (C) or max-reduced per target into `out`
+ *                      (pre-filled with -inf), rowptr [n_targets + 1] / tgt [E] describing the target-sorted rows
+ * ------------------------------------------------------------------------------------------- */
+MORIG_API int morig_fps(const float *pos, const int32_t *ptr, const int32_t *out_ptr, const int32_t *start, int32_t B,
+                        int32_t max_segment, int32_t *out, void *stream);
+MORIG_API int morig_ball_query(const float *x, const int32_t *x_ptr, const float *y, const int32_t *y_batch, int32_t M, float radius,
+                               int32_t K, int32_t *nbr, int32_t *count, void *stream);
+MORIG_API int morig_knn_topk(const float *x, int32_t ldx, const int32_t *x_ptr, const float *y, int32_t ldy, const int32_t *y_batch,
+                             int32_t M, int32_t D, int32_t k, int32_t metric, int32_t *nbr, float *score, void *stream);
+MORIG_API int morig_knn_interpolate(const float *f, int32_t ldf, const float *pos_x, const float *pos_y, const int32_t *nbr, int32_t M,
+                                    int32_t k, int32_t C, float *out, int32_t ldo, void *stream);
+MORIG_API int morig_sample_surface(const double *verts, const int64_t *faces, int32_t F, int32_t S, uint64_t seed, double *pts,
+                                   double *normals, double *ws, void *stream);
+
+typedef struct morig_edge_layer_desc {
+    const float   *A;      int32_t lda;              /* plain edge rows [E, K], or NULL                    */
+    const float   *P, *Q;  int32_t ldpq;             /* gathered rows relu(P[tgt] + Q[col]), or NULL       */
+    const int32_t *rowptr; const int32_t *col; const int32_t *tgt;
+    int32_t        n_targets, E;
+    const float   *W;      int32_t ldw;              /* [K, ldw] packed (transposed) Linear weight         */
+    const float   *bias, *scale, *shift;             /* [N] (scale / shift optional)                       */
+    float         *C;      int32_t ldc;              /* per-edge output [E, N], or NULL                    */
+    float         *out;    int32_t ldo;              /* per-target max [n_targets, N], or NULL             */
+    int32_t        N, K;
+} morig_edge_layer_desc;
+
+MORIG_API int morig_edge_mlp_layer(const morig_edge_layer_desc *d, void *stream);
+
 /* =============================================================================================
  * Training path.  The reference trains these networks with torch autograd
  * (training/train_rig.py:136-195, training/train_skin.py:139-183): train-mode BatchNorm1d inside every MLP block

@@ -54,6 +54,16 @@ class EdgeDesc(C.Structure):
 
 _P, _I = C.c_void_p, C.c_int32
 
+
+class EdgeLayerDesc(C.Structure):
+    """mirror of `morig_edge_layer_desc`"""
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_int32), ("P", C.c_void_p), ("Q", C.c_void_p), ("ldpq", C.c_int32),
+                ("rowptr", C.c_void_p), ("col", C.c_void_p), ("tgt", C.c_void_p), ("n_targets", C.c_int32), ("E", C.c_int32),
+                ("W", C.c_void_p), ("ldw", C.c_int32), ("bias", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("C", C.c_void_p), ("ldc", C.c_int32), ("out", C.c_void_p), ("ldo", C.c_int32), ("N", C.c_int32),
+                ("K", C.c_int32)]
+
+
 _SIGNATURES = {
     "morig_version": (C.c_int, []),
     "morig_last_error": (C.c_char_p, []),
@@ -90,6 +100,12 @@ _SIGNATURES = {
     "morig_chamfer_bwd_f32": (C.c_int, [_P, _I, _P, _I, _I, _P, _P, _P, _P, C.c_float, C.c_float, _P, _P]),
     "morig_info_nce_fwd": (C.c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, C.c_float, _P, _P, _P]),
     "morig_info_nce_bwd": (C.c_int, [_P, _I, _P, _I, _P, _P, _I, _P, _P, _I, _I, _I, C.c_float, _P, _I, _P, _I, _P]),
+    "morig_fps": (C.c_int, [_P, _P, _P, _P, _I, _I, _P, _P]),
+    "morig_ball_query": (C.c_int, [_P, _P, _P, _P, _I, C.c_float, _I, _P, _P, _P]),
+    "morig_knn_topk": (C.c_int, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "morig_knn_interpolate": (C.c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _P, _I, _P]),
+    "morig_sample_surface": (C.c_int, [_P, _P, _I, _I, C.c_uint64, _P, _P, _P, _P]),
+    "morig_edge_mlp_layer": (C.c_int, [C.POINTER(EdgeLayerDesc), _P]),
     # ---- training path ----
     "morig_transpose_pad_f32": (C.c_int, [_P, _I, _I, _I, _P, _I, _P]),
     "morig_wgrad_workspace": (C.c_size_t, [_I, _I, _I]),

@@ -1,10 +1,15 @@
 """Surface-geodesic graph build on the GPU: `calc_surface_geodesic` / `get_geo_edges` of the
 reference (`data_proc/common_ops.py:176-226`; offline pre-processing and `evaluate/joint2rig.py:505`) from the point
-where the surface samples and their normals exist.  The Poisson-disk sampling and normal estimation are open3d's
-(`mesh.sample_points_poisson_disk`, `estimate_normals`, :178-179) and are not rebuilt: pass their output in.
+where the surface samples and their normals exist, plus a front-end that produces them.  The reference samples with
+open3d (`mesh.sample_points_poisson_disk`, `estimate_normals`, :178-179), which is not in this image and whose random
+stream cannot be reproduced; `sample_surface_poisson` is the stand-in: area-weighted uniform surface samples (5x
+oversampled, counter-based hash RNG) thinned by farthest point sampling -- a blue-noise set like Poisson-disk sampling --
+with the face normal of each sample's triangle.
 
-    geo = surface_geodesic(np.asarray(samples.points), np.asarray(samples.normals), np.asarray(mesh.vertices))
-    geo_edge_index = geo_ball_edges(geo, radius=0.06, max_nn=15)          # rows [i, j] like the reference
+    geo = calc_surface_geodesic(verts, faces)                             # sampling + geodesic matrix, like :176-208
+    geo = surface_geodesic(np.asarray(samples.points), np.asarray(samples.normals), np.asarray(mesh.vertices))   # open3d samples
+    geo_edge_index = get_geo_edges(geo, verts)                            # rows [i, j]; the reference's random subset rule
+    geo_edge_index = geo_ball_edges(geo, radius=0.06, max_nn=15)          # deterministic variant (max_nn nearest)
 
 numpy in -> numpy out, CUDA tensors in -> CUDA tensors out.  There is no CPU path.
 """
@@ -100,3 +105,89 @@ def tpl_edges(obj_v, obj_f):
                                        _lib.stream_ptr()), "morig_tpl_edges")
     out = edges[: int(count.item())]
     return out.cpu().numpy() if as_numpy else out
+
+
+def _mesh_arrays(verts, faces, dev):
+    v = _to_dev(verts, dev)
+    f = (torch.from_numpy(np.ascontiguousarray(faces, dtype=np.int64)) if isinstance(faces, np.ndarray) else faces)
+    return v, f.to(dev, torch.int64).contiguous()
+
+
+def sample_surface_uniform(verts, faces, number_of_points, seed=0):
+    """area-weighted uniform samples on the triangle mesh and the unit normals of their faces: ([S,3], [S,3]) float64"""
+    lib = _lib.load()
+    dev, as_numpy = _device_of(verts)
+    v, f = _mesh_arrays(verts, faces, dev)
+    nf, s = f.shape[0], int(number_of_points)
+    pts = torch.empty(s, 3, dtype=torch.float64, device=dev)
+    nrm = torch.empty(s, 3, dtype=torch.float64, device=dev)
+    ws = torch.empty(2 * nf, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.morig_sample_surface(v.data_ptr(), f.data_ptr(), nf, s, int(seed), pts.data_ptr(), nrm.data_ptr(),
+                                            ws.data_ptr(), _lib.stream_ptr()), "morig_sample_surface")
+    return (pts.cpu().numpy(), nrm.cpu().numpy()) if as_numpy else (pts, nrm)
+
+
+def sample_surface_poisson(verts, faces, number_of_points=4000, seed=0, init_factor=5):
+    """stand-in for open3d's `sample_points_poisson_disk(number_of_points)` + normals (data_proc/common_ops.py:178-179):
+    init_factor x number_of_points uniform surface samples thinned to number_of_points by farthest point sampling"""
+    lib = _lib.load()
+    dev, as_numpy = _device_of(verts)
+    v, f = _mesh_arrays(verts, faces, dev)
+    s = int(number_of_points)
+    raw, nrm = sample_surface_uniform(v, f, min(init_factor * s, 16384), seed)
+    n_raw = raw.shape[0]
+    pos32 = raw.to(torch.float32).contiguous()
+    ptr = torch.tensor([0, n_raw], dtype=torch.int32, device=dev)
+    out_ptr = torch.tensor([0, s], dtype=torch.int32, device=dev)
+    idx = torch.empty(s, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.morig_fps(pos32.data_ptr(), ptr.data_ptr(), out_ptr.data_ptr(), 0, 1, n_raw, idx.data_ptr(), _lib.stream_ptr()),
+                   "morig_fps")
+    pts, nrm = raw[idx.long()], nrm[idx.long()]
+    return (pts.cpu().numpy(), nrm.cpu().numpy()) if as_numpy else (pts, nrm)
+
+
+def calc_surface_geodesic(verts, faces=None, number_of_points=4000, seed=0):
+    """`calc_surface_geodesic(mesh, number_of_points=4000)` -- data_proc/common_ops.py:176-208.  `verts` may be a mesh
+    object with `.vertices` / `.triangles` (the reference's argument) or the vertex array with `faces` given."""
+    if faces is None:
+        verts, faces = np.asarray(verts.vertices), np.asarray(verts.triangles)
+    pts, nrm = sample_surface_poisson(verts, faces, number_of_points, seed)
+    return surface_geodesic(pts, nrm, verts)
+
+
+def get_geo_edges(surface_geodesic_matrix, remesh_obj_v=None, radius=0.06, max_nn=15, seed=None):
+    """`get_geo_edges` -- data_proc/common_ops.py:214-226 with the reference's subset rule: a vertex with more than max_nn
+    ball members keeps `np.random.choice(members, max_nn, replace=False)`, drawn from numpy's global generator in vertex
+    order exactly like the reference (seed it the same way -- or pass `seed` -- to reproduce a dataset's `_geo_e.txt`).
+    Ball membership comes from the GPU; only the overflowing vertices' rows visit the host for the draw."""
+    lib = _lib.load()
+    dev, as_numpy = _device_of(surface_geodesic_matrix)
+    g = _to_dev(surface_geodesic_matrix, dev)
+    nv = g.shape[0]
+    edges = torch.empty(nv, max_nn, 2, dtype=torch.int64, device=dev)
+    deg = torch.empty(nv, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.morig_geo_ball_edges(g.data_ptr(), nv, float(radius), int(max_nn), edges.data_ptr(), deg.data_ptr(),
+                                            _lib.stream_ptr()), "morig_geo_ball_edges")
+    deg_h = deg.cpu().numpy()
+    edges_h = edges.cpu().numpy()
+    full = np.nonzero(deg_h == max_nn)[0]                                        # candidates for "more than max_nn"
+    rows = g[torch.from_numpy(full).to(dev)].cpu().numpy() if len(full) else np.zeros((0, nv))
+    if seed is not None:
+        np.random.seed(seed)
+    out, k = [], 0
+    for i in range(nv):
+        if k < len(full) and full[k] == i:
+            row = rows[k].copy()
+            row[i] += 10.0                                                       # :218 no self edge
+            ball = np.argwhere(row <= radius).squeeze(1)
+            if len(ball) > max_nn:
+                ball = np.random.choice(ball, max_nn, replace=False)             # :221
+            out.append(np.stack([np.full(len(ball), i, dtype=np.int64), ball.astype(np.int64)], axis=1))
+            k += 1
+        else:
+            out.append(edges_h[i, : deg_h[i]])
+    res = np.concatenate(out, axis=0) if out else np.zeros((0, 2), dtype=np.int64)
+    return res if as_numpy else torch.from_numpy(res).to(dev)

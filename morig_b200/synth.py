@@ -205,6 +205,27 @@ def make_batch(n_graphs: int, n_vtx: int, seed: int = 0, with_skin: bool = False
     return collate(meshes)
 
 
+def make_deform_batch(n_graphs: int, n_vtx: int, n_pts: int, seed: int = 0) -> Batch:
+    """synthetic input of the upstream flow producer (CorrNet / DeformNet, models/deformnet.py:42): a mesh batch
+    (`vtx`, edge lists, `vtx_batch`) plus an observed partial point cloud per mesh (`pts`, `pts_batch`): the key-frame-1
+    positions of the vertices on the +z side, sub-sampled to n_pts points with N(0, 0.002) noise"""
+    meshes, pts, pb = [], [], []
+    for b in range(n_graphs):
+        m = make_mesh(n_vtx, seed + b)
+        meshes.append(m)
+        rng = np.random.default_rng(1000 + seed + b)
+        moved = m["pos"] + m["flow"][:, 0:3]
+        order = np.argsort(-moved[:, 2], kind="stable")                  # most "visible" (largest z) first
+        pick = np.sort(order[: max(n_pts, 1)]) if n_pts <= n_vtx else np.sort(rng.integers(0, n_vtx, n_pts))
+        cloud = moved[pick] + rng.normal(0.0, 0.002, (len(pick), 3))
+        pts.append(cloud.astype(np.float32))
+        pb.append(np.full(len(pick), b, dtype=np.int64))
+    d = collate(meshes)
+    return Batch(vtx=d.pos, tpl_edge_index=d.tpl_edge_index, geo_edge_index=d.geo_edge_index, vtx_batch=d.batch,
+                 pts=torch.from_numpy(np.concatenate(pts)), pts_batch=torch.from_numpy(np.concatenate(pb)),
+                 num_graphs=n_graphs)
+
+
 def randomize_bn_(model: torch.nn.Module, seed: int = 0) -> None:
     """Make eval-mode BatchNorm non-trivial (SURVEY.md §8(d) 'Weights'): random running stats and
     affine terms, 10% of the scales negative so max cannot be commuted through BN."""
@@ -241,6 +262,8 @@ def seeded_state_dict(model: torch.nn.Module, seed: int = 0) -> dict:
             val = torch.rand(shape, generator=g) + 0.5
         elif leaf == "cls_token":
             val = torch.randn(shape, generator=g)
+        elif leaf == "temprature":                             # CorrNet's learnable infoNCE temperature: keep its init
+            val = ref.clone()
         elif ref.dim() == 2:                                   # Linear weight [out, in]
             bound = 1.0 / (shape[1] ** 0.5)
             val = (torch.rand(shape, generator=g) * 2 - 1) * bound

@@ -70,3 +70,17 @@ def sorted_rows(e):
     the reference in python-set iteration order)"""
     e = np.asarray(e, dtype=np.int64)
     return e[np.lexsort((e[:, 1], e[:, 0]))]
+
+
+def geo_edges_random_subset(surface_geodesic, radius=0.06, max_nn=15):
+    """`get_geo_edges` (data_proc/common_ops.py:214-226) after the geodesic matrix, WITH the reference's subset rule:
+    `np.random.choice(members, max_nn, replace=False)` from numpy's global generator, in vertex order"""
+    g = np.array(surface_geodesic, dtype=np.float64)
+    g += 10.0 * np.eye(len(g))
+    edge_index = []
+    for i in range(len(g)):
+        ball = np.argwhere(g[i, :] <= radius).squeeze(1)
+        if len(ball) > max_nn:
+            ball = np.random.choice(ball, max_nn, replace=False)
+        edge_index.append(np.concatenate((np.repeat(i, len(ball))[:, np.newaxis], ball[:, np.newaxis]), axis=1))
+    return np.concatenate(edge_index, axis=0)

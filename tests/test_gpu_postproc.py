@@ -89,8 +89,8 @@ def test_info_nce_losses_forward_and_backward():
     g2 = L.infoNCE(vd, pd, c1.to(DEV), c2.to(DEV), batch.to(DEV), pb.to(DEV), cb1.to(DEV), cb2.to(DEV), 0.07)
     g2.backward()
     assert abs(float(g2) - float(w2)) < 2e-5 * max(1.0, abs(float(w2)))
-    assert (vd.grad.cpu() - vr.grad).abs().max() < 2e-5 * max(1.0, float(vr.grad.abs().max()))
-    assert (pd.grad.cpu() - pr.grad).abs().max() < 2e-5 * max(1.0, float(pr.grad.abs().max()))
+    assert (vd.grad.cpu() - vr.grad).abs().max() < 1e-4 * max(1.0, float(vr.grad.abs().max()))
+    assert (pd.grad.cpu() - pr.grad).abs().max() < 1e-4 * max(1.0, float(pr.grad.abs().max()))
     assert torch.isfinite(got) and torch.isfinite(f.grad).all() and float(got) > 0
 
 

@@ -208,6 +208,12 @@ def test_geodesic_port_is_bit_identical_to_unmodified_reference(s, v, seed, two)
         pass
     ref_edges = co.get_geo_edges(Remeshed(verts, pts, nrm), radius=0.1, max_nn=v)
     assert np.array_equal(geodesic_port.geo_ball_edges(ref, 0.1, v), ref_edges)
+    # ... and with balls that overflow max_nn: the reference's seeded random subset, drawn in vertex order
+    np.random.seed(12)
+    ref_edges = co.get_geo_edges(Remeshed(verts, pts, nrm), radius=0.3, max_nn=4)
+    np.random.seed(12)
+    got = geodesic_port.geo_edges_random_subset(ref, 0.3, 4)
+    assert np.array_equal(got, ref_edges) and np.bincount(got[:, 0]).max() == 4
 
 
 def test_geodesic_port_against_floyd_warshall():
