@@ -335,6 +335,11 @@ MORIG_API int    morig_bn_train_fwd(const float *x, int32_t ldx, int32_t R, int3
                                     float *invstd, float *scale, float *shift, float *y, int32_t ldy, void *ws,
                                     size_t ws_bytes, void *stream);
 
+/* y = x * scale[c] + shift[c] (per column): the apply step of the BatchNorm above on its own; also the 1 / T of the
+ * key-frame mean (models/rignet.py:92-93) in the training path */
+MORIG_API int    morig_col_affine(const float *x, int32_t ldx, int32_t R, int32_t C, const float *scale, const float *shift, float *y,
+                                  int32_t ldy, void *stream);
+
 /* backward of [ReLU ->] BatchNorm(train) given dy and the saved BatchNorm input x (= ReLU output):
  *   dgamma = sum dy * xhat, dbeta = sum dy, dz = [x > 0 or !relu] * gamma * invstd * (dy - mean(dy) - xhat * mean(dy * xhat))
  * coef: scratch [3 C].  dz may alias dy. */

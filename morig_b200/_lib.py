@@ -114,6 +114,7 @@ _SIGNATURES = {
     "morig_bn_train_fwd": (C.c_int, [_P, _I, _I, _I, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P, _I, _P,
                                      C.c_size_t, _P]),
     "morig_bn_relu_bwd": (C.c_int, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P, C.c_size_t, _P]),
+    "morig_col_affine": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _I, _P]),
     "morig_relu_bwd": (C.c_int, [_P, _I, _P, _I, _I, _I, _P, _I, _P]),
     "morig_edge_gather_relu": (C.c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _P, _I, _P]),
     "morig_edge_gather_relu_bwd": (C.c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _P, _I, _P]),

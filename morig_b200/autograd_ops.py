@@ -167,3 +167,42 @@ class ConcatCols(torch.autograd.Function):
             outs.append(dout[:, off:off + w] if ctx.needs_input_grad[i] else None)     # views: consumers take row strides
             off += w
         return tuple(outs)
+
+
+class FrameMean(torch.autograd.Function):
+    """mean over the key-frame axis of x [N, T, C] (aggr_method='mean', models/rignet.py:92-93): per-vertex segment sums of
+    the [N * T, C] view, scaled by 1 / T (a power-of-two-free constant: applied through the BatchNorm-affine kernel)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        n, t, c = x.shape
+        ctx.shape = (n, t, c)
+        ptr = torch.arange(0, n * t + 1, t, dtype=torch.int32, device=x.device)
+        s = T.seg_sum(x.reshape(n * t, c), ptr, n)
+        return T.scale_cols(s, 1.0 / t)
+
+    @staticmethod
+    def backward(ctx, dout):
+        n, t, c = ctx.shape
+        idx = torch.arange(n, dtype=torch.int32, device=dout.device).repeat_interleave(t)
+        return T.row_gather(T.scale_cols(dout, 1.0 / t), idx).view(n, t, c)
+
+
+class FrameMax(torch.autograd.Function):
+    """max over the key-frame axis of x [N, T, C] (aggr_method='max', models/rignet.py:94-95; torch.max(dim=1) sends the
+    gradient to the first maximal key-frame)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        n, t, c = x.shape
+        ctx.shape = (n, t, c)
+        ptr = torch.arange(0, n * t + 1, t, dtype=torch.int32, device=x.device)
+        out, arg = T.segmax_fwd(x.reshape(n * t, c), ptr, n)
+        ctx.save_for_backward(arg)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (arg,) = ctx.saved_tensors
+        n, t, c = ctx.shape
+        return T.segmax_bwd(dout, arg, n * t).view(n, t, c)

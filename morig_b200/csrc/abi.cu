@@ -1,5 +1,6 @@
 // C-ABI plumbing: version, error string, device info.
 #include <stdarg.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace morig {
@@ -10,6 +11,15 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MORIG_NO_PDL");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 int sm_count() {

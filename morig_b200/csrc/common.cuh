@@ -57,6 +57,29 @@ __device__ __forceinline__ void amax_commit(float *amax, float v) {
     if (amax && (threadIdx.x & 31) == 0 && v > 0.f) atomicMax(reinterpret_cast<int *>(amax), __float_as_int(v));
 }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------------
+// The forward is ~70 dependent launches in one stream (or one replayed CUDA graph); with the launch attribute below the
+// next kernel's CTAs may become resident as soon as every CTA of the current one has executed pdl_trigger() (or exited)
+// and SM resources free up, run their prologue (barrier / TMEM set-up, parameter staging) and then block in pdl_wait()
+// until the predecessor grid has completed and flushed its memory.  Rule kept by every kernel of this library:
+// NO global memory is read or written before pdl_wait() except launch parameters -- so the overlap can never be observed.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();      // false when MORIG_NO_PDL=1 (A/B switch)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

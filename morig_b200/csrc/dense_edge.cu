@@ -45,6 +45,9 @@ __global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const __grid
     constexpr uint32_t FULL = 0xffffffffu;
     __shared__ float2 s_bias[H / 2], s_scale[H / 2], s_shift[H / 2];
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    pdl_trigger();
+    // the branch's weights and per-channel constants are parameters (packed before the forward started): staging them
+    // overlaps the predecessor's tail; pdl_wait() comes before the first read of data produced inside the forward
     for (int i = threadIdx.x; i < H; i += blockDim.x) {
         reinterpret_cast<float *>(s_bias)[i] = d.b1[i];
         reinterpret_cast<float *>(s_scale)[i] = d.scale[i];
@@ -68,6 +71,7 @@ __global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const __grid
     // power-of-two operand scales: max|W1| * ws in [2^14, 2^15); relu(P + Q) * as < 2^15
     auto pow2 = [](int sh) { sh = sh < -100 ? -100 : (sh > 100 ? 100 : sh); return __uint_as_float((uint32_t)(sh + 127) << 23); };
     auto expo = [](float x) { int e = (int)((__float_as_uint(x) >> 23) & 0xffu); return (e == 0 || e == 255) ? 127 : e; };
+    pdl_wait();
     const int w_sh = 14 - (expo(wmax) - 127);
     const int a_sh = 14 - (expo(d.pq_amax ? *d.pq_amax : 1.f) - 126);
     const float w_scale = pow2(w_sh), a_scale = pow2(a_sh);
@@ -285,8 +289,7 @@ static int launch_edge_mma(const morig_edge_desc *descs, int count, cudaStream_t
     const long long want = ceil_div64(tiles, EDGE_MMA_THREADS / 32);
     long long cap = (long long)sm_count() * blocks_per_sm / count;                  // persistent: warps stride over tiles
     if (cap < 1) cap = 1;
-    edge_mma_kernel<H><<<dim3((unsigned)(want < cap ? want : cap), (unsigned)count), EDGE_MMA_THREADS, 0, stream>>>(b);
-    MORIG_LAUNCH_CHECK("edge_mma_kernel");
+    MORIG_CUDA(launch_pdl(edge_mma_kernel<H>, dim3((unsigned)(want < cap ? want : cap), (unsigned)count), dim3(EDGE_MMA_THREADS), 0, stream, b));
     return 0;
 }
 
@@ -319,6 +322,8 @@ constexpr int SKINNY_THREADS = SKINNY_COLS * SKINNY_KL;
 __global__ void __cluster_dims__(1, SKINNY_SPLIT, 1) __launch_bounds__(SKINNY_THREADS) dense_skinny_kernel(const GemmP p) {
     extern __shared__ float s_mem[];                // [KL][M][COLS] k-lane partials; then [M][COLS] CTA partial at the front
     const int col = threadIdx.x % SKINNY_COLS, kl = threadIdx.x / SKINNY_COLS;
+    pdl_trigger();
+    pdl_wait();
     const int rank = blockIdx.y;                    // cluster dims (1, 8, 1): rank in the cluster == blockIdx.y
     const int n = blockIdx.x * SKINNY_COLS + col;
     const bool n_ok = n < p.N;
@@ -394,6 +399,8 @@ __global__ void __cluster_dims__(1, SKINNY_SPLIT, 1) __launch_bounds__(SKINNY_TH
 constexpr int SMALLK_MAX = 8;
 
 __global__ void __launch_bounds__(256) dense_smallk_kernel(const GemmP p) {
+    pdl_trigger();
+    pdl_wait();
     const int nq = p.N >> 2;                                    // N % 4 == 0 (checked by the launcher)
     const long long total = (long long)p.M * nq, stride = (long long)gridDim.x * blockDim.x;
     float am = 0.f;
@@ -435,8 +442,8 @@ static int launch_gemm(const GemmP &p, dim3 grid, cudaStream_t stream, const cha
         MORIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured_dev = dev;
     }
-    kern<<<grid, GEMM_THREADS, smem, stream>>>(p);
-    MORIG_LAUNCH_CHECK(name);
+    MORIG_CUDA(launch_pdl(kern, grid, dim3(GEMM_THREADS), smem, stream, p));
+    (void)name;
     return 0;
 }
 
@@ -484,13 +491,15 @@ static int launch_tc2(const GemmP &p, const void *blob, int frames, cudaStream_t
     cfg.blockDim = dim3(tc::THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     MORIG_CUDA(cudaLaunchKernelEx(&cfg, kern, tp));
     MORIG_LAUNCH_CHECK(name);
     return 0;
@@ -523,8 +532,8 @@ static int launch_tc(const GemmP &p, const void *blob, int frames, cudaStream_t 
     const long long tiles = (long long)tp.ntn * tp.ntm * frames;
     const int sms = sm_count();
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);     // persistent: one CTA per SM
-    kern<<<grid, tc::THREADS, smem, stream>>>(tp);
-    MORIG_LAUNCH_CHECK(name);
+    MORIG_CUDA(launch_pdl(kern, dim3(grid), dim3(tc::THREADS), (size_t)smem, stream, tp));
+    (void)name;
     return 0;
 }
 
@@ -574,14 +583,12 @@ extern "C" MORIG_API int morig_dense_fwd(const morig_dense_desc *d, void *stream
     if (d->K <= SMALLK_MAX && d->N % 4 == 0 && p.c_vec && d->C && !d->pool && !d->rowbias && aligned16(d->W) &&
         (!d->bias || aligned16(d->bias)) && (!d->scale || (d->shift && aligned16(d->scale) && aligned16(d->shift)))) {
         const long long blocks = ceil_div64((long long)d->M * (d->N / 4), 256), cap = (long long)sm_count() * 8;
-        dense_smallk_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(p);
-        MORIG_LAUNCH_CHECK("dense_smallk_kernel");
+        MORIG_CUDA(launch_pdl(dense_smallk_kernel, dim3((unsigned)(blocks < cap ? blocks : cap)), dim3(256), 0, stream, p));
         return 0;
     }
     if (d->M <= SKINNY_MAX_M && d->K >= 64 && p.a_vec && d->C && !d->pool && !d->rowbias) {
         const size_t smem = (size_t)SKINNY_KL * d->M * SKINNY_COLS * sizeof(float);
-        dense_skinny_kernel<<<dim3(ceil_div(d->N, SKINNY_COLS), SKINNY_SPLIT), SKINNY_THREADS, smem, stream>>>(p);
-        MORIG_LAUNCH_CHECK("dense_skinny_kernel");
+        MORIG_CUDA(launch_pdl(dense_skinny_kernel, dim3(ceil_div(d->N, SKINNY_COLS), SKINNY_SPLIT), dim3(SKINNY_THREADS), smem, stream, p));
         return 0;
     }
     if (d->Wtc && p.a_vec && !tc_disabled()) {

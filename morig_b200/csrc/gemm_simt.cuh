@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_simt_kernel(const GemmP 
     const int n0 = blockIdx.y * BN;
     const int frame = (AMODE == AMODE_GATHER) ? blockIdx.z : 0;
 
+    pdl_trigger();
+    pdl_wait();
     int M = p.M;
     if (AMODE == AMODE_GATHER) {
         M = p.rowptr[p.n_vtx_frame];                // E' (device side)

@@ -731,16 +731,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(aux + AUX_TMEM_PTR);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int M = p.M, ntm = tp.ntm;
-    if (AMODE == AMODE_GATHER) {
-        M = p.rowptr[p.n_vtx_frame];                 // E' lives on the device only
-        ntm = (M + BM - 1) / BM;
-    }
-    TileMap tm;
-    tm.ntn = tp.ntn; tm.ntm = ntm; tm.total = tp.ntn * ntm * tp.frames;
-    tm.first = blockIdx.x; tm.step = gridDim.x; tm.mult = 1; tm.rank = 0;
-    float a_scale, inv;
-    operand_scales<KIND>(p, AMODE == AMODE_GATHER, a_scale, inv);
+    pdl_trigger();                                   // the next kernel of the stream may start its own set-up
 
     if (warp == CONTROL_WARP) {
         if (lane == 0) {
@@ -762,6 +753,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above only touched shared memory / TMEM: from here on the predecessor's results are needed
+    pdl_wait();
+    int M = p.M, ntm = tp.ntm;
+    if (AMODE == AMODE_GATHER) {
+        M = p.rowptr[p.n_vtx_frame];                 // E' lives on the device only
+        ntm = (M + BM - 1) / BM;
+    }
+    TileMap tm;
+    tm.ntn = tp.ntn; tm.ntm = ntm; tm.total = tp.ntn * ntm * tp.frames;
+    tm.first = blockIdx.x; tm.step = gridDim.x; tm.mult = 1; tm.rank = 0;
+    float a_scale, inv;
+    operand_scales<KIND>(p, AMODE == AMODE_GATHER, a_scale, inv);
 
     if (warp >= CONTROL_WARP) {
         // ================= control warp: B bulk copies + MMA issue (one elected lane) =================
@@ -916,14 +919,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
-    int M = p.M;
-    if (AMODE == AMODE_GATHER) M = p.rowptr[p.n_vtx_frame];
-    const int ntm = (M + BM - 1) / BM;
-    TileMap tm;
-    tm.ntn = tp.ntn; tm.ntm = (ntm + 1) / 2; tm.total = tp.ntn * tm.ntm * tp.frames;
-    tm.first = blockIdx.x >> 1; tm.step = gridDim.x >> 1; tm.mult = 2; tm.rank = (int)rank;
-    float a_scale, inv;
-    operand_scales<KIND>(p, AMODE == AMODE_GATHER, a_scale, inv);
+    pdl_trigger();
 
     if (warp == CONTROL_WARP) {
         if (lane == 0) {
@@ -947,6 +943,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
     cluster_sync_all();                              // both CTAs' barriers exist before any remote arrival
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                      // set-up done; now the predecessor's results are needed
+    int M = p.M;
+    if (AMODE == AMODE_GATHER) M = p.rowptr[p.n_vtx_frame];
+    const int ntm = (M + BM - 1) / BM;
+    TileMap tm;
+    tm.ntn = tp.ntn; tm.ntm = (ntm + 1) / 2; tm.total = tp.ntn * tm.ntm * tp.frames;
+    tm.first = blockIdx.x >> 1; tm.step = gridDim.x >> 1; tm.mult = 2; tm.rank = (int)rank;
+    float a_scale, inv;
+    operand_scales<KIND>(p, AMODE == AMODE_GATHER, a_scale, inv);
 
     if (warp >= CONTROL_WARP) {
         reg_dec<REGS_CONTROL>();

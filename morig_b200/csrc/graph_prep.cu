@@ -17,6 +17,8 @@ namespace morig {
 __global__ void gp_keys_kernel(const int64_t *__restrict__ ei, int64_t E, int32_t n, int32_t *__restrict__ keys,
                                int32_t *__restrict__ vals) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (e >= E + n) return;
     if (e < E) {
         const int64_t j = ei[e], i = ei[E + e];
@@ -30,6 +32,8 @@ __global__ void gp_keys_kernel(const int64_t *__restrict__ ei, int64_t E, int32_
 
 __global__ void gp_rowptr_kernel(const int32_t *__restrict__ tgt, int32_t total, int32_t n, int32_t *__restrict__ rowptr) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (v > n) return;
     int lo = 0, hi = total;                          // first slot with tgt[slot] >= v
     while (lo < hi) {
@@ -135,12 +139,10 @@ extern "C" MORIG_API int morig_graph_prep(const int64_t *edge_index, int64_t E, 
     void *temp = (void *)(((uintptr_t)(vals + total) + 255) & ~(uintptr_t)255);
     size_t temp_bytes = sort_temp_bytes(total, N);
     const int T = 256;
-    gp_keys_kernel<<<(unsigned)ceil_div64(total, T), T, 0, stream>>>(edge_index, E, N, keys, vals);
-    MORIG_LAUNCH_CHECK("gp_keys_kernel");
+    MORIG_CUDA(launch_pdl(gp_keys_kernel, dim3((unsigned)ceil_div64(total, T)), dim3(T), 0, stream, edge_index, E, N, keys, vals));
     MORIG_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const int32_t *)keys, tgt, (const int32_t *)vals, col, (int)total, 0,
                                                key_bits(N), stream));
-    gp_rowptr_kernel<<<ceil_div(N + 1, T), T, 0, stream>>>(tgt, (int32_t)total, N, rowptr);
-    MORIG_LAUNCH_CHECK("gp_rowptr_kernel");
+    MORIG_CUDA(launch_pdl(gp_rowptr_kernel, dim3(ceil_div(N + 1, T)), dim3(T), 0, stream, (const int32_t *)tgt, (int32_t)total, N, rowptr));
     return 0;
 }
 

@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float *__restr
                                                             const float *__restrict__ c0, float *__restrict__ out,
                                                             int ldo, float *out_amax) {
     extern __shared__ float s_mv[];                 // [heads][C][D]  (transposed for lane-contiguous reads)
+    pdl_trigger();
+    pdl_wait();
     for (int idx = threadIdx.x; idx < heads * C * D; idx += blockDim.x) {
         const int h = idx / (C * D), rem = idx % (C * D), cc = rem / D, dd = rem % D;
         s_mv[idx] = Mv[((size_t)h * D + dd) * C + cc];
@@ -85,6 +87,8 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(float *x, int ldx, i
                                                             int n_frames) {
     const int lane = threadIdx.x & 31;
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    pdl_trigger();
+    pdl_wait();
     if (r >= R) return;
     float *row = x + (size_t)r * ldx;
     float ss = 0.f;
@@ -103,6 +107,8 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(float *x, int ldx, i
 
 __global__ void frame_reduce_kernel(const float *__restrict__ x, int N, int T, int C, int mode, float *out, int ldo) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (idx >= (int64_t)N * C) return;
     const int n = (int)(idx / C), c = (int)(idx % C);
     const float *src = x + (size_t)n * T * C + c;
@@ -117,6 +123,8 @@ __global__ void gather_cols_kernel(const float *__restrict__ src, int lds, int s
     // grid-stride over a bounded grid: the operand-range atomic below is per warp, all on one address
     const int64_t total = (int64_t)N * n_frames * C;
     float am = 0.f;
+    pdl_trigger();
+    pdl_wait();
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(idx % C);
         const int64_t r = idx / C;
@@ -133,6 +141,8 @@ __global__ void gather_cols_kernel(const float *__restrict__ src, int lds, int s
 __global__ void __launch_bounds__(256) absmax_kernel(const float *__restrict__ x, int ldx, int R, int C, float *amax) {
     const int64_t total = (int64_t)R * C;
     float am = 0.f;
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
         am = fmaxf(am, fabsf(x[(size_t)(i / C) * ldx + (i % C)]));
     amax_commit(amax, am);
@@ -141,6 +151,8 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float *__restrict__ x
 __global__ void fill_kernel(float *dst, int64_t n, float value) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    pdl_trigger();
+    pdl_wait();
     for (; i < n; i += stride) dst[i] = value;
 }
 
@@ -161,8 +173,8 @@ extern "C" MORIG_API int morig_temporal_attn_fwd(const float *x, int32_t N, int3
     const int T_ = 256;
     const int blocks = ceil_div(N * 32, T_);
     const int cap = sm_count() * 4;
-    temporal_attn_kernel<<<blocks < cap ? blocks : cap, T_, (size_t)heads * C * D * sizeof(float), stream>>>(
-        x, N, T, C, heads, D, u, l0, Mv, c0, out, ldo, out_amax);
+    MORIG_CUDA(launch_pdl(temporal_attn_kernel, dim3(blocks < cap ? blocks : cap), dim3(T_), (size_t)heads * C * D * sizeof(float), stream,
+                          x, N, T, C, heads, D, u, l0, Mv, c0, out, ldo, out_amax));
     MORIG_LAUNCH_CHECK("temporal_attn_kernel");
     return 0;
 }
@@ -172,7 +184,8 @@ extern "C" MORIG_API int morig_row_normalize(float *x, int32_t ldx, int32_t R, i
     cudaStream_t stream = (cudaStream_t)stream_;
     MORIG_CHECK_ARG(x && R > 0 && C > 0 && ldx >= C, "row_normalize: bad argument");
     MORIG_CHECK_ARG(!dst2 || (N > 0 && n_frames > 0 && R == N * n_frames), "row_normalize: R != N * n_frames");
-    row_normalize_kernel<<<(unsigned)ceil_div64((int64_t)R * 32, 256), 256, 0, stream>>>(x, ldx, R, C, dst2, N, n_frames);
+    MORIG_CUDA(launch_pdl(row_normalize_kernel, dim3((unsigned)ceil_div64((int64_t)R * 32, 256)), dim3(256), 0, stream, x, ldx, R, C, dst2, N,
+                          n_frames));
     MORIG_LAUNCH_CHECK("row_normalize_kernel");
     return 0;
 }
@@ -181,7 +194,7 @@ extern "C" MORIG_API int morig_frame_reduce(const float *x, int32_t N, int32_t T
                                   void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MORIG_CHECK_ARG(x && out && N > 0 && T > 0 && C > 0 && (mode == 0 || mode == 1), "frame_reduce: bad argument");
-    frame_reduce_kernel<<<(unsigned)ceil_div64((int64_t)N * C, 256), 256, 0, stream>>>(x, N, T, C, mode, out, ldo);
+    MORIG_CUDA(launch_pdl(frame_reduce_kernel, dim3((unsigned)ceil_div64((int64_t)N * C, 256)), dim3(256), 0, stream, x, N, T, C, mode, out, ldo));
     MORIG_LAUNCH_CHECK("frame_reduce_kernel");
     return 0;
 }
@@ -193,8 +206,8 @@ extern "C" MORIG_API int morig_gather_cols(const float *src, int32_t lds, int32_
     MORIG_CHECK_ARG(src && dst && C > 0 && N > 0 && n_frames > 0, "gather_cols: bad argument");
     const int64_t total = (int64_t)N * n_frames * C;
     const int64_t blocks = ceil_div64(total, 256), cap = (int64_t)sm_count() * 8;
-    gather_cols_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(src, lds, src_off, frame_stride, cols, C, N,
-                                                                                   n_frames, dst, ldd, dst_off, dst_amax);
+    MORIG_CUDA(launch_pdl(gather_cols_kernel, dim3((unsigned)(blocks < cap ? blocks : cap)), dim3(256), 0, stream, src, lds, src_off,
+                          frame_stride, cols, C, N, n_frames, dst, ldd, dst_off, dst_amax));
     MORIG_LAUNCH_CHECK("gather_cols_kernel");
     return 0;
 }
@@ -203,7 +216,7 @@ extern "C" MORIG_API int morig_absmax_f32(const float *x, int32_t ldx, int32_t R
     cudaStream_t stream = (cudaStream_t)stream_;
     MORIG_CHECK_ARG(x && amax && R > 0 && C > 0 && ldx >= C, "absmax_f32: bad argument");
     const int64_t blocks = ceil_div64((int64_t)R * C, 256 * 8);
-    absmax_kernel<<<(unsigned)(blocks > 148 * 8 ? 148 * 8 : blocks), 256, 0, stream>>>(x, ldx, R, C, amax);
+    MORIG_CUDA(launch_pdl(absmax_kernel, dim3((unsigned)(blocks > 148 * 8 ? 148 * 8 : blocks)), dim3(256), 0, stream, x, ldx, R, C, amax));
     MORIG_LAUNCH_CHECK("absmax_kernel");
     return 0;
 }
@@ -213,7 +226,7 @@ extern "C" MORIG_API int morig_fill_f32(float *dst, int64_t n, float value, void
     MORIG_CHECK_ARG(dst && n >= 0, "fill_f32: bad argument");
     if (n == 0) return 0;
     const int64_t blocks = ceil_div64(n, 256);
-    fill_kernel<<<(unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, stream>>>(dst, n, value);
+    MORIG_CUDA(launch_pdl(fill_kernel, dim3((unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks)), dim3(256), 0, stream, dst, n, value));
     MORIG_LAUNCH_CHECK("fill_kernel");
     return 0;
 }

@@ -694,6 +694,15 @@ extern "C" MORIG_API int morig_bn_train_fwd(const float *x, int32_t ldx, int32_t
     return 0;
 }
 
+extern "C" MORIG_API int morig_col_affine(const float *x, int32_t ldx, int32_t R, int32_t C, const float *scale, const float *shift,
+                                          float *y, int32_t ldy, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MORIG_CHECK_ARG(x && y && scale && shift && R > 0 && C > 0 && ldx >= C && ldy >= C, "col_affine: bad argument");
+    bn_apply_kernel<<<grid1d((int64_t)R * C, 256, 8), 256, 0, stream>>>(x, ldx, R, C, scale, shift, y, ldy);
+    MORIG_LAUNCH_CHECK("bn_apply_kernel");
+    return 0;
+}
+
 /* backward of Linear -> [ReLU] -> BatchNorm(train) at the BatchNorm input x (= ReLU output): dz, dgamma, dbeta */
 extern "C" MORIG_API int morig_bn_relu_bwd(const float *dy, int32_t lddy, const float *x, int32_t ldx, int32_t R, int32_t C,
                                            const float *gamma, const float *mean, const float *invstd, int32_t relu,

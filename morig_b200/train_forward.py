@@ -141,9 +141,15 @@ def motion_encode(model, pos, flow, gt, gg, binfo, dim):
 
 def aggregate(model, motion_all, aggr_method):
     """models/rignet.py:90-98"""
-    if aggr_method != "attn":
-        raise NotImplementedError("training with aggr_method 'mean' / 'max' is not built (the reference CLIs train with 'attn')")
-    return A.Normalize.apply(temporal_attn(model.aggragator, motion_all))
+    if aggr_method == "attn":
+        a = temporal_attn(model.aggragator, motion_all)
+    elif aggr_method == "mean":
+        a = A.FrameMean.apply(motion_all)
+    elif aggr_method == "max":
+        a = A.FrameMax.apply(motion_all)
+    else:
+        raise NotImplementedError(aggr_method)
+    return A.Normalize.apply(a)
 
 
 def _train_inputs(model, data, input_flow):

@@ -259,3 +259,18 @@ def concat_cols(xs) -> torch.Tensor:
                    "morig_gather_cols")
         off += x.shape[1]
     return out
+
+
+def scale_cols(x: torch.Tensor, factor: float) -> torch.Tensor:
+    """x * factor through the column-affine kernel of the dense engine's tiny-K path is overkill: one strided copy with a
+    per-column scale (morig_bn_train_fwd's apply step exposed through morig_gather_cols would not scale), so this uses
+    the BatchNorm-apply entry with scale = factor, shift = 0"""
+    x = mat(x)
+    R, C = x.shape
+    dev = x.device
+    sc = torch.full((C,), float(factor), dtype=torch.float32, device=dev)
+    sh = torch.zeros(C, dtype=torch.float32, device=dev)
+    y = torch.empty(R, C, dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().morig_col_affine(x.data_ptr(), _ld(x), R, C, sc.data_ptr(), sh.data_ptr(), y.data_ptr(), C, _sp()),
+               "morig_col_affine")
+    return y

@@ -260,6 +260,10 @@ def _t_attn_cls_bwd(q0, kc, vc, Kx, Vx, att, dout, d):
             dk[:, 1:].reshape(N, T, HD).contiguous(), dv[:, 1:].reshape(N, T, HD).contiguous())
 
 
+def _t_scale_cols(x, factor):
+    return x * factor
+
+
 def _t_concat_cols(xs):
     return torch.cat(list(xs), dim=1)
 
@@ -269,5 +273,5 @@ def install_train(monkeypatch):
     from morig_b200 import train_ops
     for name in ("linear_fwd", "matmul_nn", "wgrad", "bn_train_fwd", "bn_relu_bwd", "edge_gather_relu", "edge_gather_relu_bwd",
                  "segmax_fwd", "segmax_bwd", "seg_ptr", "row_gather", "seg_sum", "normalize_fwd", "normalize_bwd",
-                 "attn_cls_fwd", "attn_cls_bwd", "concat_cols"):
+                 "attn_cls_fwd", "attn_cls_bwd", "concat_cols", "scale_cols"):
         monkeypatch.setattr(train_ops, name, globals()["_t_" + name])

@@ -99,13 +99,17 @@ def test_training_oracle_matches_autograd_through_unmodified_reference(arch):
             assert torch.equal(v, o_bufs[k]), k
 
 
-@pytest.mark.parametrize("arch,b,n", [("jointnet_motion", 2, 64), ("masknet_motion", 1, 100), ("skinnet_motion", 2, 64)])
-def test_training_host_logic_is_exact_in_double_precision(emulated, arch, b, n):
+@pytest.mark.parametrize("arch,b,n,aggr", [("jointnet_motion", 2, 64, "attn"), ("masknet_motion", 1, 100, "attn"),
+                                           ("skinnet_motion", 2, 64, "attn"), ("jointnet_motion", 2, 49, "mean"),
+                                           ("masknet_motion", 2, 49, "max")])
+def test_training_host_logic_is_exact_in_double_precision(emulated, arch, b, n, aggr):
     """Whole networks, forward + backward + running statistics, evaluated in fp64 through this package's training
     path (autograd function composition, factorised first edge Linear, per-key-frame passes; C-ABI emulated on the
     CPU) against the fp64 training oracle.  In double precision there is no rounding chaos (argmax flips, nearly dead
     BatchNorm channels), so every parameter gradient must agree to 1e-8 of its range: an exact check of the logic."""
-    kw = synth.ARCH_KWARGS[arch]
+    kw = dict(synth.ARCH_KWARGS[arch])
+    if "aggr_method" in kw:
+        kw["aggr_method"] = aggr
     model = helpers.build_model(arch, kw, 3).double()
     sd0 = {k: v.clone() for k, v in model.state_dict().items()}
     data = synth.make_batch(b, n, seed=21, with_skin=(arch == "skinnet_motion"))
