@@ -331,7 +331,7 @@ def run_ours(args):
         d2h = sum(o.numel() * o.element_size() for o in outs)
         alg_flops_step = ALG_FLOP_PER_VERTEX * N_VTX * MESHES_PER_GPU
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
         if kstats and os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get(kstats[0]["kernel"])      # ncu dram bytes per launch of the dominant kernel

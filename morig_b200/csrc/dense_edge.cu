@@ -1,6 +1,7 @@
 // Host launchers for the tile engines (vertex dense layers, fused EdgeConv branch) and the narrow-channel EdgeConv
 // branch kernel (H <= 32: warp per 32 CSR slots, mma.sync split-fp16, in-register segmented max).
 #include <stdlib.h>
+#include <cuda.h>
 #include "gemm_tc.cuh"
 
 namespace morig {
@@ -35,9 +36,23 @@ constexpr int EDGE_BATCH_MAX = 4;
 // several branches of the same width on the same graph (e.g. the pos branches of the three GCUs of a GCNRig, which
 // all read the one pqpos buffer) share a launch: blockIdx.y selects the branch
 struct EdgeBatch { morig_edge_desc d[EDGE_BATCH_MAX]; };
+// TMA variant: one tensor map per branch over its PQ buffer ([rows, ldpq] fp32, box = H columns x 1 row, used with
+// tile::gather4: four arbitrary rows per instruction)
+struct alignas(64) EdgeMaps { CUtensorMap m[EDGE_BATCH_MAX]; };
 
-template <int H>
-__global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const __grid_constant__ EdgeBatch batch) {
+// cp.async.bulk.tensor ... tile::gather4: rows r0..r3 of the 2-D tensor, columns [c0, c0 + box) -> 4 consecutive smem rows
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *map, int c0, int r0, int r1, int r2, int r3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
+}
+
+// TMA = false: every lane gathers its own P / Q chunks with 16-byte loads straight into MMA fragments.
+// TMA = true : the neighbour rows Q[col[e]] of a tile are staged in shared memory by the TMA engine (tile::gather4,
+//              4 rows per instruction, issued by the 8 group-leader lanes, completion on a per-warp mbarrier); two
+//              stages per warp, so the gather of tile i+1 is in flight while tile i is multiplied.
+template <int H, bool TMA>
+__global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const __grid_constant__ EdgeBatch batch,
+                                                                    const __grid_constant__ EdgeMaps maps) {
     const morig_edge_desc &d = batch.d[blockIdx.y];
     constexpr int KT = H / 16, NT = H / 8;          // k-tiles and n-tiles of the m16n8k16 shape
     constexpr int KPL = H / 4;                      // contraction values of one row held by one lane
@@ -129,7 +144,33 @@ __global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const __grid
     long long id = (long long)blockIdx.x * (EDGE_MMA_THREADS / 32) + (threadIdx.x >> 5);
     int nkey[4], ncj[4], next_;
     load_idx(id, nkey, ncj, next_);
-    for (; id < total; id += warps_total) {
+    // TMA staging: [warp][stage][P | Q][32 edges][H] floats + one mbarrier per (warp, stage)
+    extern __shared__ __align__(128) uint8_t tma_smem[];
+    constexpr uint32_t ROW_BYTES = H * 4, STAGE_BYTES = 32 * ROW_BYTES;      // the tile's 32 neighbour rows Q[col[e]]
+    const int wib = threadIdx.x >> 5;
+    const uint32_t stage0 = tc::smem_u32(tma_smem) + (uint32_t)wib * 2u * STAGE_BYTES;
+    const uint32_t bar0 = tc::smem_u32(tma_smem) + (uint32_t)(EDGE_MMA_THREADS / 32) * 2u * STAGE_BYTES + (uint32_t)wib * 16u;
+    auto issue = [&](long long tid_, const int (&k4)[4], const int (&c4)[4], int st) {
+        // group leaders (t == 0) each fetch the neighbour rows of their four edges; lane 0 announces the bytes.
+        // (The target rows P[tgt[e]] stay on the per-lane load path: consecutive edges share their target, so those
+        //  loads hit L1, which the TMA engine bypasses -- measured: staging P too costs 40 % more time.)
+        const uint32_t bar = bar0 + 8u * st;
+        (void)k4;
+        if (lane == 0) tc::mbar_arrive_expect_tx(bar, STAGE_BYTES);
+        __syncwarp();
+        if (t == 0) {
+            const int fbr = (int)(tid_ / n_tiles) * N;
+            const uint32_t dst = stage0 + (uint32_t)st * STAGE_BYTES + (uint32_t)(4 * g) * ROW_BYTES;
+            tma_gather4(dst, &maps.m[blockIdx.y], d.q_off, fbr + c4[0], fbr + c4[1], fbr + c4[2], fbr + c4[3], bar);
+        }
+    };
+    if (TMA) {
+        if (lane == 0) { tc::mbar_init(bar0, 1); tc::mbar_init(bar0 + 8u, 1); tc::fence_barrier_init(); }
+        __syncwarp();
+        if (id < total) issue(id, nkey, ncj, 0);
+    }
+    int it = 0;
+    for (; id < total; id += warps_total, ++it) {
         const int f = (int)(id / n_tiles);
         const size_t fb = (size_t)f * N;
         int key[4], cj[4];
@@ -139,6 +180,32 @@ __global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const __grid
         load_idx(id + warps_total, nkey, ncj, next_);
         // ---- gather: x[j] = relu(P[tgt] + Q[col]), this lane's KPL channels ----
         float x[4][KPL];
+        if (TMA) {
+            const int st = it & 1;
+            float4 pa[4][KPL / 4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                 // target rows: per-lane loads (L1 hits inside a segment)
+                const float *pp = Pb + (fb + (size_t)max(key[j], 0)) * d.ldpq;
+#pragma unroll
+                for (int v = 0; v < KPL / 4; ++v) pa[j][v] = *reinterpret_cast<const float4 *>(pp + 4 * v);
+            }
+            tc::mbar_wait(bar0 + 8u * st, (uint32_t)((it >> 1) & 1));
+            const uint8_t *sp = tma_smem + ((size_t)wib * 2 + st) * STAGE_BYTES + (size_t)(4 * g) * ROW_BYTES + (size_t)KPL * t * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int v = 0; v < KPL / 4; ++v) {
+                    const float4 a = pa[j][v];
+                    const float4 b = *reinterpret_cast<const float4 *>(sp + j * ROW_BYTES + 16 * v);
+                    x[j][4 * v + 0] = fmaxf(a.x + b.x, 0.f) * a_scale;
+                    x[j][4 * v + 1] = fmaxf(a.y + b.y, 0.f) * a_scale;
+                    x[j][4 * v + 2] = fmaxf(a.z + b.z, 0.f) * a_scale;
+                    x[j][4 * v + 3] = fmaxf(a.w + b.w, 0.f) * a_scale;
+                }
+            }
+            __syncwarp();                               // every lane has read stage st^1's previous contents long ago;
+            if (id + warps_total < total) issue(id + warps_total, nkey, ncj, st ^ 1);   // refill the other stage now
+        } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float *pp = Pb + (fb + (size_t)max(key[j], 0)) * d.ldpq;
@@ -152,6 +219,7 @@ __global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const __grid
                 x[j][4 * v + 2] = fmaxf(a.z + b.z, 0.f) * a_scale;
                 x[j][4 * v + 3] = fmaxf(a.w + b.w, 0.f) * a_scale;
             }
+        }
         }
         // ---- segment structure of the tile (identical in the four lanes of a group) ----
         const int key_prev = __shfl_up_sync(FULL, key[3], 4);
@@ -275,22 +343,61 @@ __global__ void __launch_bounds__(EDGE_MMA_THREADS) edge_mma_kernel(const __grid
     amax_commit(d.out_amax, am);
 }
 
-template <int H>
-static int launch_edge_mma(const morig_edge_desc *descs, int count, cudaStream_t stream) {
+static bool narrow_tma_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MORIG_NARROW_TMA");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// tensor map of a PQ buffer for tile::gather4: dims {ldpq, rows} fp32, row stride ldpq * 4 bytes, box {H, 1}
+static int make_pq_map(CUtensorMap *map, const morig_edge_desc &d, int H) {
+    const cuuint64_t dims[2] = {(cuuint64_t)d.ldpq, (cuuint64_t)d.N * (cuuint64_t)(d.out_repeat == 1 ? d.n_frames : 1)};
+    const cuuint64_t strides[1] = {(cuuint64_t)d.ldpq * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)H, 1u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(d.PQ), dims, strides, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for PQ [%llu x %d]", (int)r, (unsigned long long)dims[1], d.ldpq);
+        return MORIG_E_BADARG;
+    }
+    return 0;
+}
+
+template <int H, bool TMA>
+static int launch_edge_mma_impl(const morig_edge_desc *descs, int count, cudaStream_t stream) {
+    constexpr size_t smem = TMA ? (size_t)(EDGE_MMA_THREADS / 32) * (2 * 32 * H * 4 + 16) : 0;
     static thread_local int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
-        MORIG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, edge_mma_kernel<H>, EDGE_MMA_THREADS, 0));
+        if (smem > 48 * 1024) MORIG_CUDA(cudaFuncSetAttribute(edge_mma_kernel<H, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MORIG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, edge_mma_kernel<H, TMA>, EDGE_MMA_THREADS, smem));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     EdgeBatch b;
-    for (int i = 0; i < EDGE_BATCH_MAX; ++i) b.d[i] = descs[i < count ? i : 0];
+    EdgeMaps maps;
+    for (int i = 0; i < EDGE_BATCH_MAX; ++i) {
+        b.d[i] = descs[i < count ? i : 0];
+        if (TMA) { if (int rc = make_pq_map(&maps.m[i], b.d[i], H)) return rc; }
+    }
     const morig_edge_desc &d = descs[0];
     const long long tiles = (long long)ceil_div(d.E_max, 32) * d.n_frames;          // upper bound (E' <= E_max)
     const long long want = ceil_div64(tiles, EDGE_MMA_THREADS / 32);
     long long cap = (long long)sm_count() * blocks_per_sm / count;                  // persistent: warps stride over tiles
     if (cap < 1) cap = 1;
-    MORIG_CUDA(launch_pdl(edge_mma_kernel<H>, dim3((unsigned)(want < cap ? want : cap), (unsigned)count), dim3(EDGE_MMA_THREADS), 0, stream, b));
+    MORIG_CUDA(launch_pdl(edge_mma_kernel<H, TMA>, dim3((unsigned)(want < cap ? want : cap), (unsigned)count), dim3(EDGE_MMA_THREADS), smem,
+                          stream, b, maps));
     return 0;
+}
+
+template <int H>
+static int launch_edge_mma(const morig_edge_desc *descs, int count, cudaStream_t stream) {
+    // TMA needs 16-byte aligned box starts (p_off / q_off multiples of 4 floats: checked by check_narrow) and row strides
+    if (narrow_tma_enabled() && descs[0].ldpq % 4 == 0) return launch_edge_mma_impl<H, true>(descs, count, stream);
+    return launch_edge_mma_impl<H, false>(descs, count, stream);
 }
 
 static int check_narrow(const morig_edge_desc *d) {

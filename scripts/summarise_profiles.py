@@ -27,7 +27,7 @@ lines = ["# ncu --metrics gpu__time_duration.sum --clock-control none, bench.py 
          f"# {'launches':>8s} {'total_us':>10s} {'share':>6s}  kernel"]
 for name, (n, us) in sorted(agg.items(), key=lambda x: -x[1][1]):
     lines.append(f"  {n:8d} {us:10.1f} {100 * us / tot:5.1f}%  {name[:150]}")
-open(os.path.join(PROF, "r01_launches_graph_step.txt"), "w").write("\n".join(lines) + "\n")
+open(os.path.join(PROF, "r02_launches_graph_step.txt"), "w").write("\n".join(lines) + "\n")
 
 # ---- full-set summary of the dominant kernels ----
 rows = list(csv.reader(open(os.path.join(OUT, "prof_kernels_raw.csv"))))
@@ -40,7 +40,9 @@ want = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram r
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
         ("launch__registers_per_thread", "registers/thread"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe active %"),
-        ("sm__inst_executed.sum", "warp instructions"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %")]
+        ("sm__inst_executed.sum", "warp instructions"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+        ("lts__t_bytes.sum", "L2 bytes"), ("lts__t_sectors_srcunit_tex_op_read.sum", "L2 read sectors (from L1/TEX)"),
+        ("l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum", "L1 global-load bytes")]
 labels = ["edgeconv H=256 E=278528 N=16384 frames=5", "edgeconv H=128 E=278528 N=16384 frames=5", "dense M=81920 N=1024 K=840",
           "edgeconv H=32 E=278528 N=16384 frames=5", "edgeconv H=16 E=278528 N=16384 frames=1"]
 out = ["# ncu --set full --clock-control none --import-source on, one launch of each dominant kernel shape (scripts/prof_kernels.py),",
@@ -57,7 +59,19 @@ for k, r in enumerate(data):
     if k < len(labels):
         traffic[labels[k]] = int(rd + wr)
     out.append("")
-open(os.path.join(PROF, "r01_ncu_dominant_kernels.txt"), "w").write("\n".join(out))
-json.dump(traffic, open(os.path.join(PROF, "r01_dram_traffic.json"), "w"), indent=1)
+# the narrow kernel again with the per-lane LDG gather (MORIG_NARROW_TMA=0) for the A/B of the TMA staging
+p2 = os.path.join(OUT, "prof_narrow_ldg_raw.csv")
+if os.path.exists(p2):
+    rows2 = list(csv.reader(open(p2)))
+    hdr2, units2, data2 = rows2[0], rows2[1], rows2[2:]
+    ix2 = {h: i for i, h in enumerate(hdr2)}
+    for r in data2[:1]:
+        out.append(f"## edgeconv H=32 E=278528 N=16384 frames=5, per-lane LDG.128 gather (MORIG_NARROW_TMA=0): {r[ix2['Kernel Name']][:90]}")
+        for m, lab in want:
+            if m in ix2:
+                out.append(f"  {lab:28s} {r[ix2[m]]} {units2[ix2[m]]}")
+        out.append("")
+open(os.path.join(PROF, "r02_ncu_dominant_kernels.txt"), "w").write("\n".join(out))
+json.dump(traffic, open(os.path.join(PROF, "r02_dram_traffic.json"), "w"), indent=1)
 print("\n".join(lines[:14]))
 print(traffic)
