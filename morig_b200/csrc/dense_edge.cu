@@ -358,9 +358,24 @@ static int make_pq_map(CUtensorMap *map, const morig_edge_desc &d, int H) {
     const cuuint64_t strides[1] = {(cuuint64_t)d.ldpq * sizeof(float)};
     const cuuint32_t box[2] = {(cuuint32_t)H, 1u};
     const cuuint32_t estr[2] = {1u, 1u};
-    const CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(d.PQ), dims, strides, box, estr,
-                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // the driver entry point is resolved through the runtime, so the library carries no link-time dependency on
+    // libcuda.so (it must load on machines without a driver: the build check runs on a CPU-only box)
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || !fp) {
+            set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return MORIG_E_BADARG;
+        }
+        encode = reinterpret_cast<encode_fn>(fp);
+    }
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(d.PQ), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) for PQ [%llu x %d]", (int)r, (unsigned long long)dims[1], d.ldpq);
         return MORIG_E_BADARG;

@@ -606,10 +606,17 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_
             const uint32_t heads = (tails << 1) | 1u;
             float *crow = (EPI == EPI_STORE && p.C && nl_ok) ? p.C + (size_t)rbase * p.ldc + nl : nullptr;
             // output offsets fit 32 bits (checked by the launchers)
+            const float sinv_l = scale_l < 0.f ? -inv : inv;
             auto flush = [&](int r, float m) {       // the segment ending at row r is complete (warp-uniform call)
                 const int k_seg = kblk[r];
                 if (k_seg < 0 || !nl_ok) return;
                 if (EPI == EPI_SEGMAX) {
+                    // m = max over the segment's rows of the raw accumulator = sigma * (h W1'), sigma = sign of the
+                    // BatchNorm scale (folded into the weight image).  bias -> ReLU -> BatchNorm affine is monotone in
+                    // sigma * z (non-decreasing for scale >= 0; for scale < 0 the extreme is the minimum of z, i.e. the
+                    // maximum of -z), also in floating point, so applying it ONCE to the segment's extreme gives bit for
+                    // bit the maximum of the per-edge values -- and the per-element epilogue shrinks to the running max.
+                    m = fmaf(fmaxf(fmaf(m, sinv_l, bias_l), 0.f), scale_l, shift_l);
                     float *dst = p.C + ((frame_base + (uint32_t)k_seg) * (uint32_t)p.ldc + (uint32_t)nl);
                     if ((first_cut && r == first_tail) || (last_cut && r == 31)) atomic_max_f32(dst, m);
                     else *dst = m;
@@ -626,18 +633,10 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_
             tr(13);
             float w[32];
             if (EPI == EPI_SEGMAX) {
-                // Straight-line code (32 independent rows give the FP pipes their instruction-level parallelism; a
-                // branch per row made every row its own dependent chain): bias -> ReLU -> BatchNorm affine, then the
-                // running max restarts at segment heads; the value after the last row of a segment is its maximum.
-                const float2 inv2 = make_float2(inv, inv), bias2 = make_float2(bias_l, bias_l);
-                const float2 scale2 = make_float2(scale_l, scale_l), shift2 = make_float2(shift_l, shift_l);
+                // Straight-line code over the RAW accumulators (see flush): the running max restarts at segment heads;
+                // the value after the last row of a segment is its extreme.
 #pragma unroll
-                for (int r = 0; r < 32; r += 2) {             // two rows per packed FFMA2
-                    float2 x = fma2(make_float2(__uint_as_float(v[r]), __uint_as_float(v[r + 1])), inv2, bias2);
-                    x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f);
-                    x = fma2(x, scale2, shift2);
-                    w[r] = x.x; w[r + 1] = x.y;
-                }
+                for (int r = 0; r < 32; ++r) w[r] = __uint_as_float(v[r]);
 #pragma unroll
                 for (int r = 1; r < 32; ++r) w[r] = ((heads >> r) & 1u) ? w[r] : fmaxf(w[r - 1], w[r]);
                 for (uint32_t tl = tails; tl; tl &= tl - 1) {

@@ -199,8 +199,18 @@ def _edge_mlp_parts(sd, prefix: str):
     br = EdgeBranch(W1=_pack_wt(w1f), b1=_vec(b1f), scale=_vec(s1), shift=_vec(t1), H=w1.shape[0])
     if br.H in (64, 128, 256):
         br.tc_kind = tc_kind()
-        br.W1tc, br.tc_w_inv = pack_tc_blob(w1f, br.H, tc_tile_n(br.H), br.tc_kind)
+        br.W1tc, br.tc_w_inv = pack_edge_tc_blob(w1f, br.scale, br.tc_kind)
     return wa - wb, wb, b0, br
+
+
+def pack_edge_tc_blob(w1f: torch.Tensor, scale32: torch.Tensor, kind: int):
+    """Tensor-core image of the second edge Linear for the fused EdgeConv kernel.  The kernel takes the segment's
+    maximum on the RAW accumulators and applies bias -> ReLU -> BatchNorm affine once per segment; that is exact because
+    the chain is monotone in sigma * z with sigma = sign of the BatchNorm scale (for a negative scale the largest output
+    comes from the smallest pre-activation), so the rows of channels with a negative (fp32) scale are negated here and
+    the kernel multiplies the extreme by sigma again (csrc/gemm_tc.cuh, EPI_SEGMAX flush)."""
+    sigma = torch.where(scale32.to(w1f.device) < 0, -1.0, 1.0).to(torch.float64)
+    return pack_tc_blob(w1f * sigma.unsqueeze(1), w1f.shape[0], tc_tile_n(w1f.shape[0]), kind)
 
 
 @dataclass

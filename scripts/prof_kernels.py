@@ -46,7 +46,7 @@ def edge_case(H, frames):
     vec = lambda: torch.randn(H, generator=gen).to(DEV)
     br = packing.EdgeBranch(W1=packing._pack_wt(W1).to(DEV), b1=vec(), scale=vec(), shift=vec(), H=H)
     if H >= 64:
-        blob, w_inv = packing.pack_tc_blob(W1, H, packing.tc_tile_n(H), KIND)
+        blob, w_inv = packing.pack_edge_tc_blob(W1, br.scale.cpu(), KIND)
         br.W1tc, br.tc_kind, br.tc_w_inv = blob.to(DEV), KIND, w_inv
     o = torch.full((n * frames, H), float("-inf"), device=DEV)
     profiled(lambda: engine.edgeconv(br, pq, 2 * H, 0, H, g, frames, o, H, 0))

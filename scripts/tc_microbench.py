@@ -62,7 +62,7 @@ def edge_case(H, frames):
     for name, kind in (("simt", None), ("tf32", packing.KIND_TF32), ("f16", packing.KIND_F16)):
         b = br
         if kind is not None:
-            blob, w_inv = packing.pack_tc_blob(W1, H, packing.tc_tile_n(H), kind)
+            blob, w_inv = packing.pack_edge_tc_blob(W1, br.scale.cpu(), kind)
             b = packing.EdgeBranch(W1=br.W1, b1=br.b1, scale=br.scale, shift=br.shift, H=H, W1tc=blob.to(DEV),
                                    tc_kind=kind, tc_w_inv=w_inv)
         o = torch.empty(n * frames, H, device=DEV)

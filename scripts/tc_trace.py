@@ -30,8 +30,9 @@ def make_case(which, kind, frames):
         pq = torch.randn(n * frames, 2 * H, generator=gen).to(DEV)
         W1 = torch.randn(H, H, generator=gen, dtype=torch.float64) / H ** 0.5
         vec = lambda: torch.randn(H, generator=gen).to(DEV)
-        blob, w_inv = packing.pack_tc_blob(W1, H, packing.tc_tile_n(H), kind)
-        br = packing.EdgeBranch(W1=packing._pack_wt(W1).to(DEV), b1=vec(), scale=vec(), shift=vec(), H=H,
+        scale = vec()
+        blob, w_inv = packing.pack_edge_tc_blob(W1, scale.cpu(), kind)
+        br = packing.EdgeBranch(W1=packing._pack_wt(W1).to(DEV), b1=vec(), scale=scale, shift=vec(), H=H,
                                 W1tc=blob.to(DEV), tc_kind=kind, tc_w_inv=w_inv)
         o = torch.empty(n * frames, H, device=DEV)
         return lambda: engine.edgeconv(br, pq, 2 * H, 0, H, g, frames, o, H, 0)

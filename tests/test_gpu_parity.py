@@ -157,7 +157,7 @@ def test_edgeconv_tensor_core_kinds(H, frames, mag, kind):
     W1 = torch.randn(H, H, generator=g, dtype=torch.float64) / H ** 0.5
     b1, sc, sh = (torch.randn(H, generator=g) * mag for _ in range(3))
     sc = sc / mag
-    blob, w_inv = packing.pack_tc_blob(W1, H, packing.tc_tile_n(H), kind)
+    blob, w_inv = packing.pack_edge_tc_blob(W1, sc, kind)
     br = packing.EdgeBranch(W1=packing._pack_wt(W1).to(DEV), b1=b1.to(DEV), scale=sc.to(DEV), shift=sh.to(DEV), H=H,
                             W1tc=blob.to(DEV), tc_kind=kind, tc_w_inv=w_inv)
     out = torch.full((n * frames, H), float("-inf"), device=DEV)
