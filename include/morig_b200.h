@@ -185,6 +185,8 @@ MORIG_API int morig_gather_cols(const float *src, int32_t lds, int32_t src_off, 
                       float *dst, int32_t ldd, int32_t dst_off, float *dst_amax, void *stream);
 
 MORIG_API int morig_fill_f32(float *dst, int64_t n, float value, void *stream);
+/* up to 8 (16-byte aligned) buffers in one launch: the -inf initialisation of all EdgeConv outputs of a GCNRig */
+MORIG_API int morig_fill_many_f32(float *const *dst, const int64_t *n, int32_t count, float value, void *stream);
 
 /* *amax = max(*amax, max |x[r, c]|) over r < R, c < C (row stride ldx): the operand range the fp16-split
  * tensor-core layers need for inputs that were not produced by this library (out_amax / dst_amax /

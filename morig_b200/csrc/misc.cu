@@ -156,9 +156,42 @@ __global__ void fill_kernel(float *dst, int64_t n, float value) {
     for (; i < n; i += stride) dst[i] = value;
 }
 
+// several buffers in one launch (the -inf initialisation of every EdgeConv output and pooled feature of a GCNRig)
+constexpr int FILL_MANY_MAX = 8;
+struct FillMany { float *dst[FILL_MANY_MAX]; long long n[FILL_MANY_MAX]; int count; float value; };
+
+__global__ void __launch_bounds__(256) fill_many_kernel(const FillMany f) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int k = 0; k < f.count; ++k) {
+        float4 *d4 = reinterpret_cast<float4 *>(f.dst[k]);
+        const int64_t n4 = f.n[k] >> 2;
+        const float4 v4 = make_float4(f.value, f.value, f.value, f.value);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) d4[i] = v4;
+        for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < f.n[k]; i += stride) f.dst[k][i] = f.value;
+    }
+}
+
 }  // namespace morig
 
 using namespace morig;
+
+extern "C" MORIG_API int morig_fill_many_f32(float *const *dst, const int64_t *n, int32_t count, float value, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MORIG_CHECK_ARG(dst && n && count >= 1 && count <= FILL_MANY_MAX, "fill_many_f32: count=%d unsupported (1..%d)", count, FILL_MANY_MAX);
+    FillMany f;
+    f.count = count; f.value = value;
+    int64_t total = 0;
+    for (int i = 0; i < count; ++i) {
+        MORIG_CHECK_ARG(dst[i] && n[i] >= 0 && (reinterpret_cast<uintptr_t>(dst[i]) & 15u) == 0, "fill_many_f32: buffer %d", i);
+        f.dst[i] = dst[i]; f.n[i] = n[i];
+        total += n[i];
+    }
+    const int64_t blocks = ceil_div64(total / 4 + 1, 256);
+    MORIG_CUDA(launch_pdl(fill_many_kernel, dim3((unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks)), dim3(256), 0, stream, f));
+    return 0;
+}
 
 extern "C" MORIG_API int morig_temporal_attn_fwd(const float *x, int32_t N, int32_t T, int32_t C, int32_t heads, int32_t D,
                                        const float *u, const float *l0, const float *Mv, const float *c0, float *out,

@@ -483,6 +483,18 @@ def fill(t: torch.Tensor, value: float) -> None:
     _end(tok)
 
 
+def fill_many(tensors, value: float) -> None:
+    """one launch for up to 8 buffers"""
+    tensors = list(tensors)
+    while tensors:
+        chunk, tensors = tensors[:8], tensors[8:]
+        ptrs = (ctypes.c_void_p * len(chunk))(*[t.data_ptr() for t in chunk])
+        sizes = (ctypes.c_int64 * len(chunk))(*[t.numel() for t in chunk])
+        tok = _begin("fill", 1, 0.0, 4.0 * sum(t.numel() for t in chunk)) if (_counter is not None or _timer is not None) else None
+        _lib.check(_lib.load().morig_fill_many_f32(ptrs, sizes, len(chunk), value, _lib.stream_ptr()), "morig_fill_many_f32")
+        _end(tok)
+
+
 def gather_cols(src: torch.Tensor, lds: int, src_off: int, frame_stride: int, cols: Optional[torch.Tensor], c: int,
                 n: int, n_frames: int, dst: torch.Tensor, ldd: int, dst_off: int) -> None:
     tok = _begin("gather_cols", 1, 0.0, 8.0 * n * n_frames * c) if (_counter is not None or _timer is not None) else None
@@ -509,18 +521,17 @@ def _gcu_buffers(ws: Workspace, tag: str, gp: GCUPack, R: int, dev):
     return ws.get(tag + ".pq", (R, 4 * H), dev), ws.get(tag + ".ec", (R, 2 * (H + Dp)), dev)
 
 
-def run_pos_branches(ws: Workspace, tags, gps, pqpos: torch.Tensor, gt: Graph, gg: Graph, n: int, n_frames: int) -> None:
+def run_pos_branches(ws: Workspace, tags, gps, pqpos: torch.Tensor, gt: Graph, gg: Graph, n: int, n_frames: int,
+                     also_fill=()) -> None:
     """The pos branches of several GCUs (models/basic_modules.py:194, one per edge set and GCU) only read `pos`, so
     they do not take part in the GCU chain: the EdgeConv outputs of all GCUs are initialised and, per edge set, the
     pos branches of all GCUs run as ONE launch (narrow branches) before the chain starts."""
     dev = pqpos.device
     R = n * n_frames
     ldpp = pqpos.shape[1]
-    ecs = []
-    for tag, gp in zip(tags, gps):
-        _, ec = _gcu_buffers(ws, tag, gp, R, dev)
-        fill(ec, NEG_INF)       # edge tiles merge the segments they cut with an (exact, ordered-int) atomic max
-        ecs.append(ec)
+    ecs = [_gcu_buffers(ws, tag, gp, R, dev)[1] for tag, gp in zip(tags, gps)]
+    # edge tiles merge the segments they cut with an (exact, ordered-int) atomic max: -inf start values, one launch
+    fill_many(ecs + list(also_fill), NEG_INF)
     for s, g in enumerate((gt, gg)):
         items = []
         for gp, ec in zip(gps, ecs):
@@ -573,11 +584,10 @@ def run_gcn_rig(ws: Workspace, tag: str, pk: GCNRigPack, pos: torch.Tensor, feat
     # GCU chain: input of gcu_1 is the feature block, of gcu_2 / gcu_3 the previous output block
     srcs = [(pk.feat_off, pk.gcus[0].pq_x.K), (pk.x_off[0], pk.gcus[1].pq_x.K), (pk.x_off[1], pk.gcus[2].pq_x.K)]
     tags = [f"{tag}.gcu{k}" for k in range(len(pk.gcus))]
-    run_pos_branches(ws, tags, pk.gcus, pqpos, gt, gg, n, n_frames)
+    xg = ws.get(tag + ".xg", (G, pk.glb.N), dev)
+    run_pos_branches(ws, tags, pk.gcus, pqpos, gt, gg, n, n_frames, also_fill=(xg,))
     for k, gp in enumerate(pk.gcus):
         run_gcu(ws, tags[k], gp, feat, srcs[k][0], ldf, srcs[k][1], gt, gg, n, n_frames, feat, pk.x_off[k], ldf)
-    xg = ws.get(tag + ".xg", (G, pk.glb.N), dev)
-    fill(xg, NEG_INF)
     dense(pk.glb, feat, 0, ldf, R, pool=xg, binfo=binfo, n_vtx=n)                     # x_4 is never stored
     gb = ws.get(tag + ".gb", (G, pk.t0_global.N), dev)
     dense(pk.t0_global, xg, 0, pk.glb.N, G, C=gb, ldc=pk.t0_global.N)
@@ -632,12 +642,11 @@ def run_skin(ws: Workspace, tag: str, pk: SkinPack, pos: torch.Tensor, skin_inpu
     c = pk.gcus[0].out
     xs = [ws.get(f"{tag}.x{k}", (n, c), dev) for k in range(3)]
     tags = [f"{tag}.gcu{k}" for k in range(3)]
-    run_pos_branches(ws, tags, pk.gcus, pqpos, gt, gg, n, 1)
+    xg = ws.get(tag + ".xg", (B, pk.g1.N), dev)
+    run_pos_branches(ws, tags, pk.gcus, pqpos, gt, gg, n, 1, also_fill=(xg,))
     run_gcu(ws, tags[0], pk.gcus[0], motion, 0, motion.shape[1], pk.gcus[0].pq_x.K, gt, gg, n, 1, xs[0], 0, c)
     g0 = ws.get(tag + ".g0", (n, pk.g0.N), dev)
     dense(pk.g0, xs[0], 0, c, n, C=g0, ldc=pk.g0.N)
-    xg = ws.get(tag + ".xg", (B, pk.g1.N), dev)
-    fill(xg, NEG_INF)
     dense(pk.g1, g0, 0, pk.g0.N, n, pool=xg, binfo=binfo, n_vtx=n)
     run_gcu(ws, tags[1], pk.gcus[1], xs[0], 0, c, c, gt, gg, n, 1, xs[1], 0, c)
     run_gcu(ws, tags[2], pk.gcus[2], xs[1], 0, c, c, gt, gg, n, 1, xs[2], 0, c)

@@ -79,6 +79,11 @@ def fill(t, value):
     t.fill_(value)
 
 
+def fill_many(tensors, value):
+    for t in tensors:
+        t.fill_(value)
+
+
 def gather_cols(src, lds, src_off, frame_stride, cols, c, n, n_frames, dst, ldd, dst_off):
     cc = torch.arange(c) if cols is None else cols.long()
     for f in range(n_frames):
@@ -116,7 +121,7 @@ def _require(t, name, dtype=torch.float32):
 
 
 def install(monkeypatch):
-    for name in ("graph_prep", "dense", "edgeconv", "edgeconv_batch", "fill", "gather_cols", "row_normalize", "temporal_attn",
+    for name in ("graph_prep", "dense", "edgeconv", "edgeconv_batch", "fill", "fill_many", "gather_cols", "row_normalize", "temporal_attn",
                  "frame_reduce"):
         monkeypatch.setattr(engine, name, globals()[name])
     monkeypatch.setattr(_lib, "require_cuda", _require)
