@@ -89,11 +89,11 @@ def _fixture(name):
 def test_deformnet_matches_fixture_of_the_unmodified_reference():
     """CorrNet (GCU chain + PointNet++ branch + visibility head) and DeformNet (cosine kNN interpolation + GCNDeform)
     against outputs of the reference's own modules (its GPU code branch, third-party operators restated)"""
-    import morig_b200.deformnet as dn
+    import morig_b200
     z, data = _fixture("deformnet_b2_v400_p300")
     chk = synth.make_deform_batch(int(z["graphs"]), int(z["n_vtx"]), int(z["n_pts"]), seed=int(z["data_seed"]))
     assert torch.equal(chk.vtx, data.vtx) and torch.equal(chk.pts, data.pts)          # generator is pinned
-    net = dn.deformnet(tau_nce=0.07, num_interp=5).eval()
+    net = morig_b200.deformnet(tau_nce=0.07, num_interp=5).eval()       # the factory, as models.__dict__["deformnet"]
     net.load_state_dict(synth.seeded_state_dict(net, int(z["weight_seed"])))
     net = net.to(DEV)
     torch.manual_seed(int(z["rng_seed"]))

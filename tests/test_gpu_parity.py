@@ -776,3 +776,65 @@ def test_integer_exact_kat_gcn_rig(F, O, kind, monkeypatch):
     bad = (got != want)
     assert not bad.any(), (f"{int(bad.sum())} of {bad.numel()} outputs differ, max |diff| = "
                            f"{float((got - want).abs().max())}, first at {bad.nonzero()[0].tolist()}")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_model_on_second_device_while_first_is_current():
+    """device guard: a model and its data on cuda:1 while cuda:0 is the current device (PyTorch ops guard implicitly; the
+    raw launches of this package must do it themselves) -- same bits as on cuda:0"""
+    kw = synth.ARCH_KWARGS["jointnet_motion"]
+    data = synth.make_batch(2, 256, seed=4)
+    torch.cuda.set_device(0)
+    m0 = helpers.build_model("jointnet_motion", kw, 5, "cuda:0")
+    m1 = helpers.build_model("jointnet_motion", kw, 5, "cuda:1")
+    with torch.no_grad():
+        a = m0(data.to("cuda:0"), data.pred_flow.to("cuda:0"))
+        for _ in range(3):                                   # plain launches, then the captured graph
+            b = m1(data.to("cuda:1"), data.pred_flow.to("cuda:1"))
+        torch.cuda.synchronize("cuda:1")
+    assert torch.cuda.current_device() == 0
+    for x, y in zip(a, b):
+        assert y.device == torch.device("cuda:1") and torch.equal(x.cpu(), y.cpu())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_nccl_gradient_all_reduce_two_gpus(tmp_path):
+    """dp.GradAllReduce over NCCL on two GPUs (one process per GPU): gradients equal the mean of the per-rank gradients"""
+    import subprocess
+    import sys
+    script = tmp_path / "ddp.py"
+    script.write_text('''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["MORIG_ROOT"]); sys.path.insert(0, os.path.join(os.environ["MORIG_ROOT"], "tests"))
+import helpers
+from morig_b200 import dp, synth
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+kw = synth.ARCH_KWARGS["masknet_motion"]
+model = helpers.build_model("masknet_motion", kw, 4, f"cuda:{rank}").train()
+ar = dp.GradAllReduce(model, bucket_mb=8.0)
+def grads(m, r):
+    d = synth.make_batch(1, 256, seed=300 + r).to(f"cuda:{rank}")
+    out = m(d, d.pred_flow)
+    (out[2].tanh().pow(2).mean() + out[1].sum() * 1e-3).backward()
+ar.zero_grad(); grads(model, rank); nbytes = ar.finish()
+got = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()
+want = None
+for r in range(world):
+    m = helpers.build_model("masknet_motion", kw, 4, f"cuda:{rank}").train()
+    grads(m, r)
+    g = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
+    want = g if want is None else want + g
+err = float((got - want / world).abs().max() / want.abs().max())
+if rank == 0:
+    print("RESULT", err, nbytes, got.numel())
+dist.destroy_process_group()
+''')
+    env = dict(os.environ, MORIG_ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29533", str(script)], env=env, capture_output=True, text=True, timeout=600)
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("RESULT")]
+    assert line, out.stderr[-2000:]
+    _, err, nbytes, numel = line[0].split()
+    assert float(err) < 1e-4 and int(nbytes) == 4 * int(numel)
