@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MORIG_ABI_VERSION 4
+#define MORIG_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define MORIG_API __attribute__((visibility("default")))
@@ -106,9 +106,21 @@ typedef struct morig_dense_desc {
     /* optional device scalar: atomically raised to max |C[r, n]| over everything this call stores
      * (bit pattern of a non-negative float; zero it before the first producer of a buffer)          */
     float         *c_amax;
+    /* optional: device scalar holding tc_w_inv (weight image packed on the device by morig_pack_tc_f16); overrides the
+     * by-value field when non-NULL */
+    const float   *tc_w_inv_dev;
 } morig_dense_desc;
 
 MORIG_API int morig_dense_fwd(const morig_dense_desc *d, void *stream);
+
+/* fp16-split tensor-core image of a Linear weight, built on the DEVICE (training: the weights change every step).
+ * Logical operand w_out_in [N, K]: element (n, k) = src[n * lds + k], or src[k * lds + n] when `transposed` (the input-
+ * gradient GEMM dX = dY W uses W^T).  Same byte layout as packing.pack_tc_blob(kind = F16): blob[n_tile][k_chunk of 64]
+ * [hi | lo][bn rows][16-byte chunk c ^ (row % 8)][8 fp16], values scaled by 2^j with max|W| 2^j in [2^14, 2^15);
+ * *w_inv_dev = 2^-j.  blob bytes = ceil(N / bn) * ceil(K / 64) * 2 * bn * 128;  amax_scratch: one float. */
+MORIG_API size_t morig_pack_tc_f16_bytes(int32_t N, int32_t K, int32_t bn);
+MORIG_API int    morig_pack_tc_f16(const float *src, int32_t lds, int32_t N, int32_t K, int32_t transposed, int32_t bn, void *blob,
+                                   float *w_inv_dev, float *amax_scratch, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused EdgeConv branch.  Replaces, for one of the two MLPs of EdgeConvMotion.message and for one

@@ -33,6 +33,7 @@ class DenseDesc(C.Structure):
         ("Wtc", c_f32p), ("tc_bn", C.c_int32),
         ("tc_kind", C.c_int32), ("tc_w_inv", C.c_float),
         ("a_amax", c_f32p), ("c_amax", c_f32p),
+        ("tc_w_inv_dev", c_f32p),
     ]
 
 
@@ -73,6 +74,9 @@ _SIGNATURES = {
                                    C.c_void_p]),
     "morig_knn_graph": (C.c_int, [c_f32p, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i64p, C.c_void_p]),
     "morig_dense_fwd": (C.c_int, [C.POINTER(DenseDesc), C.c_void_p]),
+    "morig_pack_tc_f16_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "morig_pack_tc_f16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
     "morig_edgeconv_fwd": (C.c_int, [C.POINTER(EdgeDesc), C.c_void_p]),
     "morig_edgeconv_fwd_batch": (C.c_int, [C.POINTER(EdgeDesc), C.c_int32, C.c_void_p]),
     "morig_surface_geodesic_workspace": (C.c_size_t, [C.c_int32, C.c_int32]),
@@ -132,7 +136,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
-ABI_VERSION = 4
+ABI_VERSION = 5
 _lib = None
 
 

@@ -674,9 +674,67 @@ static bool tc_disabled() {
     return v == 1;
 }
 
+// ---- device-side packer of the fp16-split weight image (training path) ------------------------------------------------
+__global__ void __launch_bounds__(256) pack_absmax_kernel(const float *__restrict__ src, int lds, int rows, int cols, float *amax) {
+    float am = 0.f;
+    const int64_t total = (int64_t)rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        am = fmaxf(am, fabsf(src[(size_t)(i / cols) * lds + (i % cols)]));
+    amax_commit(amax, am);
+}
+
+__global__ void __launch_bounds__(256) pack_tc_f16_kernel(const float *__restrict__ src, int lds, int N, int K, int transposed, int bn,
+                                                          int nK, int64_t total, __half *__restrict__ blob,
+                                                          const float *__restrict__ amax, float *__restrict__ w_inv_dev) {
+    // scale 2^j with max|W| 2^j in [2^14, 2^15)  (packing.pack_tc_blob: j = 14 - floor(log2(amax)))
+    const uint32_t bits = __float_as_uint(*amax);
+    int e = (int)((bits >> 23) & 0xffu);
+    int j = (e == 0 || e == 255) ? 0 : 14 - (e - 127);
+    j = j < -100 ? -100 : (j > 100 ? 100 : j);
+    const float scale = __uint_as_float((uint32_t)(j + 127) << 23);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *w_inv_dev = __uint_as_float((uint32_t)(127 - j) << 23);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        // idx enumerates the padded logical matrix [nt * bn, nK * 64] row-major
+        const int k = (int)(idx % (nK * 64));
+        const int n = (int)(idx / (nK * 64));
+        float w = 0.f;
+        if (n < N && k < K) w = transposed ? src[(size_t)k * lds + n] : src[(size_t)n * lds + k];
+        const float ws = w * scale;
+        const __half hi = __float2half_rn(ws);
+        const __half lo = __float2half_rn(ws - __half2float(hi));
+        const int nt = n / bn, r = n % bn, kc = k / 64, kk = k % 64, chunk = kk / 8, el = kk % 8;
+        const size_t base = ((((size_t)nt * nK + kc) * 2) * bn + r) * 64 + (size_t)((chunk ^ (r & 7)) * 8 + el);
+        blob[base] = hi;
+        blob[base + (size_t)bn * 64] = lo;
+    }
+}
+
 }  // namespace morig
 
 using namespace morig;
+
+extern "C" MORIG_API size_t morig_pack_tc_f16_bytes(int32_t N, int32_t K, int32_t bn) {
+    return (size_t)ceil_div(N, bn) * ceil_div(K, 64) * 2 * bn * 128;
+}
+
+extern "C" MORIG_API int morig_pack_tc_f16(const float *src, int32_t lds, int32_t N, int32_t K, int32_t transposed, int32_t bn, void *blob,
+                                           float *w_inv_dev, float *amax_scratch, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MORIG_CHECK_ARG(src && blob && w_inv_dev && amax_scratch && N > 0 && K > 0 && (bn == 128 || bn == 256), "pack_tc_f16: bad argument");
+    MORIG_CUDA(cudaMemsetAsync(amax_scratch, 0, sizeof(float), stream));
+    const int rows = transposed ? K : N, cols = transposed ? N : K;
+    const int64_t nel = (int64_t)rows * cols;
+    const int64_t b1 = ceil_div64(nel, 256 * 4);
+    pack_absmax_kernel<<<(unsigned)(b1 > 296 ? 296 : b1), 256, 0, stream>>>(src, lds, rows, cols, amax_scratch);
+    MORIG_LAUNCH_CHECK("pack_absmax_kernel");
+    const int nK = ceil_div(K, 64);
+    const int64_t total = (int64_t)ceil_div(N, bn) * bn * nK * 64;
+    const int64_t b2 = ceil_div64(total, 256);
+    pack_tc_f16_kernel<<<(unsigned)(b2 > 148 * 8 ? 148 * 8 : b2), 256, 0, stream>>>(src, lds, N, K, transposed, bn, nK, total,
+                                                                                 reinterpret_cast<__half *>(blob), amax_scratch, w_inv_dev);
+    MORIG_LAUNCH_CHECK("pack_tc_f16_kernel");
+    return 0;
+}
 
 // debug only (not declared in the public header): device buffer of 3 * 2048 * 2 int64 receiving the role timeline
 extern "C" MORIG_API void morig_debug_set_trace(long long *buf) { g_trace = buf; }
@@ -720,8 +778,9 @@ extern "C" MORIG_API int morig_dense_fwd(const morig_dense_desc *d, void *stream
         MORIG_CHECK_ARG((uint64_t)d->M * (uint64_t)(d->C ? d->ldc : 1) < (1ull << 32), "dense_fwd: M*ldc exceeds 32-bit element offsets");
         MORIG_CHECK_ARG(d->tc_kind == tc::KIND_TF32 || d->tc_kind == tc::KIND_F16, "dense_fwd: tc_kind=%d", d->tc_kind);
         if (d->tc_kind == tc::KIND_F16) {
-            MORIG_CHECK_ARG(d->a_amax && d->tc_w_inv > 0.f, "dense_fwd: the fp16 kind needs a_amax and tc_w_inv");
+            MORIG_CHECK_ARG(d->a_amax && (d->tc_w_inv > 0.f || d->tc_w_inv_dev), "dense_fwd: the fp16 kind needs a_amax and tc_w_inv");
             p.w_inv = d->tc_w_inv;
+            p.w_inv_dev = d->tc_w_inv_dev;
         }
         switch (d->tc_bn) {
             case 128: return launch_tc_kind<128, AMODE_PLAIN, EPI_STORE>(d->tc_kind, p, d->Wtc, 1, stream, "tc_dense<128>");

@@ -36,6 +36,7 @@ struct GemmP {
     // activations max-reduces |value| into *amax_out; an fp16 consumer derives its operand scale from *amax_in
     const float *amax_in; float *amax_out;
     float w_inv;                // 1 / (power-of-two scale baked into the fp16 weight image)
+    const float *w_inv_dev;     // ... or a device scalar holding it (image packed on the device: morig_pack_tc_f16)
 };
 
 constexpr int GEMM_THREADS = 256;

@@ -258,7 +258,7 @@ __device__ __forceinline__ void operand_scales(const GemmP &p, bool gather, floa
         int sh = (gather ? 14 : 15) - (e - 126);
         sh = sh < -100 ? -100 : (sh > 100 ? 100 : sh);
         a_scale = __uint_as_float((uint32_t)(sh + 127) << 23);
-        inv = __uint_as_float((uint32_t)(127 - sh) << 23) * p.w_inv;
+        inv = __uint_as_float((uint32_t)(127 - sh) << 23) * (p.w_inv_dev ? *p.w_inv_dev : p.w_inv);
     }
 }
 // packed fp32 pairs (sm_100 FADD2 / FMUL2): one instruction for two lanes of the producers' element-wise work

@@ -43,6 +43,43 @@ def _sp() -> int:
     return _lib.stream_ptr()
 
 
+def _tc_ok(M: int, K: int, N: int, A: torch.Tensor) -> bool:
+    """shapes the tcgen05 split-fp16 engine takes (csrc/gemm_tc.cuh); MORIG_TRAIN_TC=0 keeps training on the fp32 engine"""
+    import os
+    return (os.environ.get("MORIG_TRAIN_TC", "1") != "0" and M >= 256 and K >= 32 and K % 4 == 0 and N >= 16
+            and _ld(A) % 4 == 0 and A.data_ptr() % 16 == 0)
+
+
+def dense_tc(A: torch.Tensor, w: torch.Tensor, transposed: bool, n_out: int, k: int, bias: Optional[torch.Tensor],
+             relu: bool) -> torch.Tensor:
+    """C [M, n_out] = act(A [M, k] @ Wl^T + bias) on the tensor-core engine, Wl [n_out, k] = w (or w^T when `transposed`);
+    the fp16-split weight image is packed on the device (the weights change every optimisation step)"""
+    from . import engine, packing
+    lib = _lib.load()
+    A = mat(A)
+    M = A.shape[0]
+    dev = A.device
+    bn = packing.tc_tile_n(n_out)
+    w = mat(w)
+    blob = torch.empty(lib.morig_pack_tc_f16_bytes(n_out, k, bn), dtype=torch.uint8, device=dev)
+    scal = torch.empty(2, dtype=torch.float32, device=dev)                     # [w_inv, amax scratch]
+    _lib.check(lib.morig_pack_tc_f16(w.data_ptr(), _ld(w), n_out, k, 1 if transposed else 0, bn, blob.data_ptr(), scal.data_ptr(),
+                                     scal.data_ptr() + 4, _sp()), "morig_pack_tc_f16")
+    C_ = torch.empty(M, n_out, dtype=torch.float32, device=dev)
+    d = _lib.DenseDesc()
+    d.A, d.lda = A.data_ptr(), _ld(A)
+    d.W, d.ldw = blob.data_ptr(), _r4(n_out)                                    # (unused by the tensor-core path; must be valid)
+    d.bias = _lib.ptr(bias)
+    d.C, d.ldc = C_.data_ptr(), n_out
+    d.M, d.N, d.K = M, n_out, k
+    d.relu = 1 if relu else 0
+    d.Wtc, d.tc_bn, d.tc_kind, d.tc_w_inv = blob.data_ptr(), bn, packing.KIND_F16, 0.0
+    d.tc_w_inv_dev = scal.data_ptr()
+    d.a_amax = engine._amax_in(A, 0, _ld(A), M, k)
+    _lib.check(lib.morig_dense_fwd(ctypes.byref(d), _sp()), "morig_dense_fwd")
+    return C_
+
+
 def dense_ffma(A: torch.Tensor, Wt: torch.Tensor, n_out: int, bias: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
     """C [M, n_out] = act(A [M, K] @ Wt [K, ldw] + bias) on the fp32 CUDA-core engine (morig_dense_fwd without a
     tensor-core image)"""
@@ -72,13 +109,20 @@ def transpose_pad(w: torch.Tensor) -> torch.Tensor:
 
 def linear_fwd(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool = False) -> torch.Tensor:
     """act(x @ w^T + b), w [N, K] as torch stores a Linear weight"""
-    return dense_ffma(x, transpose_pad(w), w.shape[0], None if b is None else b.contiguous(), relu)
+    x = mat(x)
+    b = None if b is None else b.contiguous()
+    if _tc_ok(x.shape[0], x.shape[1], w.shape[0], x):
+        return dense_tc(x, w, False, w.shape[0], w.shape[1], b, relu)
+    return dense_ffma(x, transpose_pad(w), w.shape[0], b, relu)
 
 
 def matmul_nn(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """dy [M, N] @ w [N, K]: the input gradient of a Linear (the weight is used in its native layout)"""
     w = mat(w)
     n, k = w.shape
+    dy = mat(dy)
+    if _tc_ok(dy.shape[0], n, k, dy):
+        return dense_tc(dy, w, True, k, n, None, False)
     if w.stride(0) % 4 != 0 or w.data_ptr() % 16 != 0:
         wp = torch.zeros(n, _r4(k), dtype=torch.float32, device=w.device)
         _lib.check(_lib.load().morig_gather_cols(w.data_ptr(), _ld(w), 0, 0, 0, k, n, 1, wp.data_ptr(), wp.stride(0), 0, 0,

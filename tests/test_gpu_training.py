@@ -280,3 +280,36 @@ def test_optimisation_steps_and_eval_after_training():
     expect = helpers.oracle_forward("jointnet_motion", kw, model, data.to("cpu"), data.pred_flow.cpu())
     for o, e, k in zip(out, expect, helpers.OUT_KEYS):
         assert helpers.max_abs_diff(o, e) < helpers.TOL * max(1.0, float(e.abs().max())), k
+
+
+@pytest.mark.parametrize("N,K,bn", [(130, 100, 128), (256, 256, 256), (1024, 838 // 2 * 2, 256), (40, 64, 128)])
+def test_device_side_weight_image_equals_host_packer(N, K, bn):
+    """morig_pack_tc_f16 (weights change every training step, so the fp16-split tensor-core image is built on the device)
+    against packing.pack_tc_blob: the same bytes, for the weight and for its transpose (input-gradient GEMM)"""
+    from morig_b200 import _lib, packing
+    lib = _lib.load()
+    w = torch.randn(N, K, generator=g_(N + K))
+    for transposed in (False, True):
+        logical = w.t().contiguous() if transposed else w                      # the operand [n_out, k] the GEMM multiplies by
+        n_out, k = logical.shape
+        want, w_inv = packing.pack_tc_blob(logical.double(), k, bn, packing.KIND_F16)
+        blob = torch.zeros(lib.morig_pack_tc_f16_bytes(n_out, k, bn), dtype=torch.uint8, device=DEV)
+        scal = torch.zeros(2, device=DEV)
+        wd = w.to(DEV)
+        _lib.check(lib.morig_pack_tc_f16(wd.data_ptr(), K, n_out, k, 1 if transposed else 0, bn, blob.data_ptr(), scal.data_ptr(),
+                                         scal.data_ptr() + 4, _lib.stream_ptr()), "pack")
+        assert float(scal[0]) == w_inv
+        assert torch.equal(blob.cpu().view(torch.float16), want.view(torch.float16))
+
+
+@pytest.mark.parametrize("M,K,N", [(4099, 544, 512), (1000, 64, 128), (300000, 256, 256)])
+def test_training_gemms_on_the_tensor_core_engine(M, K, N):
+    """forward and input-gradient GEMMs of the training path take the tcgen05 split-fp16 engine for large shapes:
+    fp32-class accuracy against fp64"""
+    g = g_(M + K)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    dy = torch.randn(M, N, generator=g)
+    assert T._tc_ok(M, K, N, x.to(DEV))
+    got = T.linear_fwd(x.to(DEV), w.to(DEV), b.to(DEV), True)
+    assert close(got, torch.relu(x.double() @ w.double().t() + b.double()), 1e-5)
+    assert close(T.matmul_nn(dy.to(DEV), w.to(DEV)), dy.double() @ w.double(), 1e-5)
