@@ -154,6 +154,25 @@ class AttnCls(torch.autograd.Function):
         return dq.view_as(q0), dk.view_as(kc), dv.view_as(vc), dK, dV, None
 
 
+class ConcatColsPadded(torch.autograd.Function):
+    """torch.cat(xs, dim=1) with the width rounded up to a multiple of 4 by zero columns (the consumer pads its weight with
+    zero columns accordingly, train_forward.mlp_block), so that wide vertex layers such as mlp_transform.0 (K = 1862 / 1923)
+    qualify for the tensor-core engine"""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        ctx.widths = [x.shape[1] for x in xs]
+        return T.concat_cols(xs, 4)
+
+    @staticmethod
+    def backward(ctx, dout):
+        outs, off = [], 0
+        for i, w in enumerate(ctx.widths):
+            outs.append(dout[:, off:off + w] if ctx.needs_input_grad[i] else None)
+            off += w
+        return tuple(outs)
+
+
 class ConcatCols(torch.autograd.Function):
     @staticmethod
     def forward(ctx, *xs):

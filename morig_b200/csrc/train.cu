@@ -44,20 +44,27 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const float *__restr
 // 128 x 128 tile of dW per CTA, 8 x 8 micro-tile per thread, 16 rows of both operands per step (row-major loads are
 // already the layout the outer products need).  blockIdx.z splits the rows; partials go to the workspace and are added
 // in a fixed order by wgrad_reduce_kernel.
-constexpr int WG_T = 128, WG_M = 16, WG_THREADS = 256;
+constexpr int WG_M = 16, WG_THREADS = 256;
 
+// T = 128: 8 x 8 micro-tile per thread; T = 64 (narrow layers: N, K <= 64, e.g. the 16- / 32-channel edge branches, where a
+// 128 x 128 tile would waste 15/16 of its FMAs): 4 x 4 micro-tile
+template <int T>
 __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const float *__restrict__ dY, int lddy, const float *__restrict__ X,
                                                               int ldx, int M, int N, int K, const float *__restrict__ xs,
                                                               const float *__restrict__ xt, int rows_per_split,
                                                               float *__restrict__ part, float *__restrict__ part_b,
                                                               int vec_y, int vec_x) {
-    __shared__ __align__(16) float Ys[2][WG_M][WG_T];
-    __shared__ __align__(16) float Xs[2][WG_M][WG_T];
+    constexpr int MT = T / 16;                      // micro-tile edge
+    constexpr int C4 = T / 4;                       // float4 per tile row
+    constexpr int RPP = WG_THREADS / C4;            // rows loaded per pass (8 or 16)
+    constexpr int PASSES = WG_M / RPP;              // 2 or 1
+    __shared__ __align__(16) float Ys[2][WG_M][T];
+    __shared__ __align__(16) float Xs[2][WG_M][T];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int n0 = blockIdx.x * WG_T, k0 = blockIdx.y * WG_T;
+    const int n0 = blockIdx.x * T, k0 = blockIdx.y * T;
     const int m_begin = blockIdx.z * rows_per_split, m_end = min(M, m_begin + rows_per_split);
-    const int lrow = tid >> 5, lcol = (tid & 31) * 4;             // loads: rows lrow, lrow + 8; 4 consecutive columns
-    float4 ry[2], rx[2];
+    const int lrow = tid / C4, lcol = (tid % C4) * 4;
+    float4 ry[PASSES], rx[PASSES];
     float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), t4 = make_float4(0.f, 0.f, 0.f, 0.f);
     {
         float *s = reinterpret_cast<float *>(&s4), *t = reinterpret_cast<float *>(&t4);
@@ -68,8 +75,8 @@ __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const float *__res
     }
     auto load = [&](int m0) {
 #pragma unroll
-        for (int l = 0; l < 2; ++l) {
-            const int m = m0 + lrow + 8 * l;
+        for (int l = 0; l < PASSES; ++l) {
+            const int m = m0 + lrow + RPP * l;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
             if (m < m_end) {
                 const int n = n0 + lcol, k = k0 + lcol;
@@ -97,18 +104,18 @@ __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const float *__res
     };
     auto store = [&](int buf) {
 #pragma unroll
-        for (int l = 0; l < 2; ++l) {
-            *reinterpret_cast<float4 *>(&Ys[buf][lrow + 8 * l][lcol]) = ry[l];
-            *reinterpret_cast<float4 *>(&Xs[buf][lrow + 8 * l][lcol]) = rx[l];
+        for (int l = 0; l < PASSES; ++l) {
+            *reinterpret_cast<float4 *>(&Ys[buf][lrow + RPP * l][lcol]) = ry[l];
+            *reinterpret_cast<float4 *>(&Xs[buf][lrow + RPP * l][lcol]) = rx[l];
         }
     };
-    float acc[8][8];
-    float bsum[8];
+    float acc[MT][MT];
+    float bsum[MT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < MT; ++i) {
         bsum[i] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < MT; ++j) acc[i][j] = 0.f;
     }
     const int steps = (m_end > m_begin) ? (m_end - m_begin + WG_M - 1) / WG_M : 0;
     if (steps > 0) { load(m_begin); store(0); }
@@ -118,18 +125,19 @@ __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const float *__res
         const int buf = st & 1;
 #pragma unroll
         for (int m = 0; m < WG_M; ++m) {
-            float a[8], b[8];
-            const float4 a0 = *reinterpret_cast<const float4 *>(&Ys[buf][m][ty * 4]);
-            const float4 a1 = *reinterpret_cast<const float4 *>(&Ys[buf][m][64 + ty * 4]);
-            const float4 b0 = *reinterpret_cast<const float4 *>(&Xs[buf][m][tx * 4]);
-            const float4 b1 = *reinterpret_cast<const float4 *>(&Xs[buf][m][64 + tx * 4]);
-            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+            float a[MT], b[MT];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int h = 0; h < MT / 4; ++h) {
+                const float4 av = *reinterpret_cast<const float4 *>(&Ys[buf][m][h * 64 + ty * 4]);
+                const float4 bv = *reinterpret_cast<const float4 *>(&Xs[buf][m][h * 64 + tx * 4]);
+                a[4 * h] = av.x; a[4 * h + 1] = av.y; a[4 * h + 2] = av.z; a[4 * h + 3] = av.w;
+                b[4 * h] = bv.x; b[4 * h + 1] = bv.y; b[4 * h + 2] = bv.z; b[4 * h + 3] = bv.w;
+            }
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
                 bsum[i] += a[i];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < MT; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
             }
         }
         if (st + 1 < steps) store((st + 1) & 1);
@@ -137,11 +145,11 @@ __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const float *__res
     }
     float *out = part + (size_t)blockIdx.z * N * K;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < MT; ++i) {
         const int n = n0 + (i >> 2) * 64 + ty * 4 + (i & 3);
         if (n >= N) continue;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < MT; ++j) {
             const int k = k0 + (j >> 2) * 64 + tx * 4 + (j & 3);
             if (k < K) out[(size_t)n * K + k] = acc[i][j];
         }
@@ -200,16 +208,31 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float *__restrict__
     }
 }
 
+// sum of the per-chunk fp64 partials of one column: lanes take chunks lane, lane + 32, ... (ascending), then a butterfly --
+// a fixed order for a given chunk count, so results are reproducible run to run
+__device__ __forceinline__ void column_partials(const double *__restrict__ part, int chunks, int C, int c, int lane, double &a0,
+                                                double &a1) {
+    a0 = 0.0; a1 = 0.0;
+    for (int i = lane; i < chunks; i += 32) { a0 += part[((size_t)i * 2 + 0) * C + c]; a1 += part[((size_t)i * 2 + 1) * C + c]; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+    }
+}
+
 // train-mode BatchNorm1d forward statistics (torch semantics: biased variance normalises, the unbiased one updates
-// running_var; momentum 0.1 in the reference's MLP, models/basic_modules.py:33)
-__global__ void bn_finalize_fwd_kernel(const double *__restrict__ part, int chunks, int R, int C, const float *__restrict__ gamma,
+// running_var; momentum 0.1 in the reference's MLP, models/basic_modules.py:33).  One warp per column.
+__global__ void __launch_bounds__(256) bn_finalize_fwd_kernel(const double *__restrict__ part, int chunks, int R, int C,
+                                       const float *__restrict__ gamma,
                                        const float *__restrict__ beta, float eps, float momentum, float *running_mean,
                                        float *running_var, float *__restrict__ mean, float *__restrict__ invstd,
                                        float *__restrict__ scale, float *__restrict__ shift) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
-    double a0 = 0.0, a1 = 0.0;
-    for (int i = 0; i < chunks; ++i) { a0 += part[((size_t)i * 2 + 0) * C + c]; a1 += part[((size_t)i * 2 + 1) * C + c]; }
+    double a0, a1;
+    column_partials(part, chunks, C, c, lane, a0, a1);
+    if (lane != 0) return;
     const double mu = a0 / R;
     double var = a1 / R - mu * mu;
     if (var < 0.0) var = 0.0;
@@ -227,13 +250,15 @@ __global__ void bn_finalize_fwd_kernel(const double *__restrict__ part, int chun
 }
 
 // backward: dbeta = sum dy, dgamma = sum dy * xhat; coefficients of dx = a * (dy - m1 - xhat * m2)
-__global__ void bn_finalize_bwd_kernel(const double *__restrict__ part, int chunks, int R, int C, const float *__restrict__ gamma,
+__global__ void __launch_bounds__(256) bn_finalize_bwd_kernel(const double *__restrict__ part, int chunks, int R, int C,
+                                       const float *__restrict__ gamma,
                                        const float *__restrict__ mean, const float *__restrict__ invstd,
                                        float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
-    double a0 = 0.0, a1 = 0.0;
-    for (int i = 0; i < chunks; ++i) { a0 += part[((size_t)i * 2 + 0) * C + c]; a1 += part[((size_t)i * 2 + 1) * C + c]; }
+    double a0, a1;
+    column_partials(part, chunks, C, c, lane, a0, a1);
+    if (lane != 0) return;
     const double mu = mean[c], is = invstd[c];
     const double dg = is * (a1 - mu * a0);
     if (dgamma) dgamma[c] = (float)dg;
@@ -613,7 +638,10 @@ extern "C" MORIG_API int morig_transpose_pad_f32(const float *src, int32_t rows,
     return 0;
 }
 
+static inline int wgrad_tile(int N, int K) { return (N <= 64 && K <= 64) ? 64 : 128; }
+
 extern "C" MORIG_API int32_t morig_wgrad_splits(int32_t M, int32_t N, int32_t K) {
+    const int WG_T = wgrad_tile(N, K);
     const int tiles = ceil_div(N, WG_T) * ceil_div(K, WG_T);
     int want = ceil_div(2 * sm_count() * 2, tiles);                 // ~2 waves of 2 CTAs per SM
     const int max_by_rows = ceil_div(M, 4 * WG_M);                  // at least 64 rows per split
@@ -641,8 +669,12 @@ extern "C" MORIG_API int morig_wgrad_f32(const float *dY, int32_t lddy, const fl
     float *part = reinterpret_cast<float *>(ws);
     float *part_b = part + (size_t)splits * N * K;
     const int vec_y = (lddy % 4 == 0 && aligned16p(dY)) ? 1 : 0, vec_x = (ldx % 4 == 0 && aligned16p(X)) ? 1 : 0;
-    wgrad_kernel<<<dim3(ceil_div(N, WG_T), ceil_div(K, WG_T), splits), WG_THREADS, 0, stream>>>(
-        dY, lddy, X, ldx, M, N, K, x_scale, x_shift, rows, part, dbias ? part_b : nullptr, vec_y, vec_x);
+    if (wgrad_tile(N, K) == 64)
+        wgrad_kernel<64><<<dim3(ceil_div(N, 64), ceil_div(K, 64), splits), WG_THREADS, 0, stream>>>(
+            dY, lddy, X, ldx, M, N, K, x_scale, x_shift, rows, part, dbias ? part_b : nullptr, vec_y, vec_x);
+    else
+        wgrad_kernel<128><<<dim3(ceil_div(N, 128), ceil_div(K, 128), splits), WG_THREADS, 0, stream>>>(
+            dY, lddy, X, ldx, M, N, K, x_scale, x_shift, rows, part, dbias ? part_b : nullptr, vec_y, vec_x);
     MORIG_LAUNCH_CHECK("wgrad_kernel");
     wgrad_reduce_kernel<<<grid1d((int64_t)N * K + N, 256, 8), 256, 0, stream>>>(part, dbias ? part_b : nullptr, splits, N, K, dW,
                                                                                lddw, dbias, accumulate);
@@ -682,7 +714,7 @@ extern "C" MORIG_API int morig_bn_train_fwd(const float *x, int32_t ldx, int32_t
     if (!ws || ws_bytes < morig_colstats_workspace(R, C)) { set_error("bn_train_fwd: workspace too small"); return MORIG_E_WORKSPACE; }
     int chunks = 0;
     if (int rc = launch_colstats(x, ldx, nullptr, 0, R, C, reinterpret_cast<double *>(ws), chunks, stream)) return rc;
-    bn_finalize_fwd_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(reinterpret_cast<double *>(ws), chunks, R, C, gamma, beta, eps,
+    bn_finalize_fwd_kernel<<<ceil_div(C * 32, 256), 256, 0, stream>>>(reinterpret_cast<double *>(ws), chunks, R, C, gamma, beta, eps,
                                                                 momentum, running_mean, running_var, mean, invstd, scale,
                                                                 shift);
     MORIG_LAUNCH_CHECK("bn_finalize_fwd_kernel");
@@ -714,7 +746,7 @@ extern "C" MORIG_API int morig_bn_relu_bwd(const float *dy, int32_t lddy, const 
     if (!ws || ws_bytes < morig_colstats_workspace(R, C)) { set_error("bn_relu_bwd: workspace too small"); return MORIG_E_WORKSPACE; }
     int chunks = 0;
     if (int rc = launch_colstats(x, ldx, dy, lddy, R, C, reinterpret_cast<double *>(ws), chunks, stream)) return rc;
-    bn_finalize_bwd_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(reinterpret_cast<double *>(ws), chunks, R, C, gamma, mean, invstd,
+    bn_finalize_bwd_kernel<<<ceil_div(C * 32, 256), 256, 0, stream>>>(reinterpret_cast<double *>(ws), chunks, R, C, gamma, mean, invstd,
                                                                 dgamma, dbeta, coef);
     MORIG_LAUNCH_CHECK("bn_finalize_bwd_kernel");
     bn_relu_bwd_kernel<<<grid1d((int64_t)R * C, 256, 8), 256, 0, stream>>>(dy, lddy, x, ldx, R, C, mean, invstd, coef, relu, dz,

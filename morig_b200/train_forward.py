@@ -21,7 +21,10 @@ from . import train_ops as T
 def mlp_block(x, blk):
     """one `Seq(Linear, ReLU, BatchNorm1d)` of `MLP` -- models/basic_modules.py:31-36"""
     lin, bn = blk[0], blk[2]
-    y = A.LinReluBN.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum)
+    w = lin.weight
+    if x.shape[1] > w.shape[1]:        # input came from ConcatColsPadded: zero weight columns for the zero input columns
+        w = torch.cat([w, w.new_zeros(w.shape[0], x.shape[1] - w.shape[1])], dim=1)
+    y = A.LinReluBN.apply(x, w, lin.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum)
     _count_batch(bn)
     return y
 
@@ -95,7 +98,7 @@ def gcn_rig(mod, pos, feature, gt, gg, binfo):
     ptr = batch_ptr(binfo)
     xg, _ = A.SegMax.apply(x4, ptr, binfo.n_graphs)
     xgr = A.RowGather.apply(xg, binfo.batch32, ptr)
-    x5 = A.ConcatCols.apply(xgr, pos, feature, x1, x2, x3)
+    x5 = A.ConcatColsPadded.apply(xgr, pos, feature, x1, x2, x3)
     h = mlp(x5, mod.mlp_transform[0])
     head = mod.mlp_transform[1]
     return A.Linear.apply(h, head.weight, head.bias)

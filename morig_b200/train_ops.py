@@ -290,13 +290,15 @@ def attn_cls_bwd(q0, kc, vc, Kx, Vx, att, dout, d: int):
     return dvec[0], dvec[1], dvec[2], dK, dV
 
 
-def concat_cols(xs) -> torch.Tensor:
-    """torch.cat(xs, dim=1) through the strided-copy kernel"""
+def concat_cols(xs, pad_to: int = 1) -> torch.Tensor:
+    """torch.cat(xs, dim=1) through the strided-copy kernel; with pad_to > 1 the width is rounded up and the extra
+    columns are zero (so that the consuming Linear qualifies for the tensor-core engine: K % 4 == 0)"""
     lib = _lib.load()
     xs = [mat(x) for x in xs]
     R = xs[0].shape[0]
-    total = sum(x.shape[1] for x in xs)
-    out = torch.empty(R, total, dtype=torch.float32, device=xs[0].device)
+    width = sum(x.shape[1] for x in xs)
+    total = (width + pad_to - 1) // pad_to * pad_to
+    out = (torch.zeros if total != width else torch.empty)(R, total, dtype=torch.float32, device=xs[0].device)
     off = 0
     for x in xs:
         _lib.check(lib.morig_gather_cols(x.data_ptr(), _ld(x), 0, 0, 0, x.shape[1], R, 1, out.data_ptr(), total, off, 0, _sp()),

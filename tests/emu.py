@@ -269,8 +269,10 @@ def _t_scale_cols(x, factor):
     return x * factor
 
 
-def _t_concat_cols(xs):
-    return torch.cat(list(xs), dim=1)
+def _t_concat_cols(xs, pad_to=1):
+    y = torch.cat(list(xs), dim=1)
+    extra = (-y.shape[1]) % pad_to
+    return y if extra == 0 else torch.cat([y, y.new_zeros(y.shape[0], extra)], dim=1)
 
 
 def install_train(monkeypatch):
