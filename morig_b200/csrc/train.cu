@@ -136,8 +136,17 @@ __global__ void __launch_bounds__(WG_THREADS, 2) wgrad_kernel(const float *__res
 #pragma unroll
             for (int i = 0; i < MT; ++i) {
                 bsum[i] += a[i];
+                // packed fp32 pairs (FFMA2): one instruction per two accumulators of the row
+                const float2 a2 = make_float2(a[i], a[i]);
 #pragma unroll
-                for (int j = 0; j < MT; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < MT; j += 2) {
+                    uint64_t r;
+                    const float2 b2 = make_float2(b[j], b[j + 1]), c2 = make_float2(acc[i][j], acc[i][j + 1]);
+                    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<const uint64_t *>(&a2)),
+                        "l"(*reinterpret_cast<const uint64_t *>(&b2)), "l"(*reinterpret_cast<const uint64_t *>(&c2)));
+                    const float2 o = *reinterpret_cast<const float2 *>(&r);
+                    acc[i][j] = o.x; acc[i][j + 1] = o.y;
+                }
             }
         }
         if (st + 1 < steps) store((st + 1) & 1);
