@@ -2,6 +2,7 @@
 # One GPU-box round trip: parity tests, smoke, short bench (both arms).  Outputs -> gpurun_out/
 set -u
 mkdir -p gpurun_out
+export MORIG_BUILD_INCREMENTAL=1          # the in-tree .so travels with the snapshot
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 timeout 1500 python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -80 > gpurun_out/pytest_gpu.txt
 tail -25 gpurun_out/pytest_gpu.txt

@@ -259,12 +259,15 @@ def test_integer_exact_kat_argmax_and_gradients():
 
 def test_optimisation_steps_and_eval_after_training():
     """a few SGD steps of the reference's training recipe shape (training/train_rig.py:186-191): the loss goes down, and
-    eval() afterwards runs the fused inference kernels on the UPDATED weights and running statistics"""
+    eval() afterwards runs the fused inference kernels on the UPDATED weights and running statistics.  Train-mode BatchNorm
+    on seeded random weights gives a gradient norm of ~280 at a loss of 0.2, so plain SGD only descends monotonically for
+    learning rates <= 1e-6 (scripts/train_probe.py: the fp32 and the tensor-core GEMM paths then agree to 4 digits per
+    step); larger rates wander for either engine"""
     kw = synth.ARCH_KWARGS["jointnet_motion"]
     model = helpers.build_model("jointnet_motion", kw, 3, DEV).train()
     data = synth.make_batch(2, 256, seed=5).to(DEV)
     target = torch.tanh(torch.randn(512, 3, generator=g_(9))).to(DEV) * 0.1
-    opt = torch.optim.SGD(model.parameters(), lr=1e-3)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-7)
     losses = []
     for _ in range(4):
         opt.zero_grad()
@@ -273,7 +276,7 @@ def test_optimisation_steps_and_eval_after_training():
         loss.backward()
         opt.step()
         losses.append(float(loss.detach()))
-    assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0]
+    assert all(torch.isfinite(torch.tensor(losses))) and all(b < a for a, b in zip(losses, losses[1:])), losses
     model.eval()
     with torch.no_grad():
         out = model(data, data.pred_flow)
