@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmorig_b200.so")
+LIB_PATH = os.environ.get("MORIG_LIB") or os.path.join(_HERE, "libmorig_b200.so")   # MORIG_LIB: debug builds (role tracer)
 
 c_f32p = C.c_void_p   # device pointers travel as integers
 c_i32p = C.c_void_p

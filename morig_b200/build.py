@@ -12,7 +12,7 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-LIB = os.path.join(PKG, "libmorig_b200.so")
+LIB = os.environ.get("MORIG_LIB") or os.path.join(PKG, "libmorig_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--shared"]
@@ -35,9 +35,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     objs = []
     procs = []
-    os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
+    bdir = os.path.join(PKG, "build_trace" if os.environ.get("MORIG_TRACE") == "1" else "build")
+    os.makedirs(bdir, exist_ok=True)
     for src in sources():
-        obj = os.path.join(PKG, "build", os.path.basename(src) + ".o")
+        obj = os.path.join(bdir, os.path.basename(src) + ".o")
         cmd = [NVCC, "-c", src, "-o", obj] + [f for f in FLAGS if f != "--shared"]
         if verbose:
             cmd += ["-Xptxas", "-v"]

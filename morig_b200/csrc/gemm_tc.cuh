@@ -229,6 +229,27 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[16], uint32_t (&b)[16
                  :: "memory");
 }
 
+// register -> TMEM store of 32 lanes x 16 columns, and the wait that retires every tcgen05.st of this thread
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+           "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// one TMEM column (a RUNTIME column address: the one place where a row of the tile can be picked dynamically without
+// indexing registers) -> one register per lane; issue + wait in one statement, so the value is final on return
+__device__ __forceinline__ float tmem_ld1_sync(uint32_t taddr) {
+    uint32_t r;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r) : "r"(taddr) : "memory");
+    return __uint_as_float(r);
+}
+
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 // shared-memory matrix descriptor (K-major, SWIZZLE_128B: 8-row x 128 B atoms, 1024 B apart):
 //   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major), [32,46) stride
@@ -702,6 +723,170 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_
     if (EPI == EPI_SEGMAX || p.C) amax_commit(p.amax_out, amax_l);
 }
 
+// ---- fused-EdgeConv epilogue (EPI_SEGMAX): segmented max over the CSR target of the tile's rows -------------------
+// Same TMEM view as above (lane = channel, column = edge row).  A warp owns the 32 channels of its lane quarter and a
+// CONTIGUOUS range of RBW 32-row blocks (half the tile), so that a segment running across its blocks is carried in a
+// register and only segments that leave the warp's range need the atomic merge.  Per 32 x 32 block:
+//   1. tcgen05.ld the raw accumulators; running max along the rows IN REGISTERS (one predicated FMNMX per row, the
+//      head mask is warp-uniform), seeded with the carry when the block continues the previous block's last segment;
+//   2. tcgen05.st the running maxima back over the accumulator columns (the buffer is ours until it is released);
+//   3. for every segment tail r of the block (2-5 per block): tcgen05.ld of ONE column at the runtime address of r --
+//      TMEM is addressable by a register, registers are not -- then bias -> ReLU -> BatchNorm once per segment (see
+//      the monotonicity argument at `flush` in epilogue_role) and one coalesced 128-byte row store.
+// An earlier version picked the tail's value out of 32 registers with a branch tree: ~450 cycles per tail (ncu: branch
+// resolution + instruction-cache misses), 2100-2500 cycles per block, which made the epilogue -- not the MMAs or the
+// gathers -- the pace-setter of both fused EdgeConv kernels (role timeline, scripts/tc_trace.py).
+template <int CTAS, int BN, class Release>
+__device__ __forceinline__ void epilogue_segmax_role(const GemmP &p, float inv, uint32_t aux_addr, int *keys_smem,
+                                                     uint32_t tmem_base, int M, const TileMap &tm, int rank, int warp,
+                                                     int lane, Release release, long long *trace = nullptr) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr int NH = (CTAS == 1) ? BN / 128 : 1;   // 128-channel accumulators per buffer in this CTA's TMEM
+    constexpr int NRB = (CTAS == 1) ? 4 : 8;         // 32-row blocks per tile
+    constexpr int RBW = NRB / 2;                     // contiguous row blocks per warp
+    constexpr int BUF_COLS = (CTAS == 1) ? BN : 256;
+    constexpr int NBUF = 512 / BUF_COLS;
+    constexpr int NBUF_LOG = (NBUF == 4) ? 2 : 1;
+    static_assert(RBW * 32 + 2 <= KEYS_PER_WARP, "key strip too small");
+    const int e = warp - PRODUCER_WARPS;             // epilogue warp 0..7
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access (hardware: warp id % 4)
+    const int half = e >> 2;                         // which half of the tile's rows
+    Tracer tr{(trace && blockIdx.x == 0 && e == 0 && lane == 0) ? trace + 2 * 2048 : nullptr, 0};
+
+    // Row keys (CSR targets) of the warp's rows are fetched one tile ahead into registers and parked in a per-warp
+    // shared-memory strip for the walk: strip[32 i + lane] = key of row lane of block i; strip[128] / strip[129] = key of
+    // the row before / after the warp's range (-2 / -1 outside the matrix: never equal to a real key).
+    int *kstrip = keys_smem + e * KEYS_PER_WARP;
+    int nkey[RBW], kext;
+    auto load_keys = [&](int t) {
+#pragma unroll
+        for (int i = 0; i < RBW; ++i) nkey[i] = -1;
+        kext = -1;
+        if (t >= tm.total) return;
+        const int r0 = tm.decode(t).m0 - (CTAS == 2 ? rank * BM : 0) + half * (32 * RBW);
+#pragma unroll
+        for (int i = 0; i < RBW; ++i) {
+            const int r = r0 + 32 * i + lane;
+            if (r < M) nkey[i] = p.tgt[r];
+        }
+        if (lane == 0) kext = (r0 > 0) ? ((r0 - 1 < M) ? p.tgt[r0 - 1] : -1) : -2;
+        if (lane == 31 && r0 + 32 * RBW < M) kext = p.tgt[r0 + 32 * RBW];
+    };
+    load_keys(tm.first);
+    float amax_l = 0.f;                              // max |stored value| seen by this lane (GemmP::amax_out)
+
+    int li = 0;
+    for (int t = tm.first; t < tm.total; t += tm.step, ++li) {
+        const TileCoord tcd = tm.decode(t);
+        const int buf = li & (NBUF - 1);
+        const int n0 = tcd.n_tile * ((CTAS == 1) ? BN : 256) + (CTAS == 2 ? rank * 128 : 0) + q * 32 + lane;
+        __syncwarp();                                // the previous tile's reads of the strip are done
+#pragma unroll
+        for (int i = 0; i < RBW; ++i) kstrip[32 * i + lane] = nkey[i];
+        if (lane == 0) kstrip[128] = kext;
+        if (lane == 31) kstrip[129] = kext;
+        __syncwarp();
+        load_keys(t + tm.step);                      // in flight during this tile
+        // per-channel constants and the output column of this lane (L1 / L2 hits; their latency hides behind the wait
+        // for the accumulator).  sigma = sign of the BatchNorm scale is folded into the weight image, see `flush`.
+        float bias_l[NH], scale_l[NH], shift_l[NH], sinv_l[NH];
+        float *cbase[NH];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            const int nl = n0 + h * 128;
+            const bool ok = nl < p.N;
+            bias_l[h] = ok ? p.bias[nl] : 0.f;
+            scale_l[h] = ok ? p.scale[nl] : 1.f;
+            shift_l[h] = ok ? p.shift[nl] : 0.f;
+            sinv_l[h] = scale_l[h] < 0.f ? -inv : inv;
+            // output offsets fit 32 bits (checked by the launchers)
+            cbase[h] = ok ? p.C + ((uint32_t)(tcd.frame * p.n_vtx_frame) * (uint32_t)p.ldc + (uint32_t)nl) : nullptr;
+        }
+
+        tr(10);
+        mbar_wait(aux_addr + AUX_ACC_FULL + 8u * buf, (uint32_t)((li >> NBUF_LOG) & 1));
+        tr(11);
+        tc_fence_after();
+        // TMEM address of (lane quarter, accumulator buffer, first row of the warp's range)
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BUF_COLS + half * (32 * RBW));
+        uint32_t v[32];
+        uint32_t (&va)[16] = reinterpret_cast<uint32_t (&)[16]>(v[0]);
+        uint32_t (&vb)[16] = reinterpret_cast<uint32_t (&)[16]>(v[16]);
+        tmem_ld16_issue(tbase, va);
+        tmem_ld16_issue(tbase + 16u, vb);
+        float carry[NH];                             // running max of the segment that is open at the end of a block
+#pragma unroll
+        for (int h = 0; h < NH; ++h) carry[h] = 0.f;
+        bool open_cut = false;                       // the segment open at the START of the block began before the range
+        // The unit loop is deliberately NOT unrolled: twenty warps of three roles share the instruction cache.
+#pragma unroll 1
+        for (int i = 0; i < RBW; ++i) {
+            // segment structure of block i: warp-uniform masks (identical for both channel halves)
+            const int *kblk = kstrip + 32 * i;
+            const int key = kblk[lane];
+            const int key_dn = __shfl_down_sync(FULL, key, 1);
+            const uint32_t tails = __ballot_sync(FULL, (lane == 31) || (key != key_dn));
+            const uint32_t heads = (tails << 1) | 1u;
+            const bool first_cut = kblk[0] == ((i == 0) ? kstrip[128] : kblk[-1]);            // continues from the previous row
+            const bool last_cut = kblk[31] == ((i == RBW - 1) ? kstrip[129] : kblk[32]);      // ... into the next row
+            const int first_tail = __ffs(tails) - 1;
+            const bool cont = (i > 0) && first_cut;          // row 0 continues the segment carried in `carry`
+            if (i == 0) open_cut = first_cut;
+            const bool defer = last_cut && (i < RBW - 1);    // the last segment goes on in this warp's next block
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {                   // NH = 2 only in the small-batch cta_group::1 fallback of H = 256
+            const uint32_t tcol = tbase + (uint32_t)(h * 128 + i * 32);
+
+            tmem_ld_wait(va, vb);
+            tr(13);
+            // running max along the rows, restarted at segment heads (uniform predicates)
+            float w[32];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) w[r] = __uint_as_float(v[r]);
+            if (cont) w[0] = fmaxf(carry[h], w[0]);
+#pragma unroll
+            for (int r = 1; r < 32; ++r)
+                if (!((heads >> r) & 1u)) w[r] = fmaxf(w[r - 1], w[r]);
+            if (defer) carry[h] = w[31];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) v[r] = __float_as_uint(w[r]);
+            tmem_st16(tcol, va);
+            tmem_st16(tcol + 16u, vb);
+            tmem_st_wait();
+            // flush the finished segments: the value after the last row of a segment is its extreme
+            const float bias_h = bias_l[h], scale_h = scale_l[h], shift_h = shift_l[h], sinv_h = sinv_l[h];
+            float *const cb = cbase[h];
+            for (uint32_t tl = defer ? (tails & 0x7fffffffu) : tails; tl; tl &= tl - 1) {
+                const int r = __ffs(tl) - 1;
+                const int k_seg = kblk[r];
+                float m = tmem_ld1_sync(tcol + (uint32_t)r);
+                if (k_seg < 0 || cb == nullptr) continue;        // rows past the end of the matrix / channels past N
+                m = fmaf(fmaxf(fmaf(m, sinv_h, bias_h), 0.f), scale_h, shift_h);
+                float *dst = cb + (uint32_t)k_seg * (uint32_t)p.ldc;
+                // a segment that leaves the warp's range is merged with the ordered-int atomic max (exact and order
+                // independent, hence deterministic); everything else is a plain store
+                if ((r == first_tail && first_cut && open_cut) || (r == 31 && last_cut)) atomic_max_f32(dst, m);
+                else *dst = m;
+                amax_l = fmaxf(amax_l, fabsf(m));                // only the maxima are stored
+            }
+            if (h + 1 < NH || i + 1 < RBW) {                  // next unit: the other channel half, or the next row block
+                const uint32_t tnext = tbase + (uint32_t)((h + 1 < NH) ? (h + 1) * 128 + i * 32 : (i + 1) * 32);
+                tmem_ld16_issue(tnext, va);
+                tmem_ld16_issue(tnext + 16u, vb);
+            }
+            tr(16);
+            }
+            open_cut = defer && (first_tail == 31) && first_cut && open_cut;
+        }
+        tr(17);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) release(buf);             // buffer may be overwritten by tile li + NBUF
+        tr(12);
+    }
+    amax_commit(p.amax_out, amax_l);
+}
+
 // =============================================================================================================
 // cta_group::1 kernel: BN / 128 UMMAs of 128 (channels) x 128 (rows) per k-step
 // =============================================================================================================
@@ -861,8 +1046,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
                                    [&](int s) { mbar_arrive(bar_a(s)); }, tp.trace);
     } else {
         reg_inc<REGS_EPILOGUE>();
-        epilogue_role<1, BN, EPI>(p, inv, aux_addr, reinterpret_cast<int *>(aux + AUX_BYTES), tmem_base, M, tm, 0, warp, lane,
-                                  [&](int b) { mbar_arrive(bar_acce(b)); }, tp.trace);
+        auto release = [&](int b) { mbar_arrive(bar_acce(b)); };
+        if constexpr (EPI == EPI_SEGMAX)
+            epilogue_segmax_role<1, BN>(p, inv, aux_addr, reinterpret_cast<int *>(aux + AUX_BYTES), tmem_base, M, tm, 0, warp,
+                                        lane, release, tp.trace);
+        else
+            epilogue_role<1, BN, EPI>(p, inv, aux_addr, reinterpret_cast<int *>(aux + AUX_BYTES), tmem_base, M, tm, 0, warp,
+                                      lane, release, tp.trace);
     }
     tc_fence_before();
     __syncthreads();
@@ -1051,11 +1241,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
         }, tp.trace);
     } else {
         reg_inc<REGS_EPILOGUE>();
-        epilogue_role<2, BN2, EPI>(p, inv, aux_addr, reinterpret_cast<int *>(aux + AUX_BYTES), tmem_base, M, tm, (int)rank, warp,
-                                   lane, [&](int b) {
+        auto release = [&](int b) {
             if (rank == 0) mbar_arrive(bar_acce(b));
             else mbar_arrive_cluster(bar_acce(b), 0);
-        }, tp.trace);
+        };
+        if constexpr (EPI == EPI_SEGMAX)
+            epilogue_segmax_role<2, BN2>(p, inv, aux_addr, reinterpret_cast<int *>(aux + AUX_BYTES), tmem_base, M, tm, (int)rank,
+                                         warp, lane, release, tp.trace);
+        else
+            epilogue_role<2, BN2, EPI>(p, inv, aux_addr, reinterpret_cast<int *>(aux + AUX_BYTES), tmem_base, M, tm, (int)rank,
+                                       warp, lane, release, tp.trace);
     }
     tc_fence_before();
     __syncthreads();
