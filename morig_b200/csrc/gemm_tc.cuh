@@ -65,12 +65,22 @@ constexpr int CONTROL_WARP = PRODUCER_WARPS + EPILOGUE_WARPS;
 constexpr int THREADS = 32 * (PRODUCER_WARPS + EPILOGUE_WARPS + 4);    // control warp + 3 idle warps: a full warpgroup
 // Register budget: 20 warps x 96 registers at launch (640 threads cap the launch allocation at 61440 of the 65536
 // registers, and setmaxnreg can only redistribute what the CTA was given); the roles then rebalance with setmaxnreg
-// (which works on whole warpgroups, hence the 3 idle warps next to the control warp): every scheduler hosts
-// 2 producer warps (112) + 2 epilogue warps (104) + 1 control-group warp (48) = 480 = 5 x 96 registers/lane.  Both data roles are latency-bound
-// straight-line code, so two warps of each per scheduler (hiding each other's stalls) matter more than deep
-// per-thread register rings.
-constexpr int REGS_PRODUCER = 112, REGS_EPILOGUE = 104, REGS_CONTROL = 48;
-static_assert(2 * REGS_PRODUCER + 2 * REGS_EPILOGUE + REGS_CONTROL <= 5 * 96, "setmaxnreg budget exceeds the launch allocation");
+// (which works on whole warpgroups, hence the 3 idle warps next to the control warp).  Every scheduler hosts 2 producer
+// warps + 2 epilogue warps + 1 control-group warp, and 2 P + 2 E + C must stay within 5 x 96 registers per lane:
+//   fused EdgeConv (gather producers: two 32-register load buffers, eight row pointers, prefetched indices; segmented-max
+//       epilogue with TMEM write-back: one 32-row block in registers): P = 128, E = 88, C = 48
+//       (a third load buffer at P = 144 / E = 72 was measured: no gain -- the producers are bound by instruction issue and
+//       dependent-issue latency, not by the ~1000-cycle gather latency)
+//   dense layers (plain producers: 16 registers per buffer; store / pool epilogue with two 32-register arrays):
+//       P = 112, E = 104, C = 48
+// Both data roles are latency-bound straight-line code, so two warps of each per scheduler (hiding each other's stalls)
+// matter more than deeper per-thread rings.
+constexpr int REGS_CONTROL = 48;
+template <int AMODE> struct RoleCfg {
+    static constexpr int REGS_PRODUCER = (AMODE == AMODE_GATHER) ? 128 : 112;
+    static constexpr int REGS_EPILOGUE = (AMODE == AMODE_GATHER) ? 88 : 104;
+    static_assert(2 * REGS_PRODUCER + 2 * REGS_EPILOGUE + REGS_CONTROL <= 5 * 96, "setmaxnreg budget exceeds the launch allocation");
+};
 constexpr int ROWS_PER_THREAD = BM / (PRODUCER_WARPS * 4);       // 4 rows, one 16-byte fp32 chunk each
 constexpr int AUX_BYTES = 1024;                                  // barriers, tmem pointer
 constexpr int PIPE_BYTES = 192 * 1024;                           // operand ring (every configuration)
@@ -347,6 +357,36 @@ struct TileMap {
     __device__ __forceinline__ int my_tiles() const { return total > first ? (total - 1 - first) / step + 1 : 0; }
 };
 
+// The same stream with the coordinates kept incrementally: one add / compare / select chain per tile instead of the
+// four integer divisions of decode() (ncu: ~190 of a producer warp's ~880 instructions per tile were tile arithmetic).
+struct TileIter {
+    int t, n_tile, mi, frame;        // mi = m-tile (cta_group::2: pair-tile) index inside the key-frame
+    int d_n, d_m, d_f;               // `step` decomposed in the mixed radix (ntn, ntm)
+    int ntn, ntm, total, step, mult, rank;
+    __device__ __forceinline__ void init(const TileMap &tm) {
+        ntn = tm.ntn; ntm = tm.ntm; total = tm.total; step = tm.step; mult = tm.mult; rank = tm.rank;
+        t = tm.first;
+        n_tile = t % ntn;
+        const int r = t / ntn;
+        mi = r % ntm; frame = r / ntm;
+        d_n = step % ntn;
+        const int a = step / ntn;
+        d_m = a % ntm; d_f = a / ntm;
+    }
+    __device__ __forceinline__ bool valid() const { return t < total; }
+    __device__ __forceinline__ int m0() const { return (mi * mult + rank) * BM; }
+    __device__ __forceinline__ void next() {
+        t += step;
+        n_tile += d_n;
+        int c = (n_tile >= ntn) ? 1 : 0;
+        n_tile -= c ? ntn : 0;
+        mi += d_m + c;
+        c = (mi >= ntm) ? 1 : 0;
+        mi -= c ? ntm : 0;
+        frame += d_f + c;
+    }
+};
+
 // ================= producer warps: A stage images =================
 // The producers work in ring UNITS of 32 k-columns: thread -> 4 consecutive k-columns (one float4) of 4 rows.  A TF32
 // stage is one unit (16-byte hi and lo chunks), an FP16 stage two units (8-byte chunks).  Two register buffers rotate:
@@ -493,6 +533,154 @@ __device__ __forceinline__ void producer_role(const GemmP &p, float a_scale, uin
             issue(pb1, qb1);
         }
         remaining -= 2;
+    }
+}
+
+// ---- gather producers of the fused EdgeConv (AMODE_GATHER): relu(P[tgt[e]] + Q[col[e]]) per CSR slot ---------------------
+// The same ring protocol as producer_role, specialised so that nothing is computed per unit that can be known earlier:
+//   * NU = K / 32 units per tile is a template parameter (H = 64 / 128 / 256 -> 2 / 4 / 8): the tile body is fully
+//     unrolled, the unit's column offset is an immediate of the load instruction, the fp16 half-row (unit & 1) and the
+//     register buffer are compile-time, the eight row pointers are formed once per tile;
+//   * the ReLU rides on the fp32 -> fp16 conversion (cvt.rn.relu.f16x2.f32): hi = x with the low mantissa bits cleared and
+//     lo = x - hi have the sign of x (truncation), so for x < 0 both convert to +0 and for x >= 0 nothing changes --
+//     bit-identical to splitting relu(x), four FMNMX per 16-byte chunk cheaper;
+//   * tile coordinates advance incrementally (TileIter).
+// ncu (source view) had the old producers at ~200 instructions per unit and warp against ~80 of arithmetic; with the
+// TMEM write-back epilogue the producers set the pace of both fused EdgeConv kernels.
+__device__ __forceinline__ uint32_t pack_h2_relu(float lo_k, float hi_k) {
+    uint32_t r;                                          // upper half <- first source, lower half <- second
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_k), "f"(lo_k));
+    return r;
+}
+
+template <int KIND, int NU, class Arrive>
+__device__ __forceinline__ void producer_gather_role(const GemmP &p, float a_scale, uint8_t *smem, uint32_t a_stride,
+                                                     uint32_t aux_addr, int S, int M, const TileMap &tm, int tid, int lane,
+                                                     Arrive arrive, long long *trace = nullptr) {
+    constexpr int UPS = KindCfg<KIND>::UPS;
+    constexpr int RPT = ROWS_PER_THREAD;
+    static_assert(NU >= 2 && NU % 2 == 0, "two register buffers alternate over an even number of units per tile");
+    Tracer tr{(trace && blockIdx.x == 0 && tid == 0) ? trace : nullptr, 0};
+    const int c = tid & 7;
+    const int w = tid >> 5, g = (tid >> 3) & 3;
+    int s = 0;                                   // stage ring position
+    uint32_t wait_ph = 1;                        // parity of "stage s is free" (passes on a fresh barrier)
+
+    uint32_t soff[RPT];                          // see producer_role
+#pragma unroll
+    for (int ps = 0; ps < RPT; ++ps) {
+        const int row = producer_row(w, g, ps);
+        soff[ps] = (KIND == KIND_F16) ? (uint32_t)(row * 128 + (((c >> 1) ^ (row & 7)) << 4) + ((c & 1) << 3))
+                                      : (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4));
+    }
+
+    TileIter it;                                 // the tile whose units are being stored
+    it.init(tm);
+    if (!it.valid()) return;
+    const int last_row = M - 1;
+    int ni[RPT], nj[RPT];                        // gather indices, fetched one tile ahead
+    const float *rp[RPT], *rq[RPT];              // this thread's 16-byte column of its four P / Q rows
+    auto fetch_idx = [&](int m0) {
+#pragma unroll
+        for (int ps = 0; ps < RPT; ++ps) {
+            const int r = min(m0 + producer_row(w, g, ps), last_row);      // rows past the end re-read the last valid row
+            ni[ps] = p.tgt[r];
+            nj[ps] = p.col[r];
+        }
+    };
+    auto set_rows = [&](int frame) {             // element offsets fit 32 bits (checked by the launchers)
+        const uint32_t fb = (uint32_t)frame * (uint32_t)p.n_vtx_frame;
+#pragma unroll
+        for (int ps = 0; ps < RPT; ++ps) {
+            rp[ps] = p.P + ((fb + (uint32_t)ni[ps]) * (uint32_t)p.ldpq + 4u * c);
+            rq[ps] = p.Q + ((fb + (uint32_t)nj[ps]) * (uint32_t)p.ldpq + 4u * c);
+        }
+    };
+    auto issue = [&](float4 (&pd)[RPT], float4 (&qd)[RPT], const int unit) {      // `unit` is a literal at every call site
+#pragma unroll
+        for (int ps = 0; ps < RPT; ++ps) {
+            pd[ps] = *reinterpret_cast<const float4 *>(rp[ps] + unit * KC);
+            qd[ps] = *reinterpret_cast<const float4 *>(rq[ps] + unit * KC);
+        }
+    };
+    auto store_unit = [&](const int us, const float4 (&pd)[RPT], const float4 (&qd)[RPT]) {   // `us` is a literal too
+        if (us == 0) {
+            tr(1);
+            mbar_wait(aux_addr + AUX_MMA_DONE + 8u * s, wait_ph);    // MMAs that read this stage one ring turn ago retired
+            tr(2);
+        }
+        uint8_t *a_hi = smem + s * a_stride;
+        uint8_t *a_lo = a_hi + A_HALF_BYTES;
+#pragma unroll
+        for (int ps = 0; ps < RPT; ++ps) {
+            float2 va = add2(make_float2(pd[ps].x, pd[ps].y), make_float2(qd[ps].x, qd[ps].y));
+            float2 vb = add2(make_float2(pd[ps].z, pd[ps].w), make_float2(qd[ps].z, qd[ps].w));
+            if (KIND == KIND_F16) {
+                const float2 s2 = make_float2(a_scale, a_scale);
+                va = mul2(va, s2); vb = mul2(vb, s2);
+                const float2 ha = make_float2(tf32_hi(va.x), tf32_hi(va.y)), hb = make_float2(tf32_hi(vb.x), tf32_hi(vb.y));
+                const float2 la = sub2(va, ha), lb = sub2(vb, hb);
+                const uint32_t off = soff[ps] ^ (us ? 64u : 0u);     // unit 1 = the other half of the swizzled row
+                *reinterpret_cast<uint2 *>(a_hi + off) = make_uint2(pack_h2_relu(ha.x, ha.y), pack_h2_relu(hb.x, hb.y));
+                *reinterpret_cast<uint2 *>(a_lo + off) = make_uint2(pack_h2_relu(la.x, la.y), pack_h2_relu(lb.x, lb.y));
+            } else {
+                va.x = fmaxf(va.x, 0.f); va.y = fmaxf(va.y, 0.f); vb.x = fmaxf(vb.x, 0.f); vb.y = fmaxf(vb.y, 0.f);
+                const float2 ha = make_float2(tf32_hi(va.x), tf32_hi(va.y)), hb = make_float2(tf32_hi(vb.x), tf32_hi(vb.y));
+                const float2 la = sub2(va, ha), lb = sub2(vb, hb);
+                *reinterpret_cast<float4 *>(a_hi + soff[ps]) = make_float4(ha.x, ha.y, hb.x, hb.y);
+                *reinterpret_cast<float4 *>(a_lo + soff[ps]) = make_float4(la.x, la.y, lb.x, lb.y);
+            }
+        }
+        if (us == UPS - 1) {
+            fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) arrive(s);
+            tr(3);
+            if (++s == S) { s = 0; wait_ph ^= 1; }
+        }
+    };
+
+    float4 pb0[RPT], pb1[RPT], qb0[RPT], qb1[RPT];
+    fetch_idx(it.m0());
+    set_rows(it.frame);
+    {
+        TileIter nx = it;
+        nx.next();
+        if (nx.valid()) fetch_idx(nx.m0());
+    }
+    issue(pb0, qb0, 0);
+    issue(pb1, qb1, 1);
+    // Invariant at the top of the loop: units 0 / 1 of tile `it` are in flight in buffers 0 / 1, ni / nj hold the indices
+    // of the tile after it.  Unit u is stored from buffer u & 1, which is then refilled with unit u + 2 -- of this tile
+    // (same row pointers, immediate column offset) or, for the last two units, of the next tile, whose row pointers
+    // replace the current ones as soon as every load of the current tile has been issued.
+    for (;;) {
+        bool next_valid = false;
+#pragma unroll
+        for (int lu = 0; lu < NU; ++lu) {
+            if (lu & 1) store_unit(UPS - 1, pb1, qb1);
+            else store_unit(0, pb0, qb0);
+            if (lu + 2 < NU) {
+                if (lu & 1) issue(pb1, qb1, lu + 2);
+                else issue(pb0, qb0, lu + 2);
+            } else {
+                if (lu + 2 == NU) {
+                    it.next();
+                    next_valid = it.valid();
+                    if (next_valid) {
+                        set_rows(it.frame);
+                        TileIter nx = it;
+                        nx.next();
+                        if (nx.valid()) fetch_idx(nx.m0());                // consumed a tile later
+                    }
+                }
+                if (next_valid) {
+                    if (lu & 1) issue(pb1, qb1, lu + 2 - NU);
+                    else issue(pb0, qb0, lu + 2 - NU);
+                }
+            }
+        }
+        if (!next_valid) break;
     }
 }
 
@@ -789,19 +977,21 @@ __device__ __forceinline__ void epilogue_segmax_role(const GemmP &p, float inv, 
         load_keys(t + tm.step);                      // in flight during this tile
         // per-channel constants and the output column of this lane (L1 / L2 hits; their latency hides behind the wait
         // for the accumulator).  sigma = sign of the BatchNorm scale is folded into the weight image, see `flush`.
-        float bias_l[NH], scale_l[NH], shift_l[NH], sinv_l[NH];
-        float *cbase[NH];
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
+        // (NH = 2, the small-batch fallback, reloads them per unit instead of holding two sets in 72 registers.)
+        struct LaneConsts { float bias, scale, shift, sinv; float *cb; };
+        auto lane_consts = [&](int h) {
+            LaneConsts k;
             const int nl = n0 + h * 128;
             const bool ok = nl < p.N;
-            bias_l[h] = ok ? p.bias[nl] : 0.f;
-            scale_l[h] = ok ? p.scale[nl] : 1.f;
-            shift_l[h] = ok ? p.shift[nl] : 0.f;
-            sinv_l[h] = scale_l[h] < 0.f ? -inv : inv;
+            k.bias = ok ? p.bias[nl] : 0.f;
+            k.scale = ok ? p.scale[nl] : 1.f;
+            k.shift = ok ? p.shift[nl] : 0.f;
+            k.sinv = k.scale < 0.f ? -inv : inv;
             // output offsets fit 32 bits (checked by the launchers)
-            cbase[h] = ok ? p.C + ((uint32_t)(tcd.frame * p.n_vtx_frame) * (uint32_t)p.ldc + (uint32_t)nl) : nullptr;
-        }
+            k.cb = ok ? p.C + ((uint32_t)(tcd.frame * p.n_vtx_frame) * (uint32_t)p.ldc + (uint32_t)nl) : nullptr;
+            return k;
+        };
+        LaneConsts k0 = lane_consts(0);
 
         tr(10);
         mbar_wait(aux_addr + AUX_ACC_FULL + 8u * buf, (uint32_t)((li >> NBUF_LOG) & 1));
@@ -854,8 +1044,9 @@ __device__ __forceinline__ void epilogue_segmax_role(const GemmP &p, float inv, 
             tmem_st16(tcol + 16u, vb);
             tmem_st_wait();
             // flush the finished segments: the value after the last row of a segment is its extreme
-            const float bias_h = bias_l[h], scale_h = scale_l[h], shift_h = shift_l[h], sinv_h = sinv_l[h];
-            float *const cb = cbase[h];
+            const LaneConsts kh = (NH == 1) ? k0 : lane_consts(h);
+            const float bias_h = kh.bias, scale_h = kh.scale, shift_h = kh.shift, sinv_h = kh.sinv;
+            float *const cb = kh.cb;
             for (uint32_t tl = defer ? (tails & 0x7fffffffu) : tails; tl; tl &= tl - 1) {
                 const int r = __ffs(tl) - 1;
                 const int k_seg = kblk[r];
@@ -1041,11 +1232,21 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
             }
         }
     } else if (warp < PRODUCER_WARPS) {
-        reg_inc<REGS_PRODUCER>();
-        producer_role<KIND, AMODE>(p, a_scale, smem, a_stride, aux_addr, S, nK, M, tm, tid, lane,
-                                   [&](int s) { mbar_arrive(bar_a(s)); }, tp.trace);
+        reg_inc<RoleCfg<AMODE>::REGS_PRODUCER>();
+        auto arrive = [&](int s) { mbar_arrive(bar_a(s)); };
+        if constexpr (AMODE == AMODE_GATHER) {           // K = H in {64, 128} (BN = 128) or 256: K / 32 units per tile
+            if constexpr (BN == 128) {
+                if (p.K <= 64) producer_gather_role<KIND, 2>(p, a_scale, smem, a_stride, aux_addr, S, M, tm, tid, lane, arrive, tp.trace);
+                else producer_gather_role<KIND, 4>(p, a_scale, smem, a_stride, aux_addr, S, M, tm, tid, lane, arrive, tp.trace);
+            } else {
+                producer_gather_role<KIND, 8>(p, a_scale, smem, a_stride, aux_addr, S, M, tm, tid, lane, arrive, tp.trace);
+            }
+        } else {
+            producer_role<KIND, AMODE>(p, a_scale, smem, a_stride, aux_addr, S, nK, M, tm, tid, lane, arrive, tp.trace);
+        }
     } else {
-        reg_inc<REGS_EPILOGUE>();
+        if constexpr (RoleCfg<AMODE>::REGS_EPILOGUE >= 96) reg_inc<RoleCfg<AMODE>::REGS_EPILOGUE>();
+        else reg_dec<RoleCfg<AMODE>::REGS_EPILOGUE>();
         auto release = [&](int b) { mbar_arrive(bar_acce(b)); };
         if constexpr (EPI == EPI_SEGMAX)
             epilogue_segmax_role<1, BN>(p, inv, aux_addr, reinterpret_cast<int *>(aux + AUX_BYTES), tmem_base, M, tm, 0, warp,
@@ -1234,13 +1435,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
             }
         }
     } else if (warp < PRODUCER_WARPS) {
-        reg_inc<REGS_PRODUCER>();
-        producer_role<KIND, AMODE>(p, a_scale, smem, a_stride, aux_addr, S, nK, M, tm, tid, lane, [&](int s) {
+        reg_inc<RoleCfg<AMODE>::REGS_PRODUCER>();
+        auto arrive = [&](int s) {
             if (rank == 0) mbar_arrive(bar_a(s));
             else mbar_arrive_cluster(bar_a(s), 0);
-        }, tp.trace);
+        };
+        if constexpr (AMODE == AMODE_GATHER)             // K = H = 256: 8 units per tile
+            producer_gather_role<KIND, 8>(p, a_scale, smem, a_stride, aux_addr, S, M, tm, tid, lane, arrive, tp.trace);
+        else
+            producer_role<KIND, AMODE>(p, a_scale, smem, a_stride, aux_addr, S, nK, M, tm, tid, lane, arrive, tp.trace);
     } else {
-        reg_inc<REGS_EPILOGUE>();
+        if constexpr (RoleCfg<AMODE>::REGS_EPILOGUE >= 96) reg_inc<RoleCfg<AMODE>::REGS_EPILOGUE>();
+        else reg_dec<RoleCfg<AMODE>::REGS_EPILOGUE>();
         auto release = [&](int b) {
             if (rank == 0) mbar_arrive(bar_acce(b));
             else mbar_arrive_cluster(bar_acce(b), 0);
