@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MORIG_ABI_VERSION 5
+#define MORIG_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define MORIG_API __attribute__((visibility("default")))
@@ -199,6 +199,13 @@ MORIG_API int morig_gather_cols(const float *src, int32_t lds, int32_t src_off, 
 MORIG_API int morig_fill_f32(float *dst, int64_t n, float value, void *stream);
 /* up to 8 (16-byte aligned) buffers in one launch: the -inf initialisation of all EdgeConv outputs of a GCNRig */
 MORIG_API int morig_fill_many_f32(float *const *dst, const int64_t *n, int32_t count, float value, void *stream);
+/* Start values only where the fused EdgeConv kernels merge with the atomic max: for every entry k (<= 8), every vertex v
+ * whose CSR segment [rowptr[k][v], rowptr[k][v+1]) straddles a multiple of 32 slots and every key-frame f, writes `value`
+ * to out[k][(f*N + v)*ld[k] + col0[k] .. + ncols[k]).  All other vertices are written by one plain store of the kernel
+ * that owns their segment.  Replaces the reference's zero-initialised scatter output (torch_scatter `scatter(...,
+ * reduce='max')` behind models/basic_modules.py:180-181) for the EdgeConv outputs of one GCNRig in a single launch. */
+MORIG_API int morig_fill_cut_f32(const int32_t *const *rowptr, float *const *out, const int32_t *ld, const int32_t *col0,
+                                 const int32_t *ncols, int32_t count, int32_t N, int32_t frames, float value, void *stream);
 
 /* *amax = max(*amax, max |x[r, c]|) over r < R, c < C (row stride ldx): the operand range the fp16-split
  * tensor-core layers need for inputs that were not produced by this library (out_amax / dst_amax /

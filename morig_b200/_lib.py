@@ -97,6 +97,7 @@ _SIGNATURES = {
                                     C.c_int32, c_f32p, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
     "morig_fill_f32": (C.c_int, [c_f32p, C.c_int64, C.c_float, C.c_void_p]),
     "morig_fill_many_f32": (C.c_int, [_P, _P, _I, C.c_float, _P]),
+    "morig_fill_cut_f32": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, C.c_float, _P]),
     "morig_absmax_f32": (C.c_int, [c_f32p, C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
     "morig_nms_meanshift_workspace": (C.c_size_t, [_I]),
     "morig_nms_meanshift": (C.c_int, [_P, _P, _I, C.c_double, C.c_double, C.c_double, _P, _P, C.c_size_t, _P]),
@@ -136,7 +137,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
-ABI_VERSION = 5
+ABI_VERSION = 6
 _lib = None
 
 

@@ -546,7 +546,10 @@ __device__ __forceinline__ void producer_role(const GemmP &p, float a_scale, uin
 //     bit-identical to splitting relu(x), four FMNMX per 16-byte chunk cheaper;
 //   * tile coordinates advance incrementally (TileIter).
 // ncu (source view) had the old producers at ~200 instructions per unit and warp against ~80 of arithmetic; with the
-// TMEM write-back epilogue the producers set the pace of both fused EdgeConv kernels.
+// TMEM write-back epilogue the producers set the pace of both fused EdgeConv kernels.  Measured and dropped: a third
+// register buffer (loads three units ahead) and an L2 prefetch of the rows of the tile after the next one (half of
+// the kernel's L2 requests miss in a cold-cache ncu replay, but inside the step the operand is largely L2-resident):
+// neither moved the kernels.
 __device__ __forceinline__ uint32_t pack_h2_relu(float lo_k, float hi_k) {
     uint32_t r;                                          // upper half <- first source, lower half <- second
     asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_k), "f"(lo_k));
@@ -580,12 +583,12 @@ __device__ __forceinline__ void producer_gather_role(const GemmP &p, float a_sca
     const int last_row = M - 1;
     int ni[RPT], nj[RPT];                        // gather indices, fetched one tile ahead
     const float *rp[RPT], *rq[RPT];              // this thread's 16-byte column of its four P / Q rows
-    auto fetch_idx = [&](int m0) {
+    auto fetch_idx = [&](int m0) {               // volatile asm: the loads must issue HERE, a tile ahead of their use
 #pragma unroll
         for (int ps = 0; ps < RPT; ++ps) {
             const int r = min(m0 + producer_row(w, g, ps), last_row);      // rows past the end re-read the last valid row
-            ni[ps] = p.tgt[r];
-            nj[ps] = p.col[r];
+            asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(ni[ps]) : "l"(p.tgt + r));
+            asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(nj[ps]) : "l"(p.col + r));
         }
     };
     auto set_rows = [&](int frame) {             // element offsets fit 32 bits (checked by the launchers)

@@ -173,9 +173,65 @@ __global__ void __launch_bounds__(256) fill_many_kernel(const FillMany f) {
     }
 }
 
+// Selective start values for the fused EdgeConv outputs: only the vertices whose CSR segment straddles a multiple of 32
+// slots are ever merged with the atomic max (every edge kernel cuts its tiles into row ranges that are multiples of 32:
+// 32 slots per warp in edge_mma_kernel, 64 / 128 rows per epilogue warp in the tcgen05 kernels, 32 / 64 rows per column
+// walker in the CUDA-core fallback); every other vertex is written by exactly one plain store.  So instead of
+// streaming -inf over whole [R, 2 (H + Dp)] buffers (304 MB per GCNRig at 4 x 4096 vertices x 5 key-frames) one warp
+// per (vertex, branch group) tests the segment and fills `ncols` columns of that vertex in every key-frame.
+constexpr int FILL_CUT_MAX = 8;
+struct FillCut {
+    const int32_t *rowptr[FILL_CUT_MAX];
+    float *out[FILL_CUT_MAX];
+    int ld[FILL_CUT_MAX], col0[FILL_CUT_MAX], ncols[FILL_CUT_MAX];
+    int count, N, frames;
+    float value;
+};
+
+__global__ void __launch_bounds__(256) fill_cut_kernel(const FillCut f) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t total = (int64_t)f.N * f.count;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
+        const int k = (int)(w / f.N), v = (int)(w - (int64_t)k * f.N);
+        const int a = f.rowptr[k][v], b = f.rowptr[k][v + 1];
+        if (b <= a || (a >> 5) == ((b - 1) >> 5)) continue;              // empty, or inside one 32-slot range: plain store
+        const int nc = f.ncols[k];
+        for (int fr = 0; fr < f.frames; ++fr) {
+            float *row = f.out[k] + ((size_t)fr * f.N + v) * (size_t)f.ld[k] + f.col0[k];
+            if (((nc | f.ld[k] | f.col0[k]) & 3) == 0) {
+                const float4 v4 = make_float4(f.value, f.value, f.value, f.value);
+                for (int c = 4 * lane; c < nc; c += 128) *reinterpret_cast<float4 *>(row + c) = v4;
+            } else {
+                for (int c = lane; c < nc; c += 32) row[c] = f.value;
+            }
+        }
+    }
+}
+
 }  // namespace morig
 
 using namespace morig;
+
+extern "C" MORIG_API int morig_fill_cut_f32(const int32_t *const *rowptr, float *const *out, const int32_t *ld, const int32_t *col0,
+                                            const int32_t *ncols, int32_t count, int32_t N, int32_t frames, float value,
+                                            void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MORIG_CHECK_ARG(rowptr && out && ld && col0 && ncols && count >= 1 && count <= FILL_CUT_MAX && N > 0 && frames >= 1,
+                    "fill_cut_f32: count=%d (1..%d), N=%d, frames=%d", count, FILL_CUT_MAX, N, frames);
+    FillCut f;
+    f.count = count; f.N = N; f.frames = frames; f.value = value;
+    for (int i = 0; i < count; ++i) {
+        MORIG_CHECK_ARG(rowptr[i] && out[i] && ncols[i] > 0 && col0[i] >= 0 && ld[i] >= col0[i] + ncols[i] &&
+                        (reinterpret_cast<uintptr_t>(out[i]) & 15u) == 0, "fill_cut_f32: entry %d", i);
+        f.rowptr[i] = rowptr[i]; f.out[i] = out[i]; f.ld[i] = ld[i]; f.col0[i] = col0[i]; f.ncols[i] = ncols[i];
+    }
+    const int64_t blocks = ceil_div64((int64_t)N * count, 8);             // 8 warps per block, one (vertex, entry) per warp
+    MORIG_CUDA(launch_pdl(fill_cut_kernel, dim3((unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks)), dim3(256), 0, stream, f));
+    return 0;
+}
 
 extern "C" MORIG_API int morig_fill_many_f32(float *const *dst, const int64_t *n, int32_t count, float value, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

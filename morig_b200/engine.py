@@ -495,6 +495,24 @@ def fill_many(tensors, value: float) -> None:
         _end(tok)
 
 
+def fill_cut(entries, n: int, n_frames: int, value: float) -> None:
+    """`morig_fill_cut_f32`: start values for the rows the edge kernels merge atomically.  entries = (Graph, out, ld, col0,
+    ncols); one launch for up to 8 of them"""
+    entries = list(entries)
+    while entries:
+        chunk, entries = entries[:8], entries[8:]
+        k = len(chunk)
+        rp = (ctypes.c_void_p * k)(*[g.rowptr.data_ptr() for g, *_ in chunk])
+        op = (ctypes.c_void_p * k)(*[o.data_ptr() for _, o, *_ in chunk])
+        ld = (ctypes.c_int32 * k)(*[e[2] for e in chunk])
+        c0 = (ctypes.c_int32 * k)(*[e[3] for e in chunk])
+        nc = (ctypes.c_int32 * k)(*[e[4] for e in chunk])
+        tok = (_begin("fill", 1, 0.0, 4.0 * n * k) if (_counter is not None or _timer is not None) else None)
+        _lib.check(_lib.load().morig_fill_cut_f32(rp, op, ld, c0, nc, k, n, n_frames, value, _lib.stream_ptr()),
+                   "morig_fill_cut_f32")
+        _end(tok)
+
+
 def gather_cols(src: torch.Tensor, lds: int, src_off: int, frame_stride: int, cols: Optional[torch.Tensor], c: int,
                 n: int, n_frames: int, dst: torch.Tensor, ldd: int, dst_off: int) -> None:
     tok = _begin("gather_cols", 1, 0.0, 8.0 * n * n_frames * c) if (_counter is not None or _timer is not None) else None
@@ -530,8 +548,14 @@ def run_pos_branches(ws: Workspace, tags, gps, pqpos: torch.Tensor, gt: Graph, g
     R = n * n_frames
     ldpp = pqpos.shape[1]
     ecs = [_gcu_buffers(ws, tag, gp, R, dev)[1] for tag, gp in zip(tags, gps)]
-    # edge tiles merge the segments they cut with an (exact, ordered-int) atomic max: -inf start values, one launch
-    fill_many(ecs + list(also_fill), NEG_INF)
+    # edge tiles merge the segments they cut with an (exact, ordered-int) atomic max: -inf start values for exactly those
+    # vertices (per edge set: the CSR decides), one launch; the pooled feature gets a plain fill
+    gt.join()
+    gg.join()
+    fill_cut([(g, ec, 2 * (gp.H + gp.Dp), s * (gp.H + gp.Dp), gp.H + gp.Dp)
+              for gp, ec in zip(gps, ecs) for s, g in enumerate((gt, gg))], n, n_frames, NEG_INF)
+    if also_fill:
+        fill_many(list(also_fill), NEG_INF)
     for s, g in enumerate((gt, gg)):
         items = []
         for gp, ec in zip(gps, ecs):

@@ -84,6 +84,16 @@ def fill_many(tensors, value):
         t.fill_(value)
 
 
+def fill_cut(entries, n, n_frames, value):
+    """emulation of morig_fill_cut_f32 (include/morig_b200.h): the vertices whose CSR segment straddles a multiple of 32 slots"""
+    for g, out, ld, col0, ncols in entries:
+        rp = g.rowptr.long()
+        a, b = rp[:-1], rp[1:]
+        cut = (b > a) & ((a >> 5) != ((b - 1) >> 5))
+        rows = _view(out, 0, n * n_frames, ld, ld).reshape(n_frames, n, ld)
+        rows[:, cut, col0:col0 + ncols] = value
+
+
 def gather_cols(src, lds, src_off, frame_stride, cols, c, n, n_frames, dst, ldd, dst_off):
     cc = torch.arange(c) if cols is None else cols.long()
     for f in range(n_frames):
@@ -121,7 +131,7 @@ def _require(t, name, dtype=torch.float32):
 
 
 def install(monkeypatch):
-    for name in ("graph_prep", "dense", "edgeconv", "edgeconv_batch", "fill", "fill_many", "gather_cols", "row_normalize", "temporal_attn",
+    for name in ("graph_prep", "dense", "edgeconv", "edgeconv_batch", "fill", "fill_many", "fill_cut", "gather_cols", "row_normalize", "temporal_attn",
                  "frame_reduce"):
         monkeypatch.setattr(engine, name, globals()[name])
     monkeypatch.setattr(_lib, "require_cuda", _require)

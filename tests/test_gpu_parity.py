@@ -171,6 +171,28 @@ def test_edgeconv_tensor_core_kinds(H, frames, mag, kind):
         assert helpers.max_abs_diff(out[f * n:(f + 1) * n], ref) < 1e-5 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,e,frames", [(300, 2500, 1), (1024, 16384, 5), (64, 9000, 2)])
+def test_fill_cut_touches_exactly_the_straddling_segments(n, e, frames):
+    """morig_fill_cut_f32 (start values of the fused EdgeConv outputs): -inf lands on the vertices whose CSR segment straddles
+    a multiple of 32 slots, in every key-frame and only in the given column range; everything else keeps its content"""
+    g_ = torch.Generator().manual_seed(n + e)
+    ei = torch.randint(0, n, (2, e), generator=g_)
+    ei[1, : e // 3] = 7                                   # a hub: one long segment
+    g = engine.graph_prep(ei.to(DEV), n)
+    ld, col0, ncols = 52, 20, 24
+    out = torch.arange(frames * n * ld, dtype=torch.float32, device=DEV).reshape(frames * n, ld).contiguous()
+    want = out.clone().cpu().reshape(frames, n, ld)
+    engine.fill_cut([(g, out, ld, col0, ncols), (g, out, ld, 1, 3)], n, frames, float("-inf"))
+    rp = g.rowptr.cpu().long()
+    a, b = rp[:-1], rp[1:]
+    cut = (b > a) & ((a >> 5) != ((b - 1) >> 5))
+    assert bool(cut.any()) and (n == 64 or not bool(cut.all()))      # the 64-vertex case: every segment is long
+    want[:, cut, col0:col0 + ncols] = float("-inf")
+    want[:, cut, 1:4] = float("-inf")
+    assert torch.equal(out.cpu().reshape(frames, n, ld), want)
+
+
 @pytest.mark.parametrize("H,frames,repeat,n,e,ldo_pad", [(16, 1, 1, 1500, 12000, 0), (16, 1, 5, 1500, 12000, 3),
                                                         (32, 3, 1, 1500, 12000, 0), (32, 1, 1, 5, 3, 1),
                                                         (16, 2, 1, 40, 0, 0), (32, 5, 1, 4096, 61440, 0)])
