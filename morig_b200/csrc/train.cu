@@ -17,7 +17,9 @@
 //   row_gather / seg_sum repeat_interleave(x_global, bincount(batch)) and its gradient
 //   normalize fwd / bwd  F.normalize(dim=1)
 //   attn_cls fwd / bwd   cls-query attention over the key-frames (models/rignet.py:36-45)
+#include <stdlib.h>
 #include "common.cuh"
+#include "wgrad_tc.cuh"
 
 namespace morig {
 
@@ -649,18 +651,61 @@ extern "C" MORIG_API int morig_transpose_pad_f32(const float *src, int32_t rows,
 
 static inline int wgrad_tile(int N, int K) { return (N <= 64 && K <= 64) ? 64 : 128; }
 
-extern "C" MORIG_API int32_t morig_wgrad_splits(int32_t M, int32_t N, int32_t K) {
+// launch geometry of a weight gradient: tensor-core kernel (csrc/wgrad_tc.cuh) for layers that fill a 128-row tile and
+// have enough rows to amortise its set-up, CUDA-core kernel otherwise (narrow layers, tiny batches, MORIG_TRAIN_TC=0)
+struct WgradPlan { int tc, bkw, splits, rows; };
+static WgradPlan wgrad_plan(int M, int N, int K) {
+    static int tc_off = -1;
+    if (tc_off < 0) {
+        const char *e = getenv("MORIG_TRAIN_TC");
+        tc_off = (e && e[0] == '0') ? 1 : 0;
+    }
+    WgradPlan p{};
+    p.tc = (!tc_off && M >= 2048 && N >= 64 && K >= 64) ? 1 : 0;
+    if (p.tc) {
+        p.bkw = K > 128 ? 256 : 128;
+        const int tiles = ceil_div(N, tcw::W_BN) * ceil_div(K, p.bkw);
+        int want = ceil_div(sm_count(), tiles);                     // one CTA per SM, about one wave
+        const int max_by_rows = M / 512;                            // at least 16 stages of 32 rows per slice
+        if (want > max_by_rows) want = max_by_rows;
+        if (want > 256) want = 256;
+        p.splits = want < 1 ? 1 : want;
+        p.rows = ceil_div(ceil_div(M, p.splits), tcw::W_ROWS) * tcw::W_ROWS;
+        return p;
+    }
     const int WG_T = wgrad_tile(N, K);
     const int tiles = ceil_div(N, WG_T) * ceil_div(K, WG_T);
     int want = ceil_div(2 * sm_count() * 2, tiles);                 // ~2 waves of 2 CTAs per SM
     const int max_by_rows = ceil_div(M, 4 * WG_M);                  // at least 64 rows per split
     if (want > max_by_rows) want = max_by_rows;
     if (want > 256) want = 256;
-    return want < 1 ? 1 : want;
+    p.splits = want < 1 ? 1 : want;
+    p.rows = ceil_div(ceil_div(M, p.splits), WG_M) * WG_M;
+    return p;
 }
+
+extern "C" MORIG_API int32_t morig_wgrad_splits(int32_t M, int32_t N, int32_t K) { return wgrad_plan(M, N, K).splits; }
 
 extern "C" MORIG_API size_t morig_wgrad_workspace(int32_t M, int32_t N, int32_t K) {
     return (size_t)morig_wgrad_splits(M, N, K) * ((size_t)N * K + N) * sizeof(float);
+}
+
+template <int BKW>
+static int launch_wgrad_tc(const float *dY, int lddy, const float *X, int ldx, int M, int N, int K, const WgradPlan &pl, float *part,
+                           float *part_b, cudaStream_t stream) {
+    auto kern = tcw::wgrad_tc_kernel<BKW>;
+    constexpr int smem = tcw::WCfg<BKW>::SMEM;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    MORIG_CUDA(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        MORIG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured_dev = dev;
+    }
+    kern<<<dim3(ceil_div(N, tcw::W_BN), ceil_div(K, BKW), pl.splits), tcw::W_THREADS, smem, stream>>>(dY, lddy, X, ldx, M, N, K, pl.rows,
+                                                                                                     part, part_b);
+    MORIG_LAUNCH_CHECK("wgrad_tc_kernel");
+    return 0;
 }
 
 extern "C" MORIG_API int morig_wgrad_f32(const float *dY, int32_t lddy, const float *X, int32_t ldx, int32_t M, int32_t N,
@@ -668,23 +713,32 @@ extern "C" MORIG_API int morig_wgrad_f32(const float *dY, int32_t lddy, const fl
                                          float *dbias, int32_t accumulate, void *ws, size_t ws_bytes, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MORIG_CHECK_ARG(dY && X && dW && M > 0 && N > 0 && K > 0 && lddy >= N && ldx >= K && lddw >= K, "wgrad: bad argument");
-    const int splits = morig_wgrad_splits(M, N, K);
+    WgradPlan pl = wgrad_plan(M, N, K);
+    const int splits = pl.splits;
     if (ws_bytes < (size_t)splits * ((size_t)N * K + N) * sizeof(float) || !ws) {
         set_error("wgrad: workspace too small");
         return MORIG_E_WORKSPACE;
     }
-    int rows = ceil_div(M, splits);
-    rows = ceil_div(rows, WG_M) * WG_M;
     float *part = reinterpret_cast<float *>(ws);
     float *part_b = part + (size_t)splits * N * K;
-    const int vec_y = (lddy % 4 == 0 && aligned16p(dY)) ? 1 : 0, vec_x = (ldx % 4 == 0 && aligned16p(X)) ? 1 : 0;
-    if (wgrad_tile(N, K) == 64)
-        wgrad_kernel<64><<<dim3(ceil_div(N, 64), ceil_div(K, 64), splits), WG_THREADS, 0, stream>>>(
-            dY, lddy, X, ldx, M, N, K, x_scale, x_shift, rows, part, dbias ? part_b : nullptr, vec_y, vec_x);
-    else
-        wgrad_kernel<128><<<dim3(ceil_div(N, 128), ceil_div(K, 128), splits), WG_THREADS, 0, stream>>>(
-            dY, lddy, X, ldx, M, N, K, x_scale, x_shift, rows, part, dbias ? part_b : nullptr, vec_y, vec_x);
-    MORIG_LAUNCH_CHECK("wgrad_kernel");
+    if (pl.tc && !x_scale && !x_shift) {
+        if (int rc = (pl.bkw == 256) ? launch_wgrad_tc<256>(dY, lddy, X, ldx, M, N, K, pl, part, dbias ? part_b : nullptr, stream)
+                                     : launch_wgrad_tc<128>(dY, lddy, X, ldx, M, N, K, pl, part, dbias ? part_b : nullptr, stream))
+            return rc;
+    } else {
+        if (pl.tc) {                                 // column affine on X: CUDA-core kernel with the tensor-core plan's slices
+            pl.rows = ceil_div(pl.rows, WG_M) * WG_M;
+        }
+        const int rows = pl.rows;
+        const int vec_y = (lddy % 4 == 0 && aligned16p(dY)) ? 1 : 0, vec_x = (ldx % 4 == 0 && aligned16p(X)) ? 1 : 0;
+        if (wgrad_tile(N, K) == 64)
+            wgrad_kernel<64><<<dim3(ceil_div(N, 64), ceil_div(K, 64), splits), WG_THREADS, 0, stream>>>(
+                dY, lddy, X, ldx, M, N, K, x_scale, x_shift, rows, part, dbias ? part_b : nullptr, vec_y, vec_x);
+        else
+            wgrad_kernel<128><<<dim3(ceil_div(N, 128), ceil_div(K, 128), splits), WG_THREADS, 0, stream>>>(
+                dY, lddy, X, ldx, M, N, K, x_scale, x_shift, rows, part, dbias ? part_b : nullptr, vec_y, vec_x);
+        MORIG_LAUNCH_CHECK("wgrad_kernel");
+    }
     wgrad_reduce_kernel<<<grid1d((int64_t)N * K + N, 256, 8), 256, 0, stream>>>(part, dbias ? part_b : nullptr, splits, N, K, dW,
                                                                                lddw, dbias, accumulate);
     MORIG_LAUNCH_CHECK("wgrad_reduce_kernel");

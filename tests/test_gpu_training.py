@@ -38,6 +38,24 @@ def test_linear_fwd_input_grad_and_wgrad(M, K, N):
     assert close(dW, dy.double().t() @ x.double(), 1e-5) and close(db, dy.double().sum(0), 1e-5)
 
 
+@pytest.mark.parametrize("M,N,K,pad", [(5000, 64, 64, 0), (40000, 200, 130, 3), (3000, 1024, 300, 0), (2048, 128, 1000, 5),
+                                       (70001, 256, 256, 0)])
+def test_wgrad_tensor_core_kernel(M, N, K, pad):
+    """csrc/wgrad_tc.cuh (3xTF32 tcgen05, transposing producers): ragged tile edges, row slices that do not fill a stage,
+    operands that are column slices of wider buffers; and an integer-valued case that must be exact"""
+    g = g_(M + N + K)
+    dy_full = torch.randn(M, N + pad, generator=g).to(DEV)
+    x_full = (torch.randn(M, K + 2 * pad, generator=g) * 3 + 0.5).to(DEV)
+    dy, x = dy_full[:, pad:], x_full[:, pad:pad + K]
+    dW, db = T.wgrad(dy, x, True)
+    assert close(dW, dy.cpu().double().t() @ x.cpu().double(), 1e-5) and close(db, dy.cpu().double().sum(0), 1e-5)
+    dyi = torch.randint(-3, 4, (M, N), generator=g).float().to(DEV)
+    xi = torch.randint(-4, 5, (M, K), generator=g).float().to(DEV)
+    dWi, dbi = T.wgrad(dyi, xi, True)
+    assert torch.equal(dWi.cpu().double(), dyi.cpu().double().t() @ xi.cpu().double())
+    assert torch.equal(dbi.cpu().double(), dyi.cpu().double().sum(0))
+
+
 def test_kernels_take_column_slices_in_place():
     """row strides are passed down: column slices of wider buffers (P / Q halves, key-frame slices of the flow, slices
     of a concatenated gradient) are used without copies"""
