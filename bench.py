@@ -331,7 +331,7 @@ def run_ours(args):
         ms_train = float(t.item()) / args.train_steps
         train = {"ms_per_step": ms_train, "meshes_per_s": MESHES_PER_GPU * world / (ms_train / 1e3),
                  "steps": args.train_steps, "allreduce_bytes_per_step": nbytes, "buckets": len(ar.buckets),
-                 "what": "forward + backward (train-mode BatchNorm, fp32 CUDA-core GEMMs) + flat-buffer gradient all-reduce, "
+                 "what": "forward + backward (train-mode BatchNorm; forward / input-gradient GEMMs on the tcgen05 split-fp16 engine, weight gradients 3xTF32 tcgen05) + flat-buffer gradient all-reduce, "
                          "max over ranks; BatchNorm statistics per replica",
                  "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
         ar.close()
