@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MORIG_ABI_VERSION 6
+#define MORIG_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define MORIG_API __attribute__((visibility("default")))
@@ -353,7 +353,7 @@ MORIG_API int    morig_wgrad_f32(const float *dY, int32_t lddy, const float *X, 
 MORIG_API size_t morig_colstats_workspace(int32_t R, int32_t C);
 MORIG_API int    morig_bn_train_fwd(const float *x, int32_t ldx, int32_t R, int32_t C, const float *gamma, const float *beta,
                                     float eps, float momentum, float *running_mean, float *running_var, float *mean,
-                                    float *invstd, float *scale, float *shift, float *y, int32_t ldy, void *ws,
+                                    float *invstd, float *scale, float *shift, float *y, int32_t ldy, float *y_amax, void *ws,
                                     size_t ws_bytes, void *stream);
 
 /* y = x * scale[c] + shift[c] (per column): the apply step of the BatchNorm above on its own; also the 1 / T of the
@@ -366,8 +366,8 @@ MORIG_API int    morig_col_affine(const float *x, int32_t ldx, int32_t R, int32_
  * coef: scratch [3 C].  dz may alias dy. */
 MORIG_API int    morig_bn_relu_bwd(const float *dy, int32_t lddy, const float *x, int32_t ldx, int32_t R, int32_t C,
                                    const float *gamma, const float *mean, const float *invstd, int32_t relu, float *dz,
-                                   int32_t lddz, float *dgamma, float *dbeta, float *coef, void *ws, size_t ws_bytes,
-                                   void *stream);
+                                   int32_t lddz, float *dgamma, float *dbeta, float *coef, float *dz_amax, void *ws,
+                                   size_t ws_bytes, void *stream);
 /* dz = [y > 0] * dy */
 MORIG_API int    morig_relu_bwd(const float *dy, int32_t lddy, const float *y, int32_t ldy, int32_t R, int32_t C, float *dz,
                                 int32_t lddz, void *stream);
@@ -376,7 +376,8 @@ MORIG_API int    morig_relu_bwd(const float *dy, int32_t lddy, const float *y, i
  * valid CSR slots (models/basic_modules.py:193-194); backward: dP[v] = sum over v's in-edges, dQ[u] = sum over u's
  * out-edges of [h > 0] * dh (both overwritten) */
 MORIG_API int    morig_edge_gather_relu(const float *P, int32_t ldp, const float *Q, int32_t ldq, const int32_t *tgt,
-                                        const int32_t *col, int32_t E, int32_t C, float *h, int32_t ldh, void *stream);
+                                        const int32_t *col, int32_t E, int32_t C, float *h, int32_t ldh, float *h_amax,
+                                        void *stream);
 MORIG_API int    morig_edge_gather_relu_bwd(const float *dh, int32_t lddh, const float *h, int32_t ldh, const int32_t *rowptr,
                                             const int32_t *col, int32_t N, int32_t E, int32_t C, float *dP, int32_t ldp,
                                             float *dQ, int32_t ldq, void *stream);

@@ -117,12 +117,12 @@ _SIGNATURES = {
     "morig_wgrad_workspace": (C.c_size_t, [_I, _I, _I]),
     "morig_wgrad_f32": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _I, _P, C.c_size_t, _P]),
     "morig_colstats_workspace": (C.c_size_t, [_I, _I]),
-    "morig_bn_train_fwd": (C.c_int, [_P, _I, _I, _I, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P, _I, _P,
+    "morig_bn_train_fwd": (C.c_int, [_P, _I, _I, _I, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P,
                                      C.c_size_t, _P]),
-    "morig_bn_relu_bwd": (C.c_int, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P, C.c_size_t, _P]),
+    "morig_bn_relu_bwd": (C.c_int, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "morig_col_affine": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _I, _P]),
     "morig_relu_bwd": (C.c_int, [_P, _I, _P, _I, _I, _I, _P, _I, _P]),
-    "morig_edge_gather_relu": (C.c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _P, _I, _P]),
+    "morig_edge_gather_relu": (C.c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _P, _I, _P, _P]),
     "morig_edge_gather_relu_bwd": (C.c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P, _I, _P, _I, _P]),
     "morig_segmax_fwd": (C.c_int, [_P, _I, _P, _I, _I, _P, _I, _P, _I, _P]),
     "morig_segmax_bwd": (C.c_int, [_P, _I, _P, _I, _I, _I, _P, _I, _I, _P]),
@@ -137,7 +137,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
-ABI_VERSION = 6
+ABI_VERSION = 7
 _lib = None
 
 

@@ -57,6 +57,23 @@ __device__ __forceinline__ void amax_commit(float *amax, float v) {
     if (amax && (threadIdx.x & 31) == 0 && v > 0.f) atomicMax(reinterpret_cast<int *>(amax), __float_as_int(v));
 }
 
+// the same for a whole thread block (blockDim.x a multiple of 32, at most 1024): ONE atomic per block -- same-address
+// atomics serialise, so the memory-bound row kernels must not issue one per warp.  Must be reached by every thread.
+__device__ __forceinline__ void amax_commit_block(float *amax, float v) {
+    __shared__ float s_am[32];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) s_am[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < nw ? s_am[lane] : 0.f;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+        if (amax && lane == 0 && v > 0.f) atomicMax(reinterpret_cast<int *>(amax), __float_as_int(v));
+    }
+}
+
 // ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------------
 // The forward is ~70 dependent launches in one stream (or one replayed CUDA graph); with the launch attribute below the
 // next kernel's CTAs may become resident as soon as every CTA of the current one has executed pdl_trigger() (or exited)

@@ -143,9 +143,19 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float *__restrict__ x
     float am = 0.f;
     pdl_trigger();
     pdl_wait();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
-        am = fmaxf(am, fabsf(x[(size_t)(i / C) * ldx + (i % C)]));
-    amax_commit(amax, am);
+    if (((C | ldx) & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) {       // 16-byte loads
+        const int C4 = C >> 2;
+        const int64_t total4 = (int64_t)R * C4;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = i / C4;
+            const float4 v = *reinterpret_cast<const float4 *>(x + (size_t)r * ldx + 4 * (i - r * C4));
+            am = fmaxf(fmaxf(am, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+            am = fmaxf(am, fabsf(x[(size_t)(i / C) * ldx + (i % C)]));
+    }
+    amax_commit_block(amax, am);
 }
 
 __global__ void fill_kernel(float *dst, int64_t n, float value) {

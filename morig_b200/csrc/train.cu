@@ -18,12 +18,19 @@
 //   normalize fwd / bwd  F.normalize(dim=1)
 //   attn_cls fwd / bwd   cls-query attention over the key-frames (models/rignet.py:36-45)
 #include <stdlib.h>
+#include <initializer_list>
 #include "common.cuh"
 #include "wgrad_tc.cuh"
 
 namespace morig {
 
 static inline bool aligned16p(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool vec4_ok(int C, std::initializer_list<int> lds, std::initializer_list<const void *> ptrs) {
+    if (C % 4) return false;
+    for (int ld : lds) if (ld % 4) return false;
+    for (const void *p : ptrs) if (!aligned16p(p)) return false;
+    return true;
+}
 
 // ---- W [rows, cols] (row stride lds) -> dst [cols, ldd], dst[c][r] = src[r][c], columns r >= rows zero -------------------
 __global__ void __launch_bounds__(256) transpose_pad_kernel(const float *__restrict__ src, int rows, int cols, int lds,
@@ -200,7 +207,23 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float *__restrict__
     const int r_begin = blockIdx.y * rows_per_chunk, r_end = min(R, r_begin + rows_per_chunk);
     double a0 = 0.0, a1 = 0.0;
     if (c < C) {
-        for (int r = r_begin + ry; r < r_end; r += 8) {
+        // four rows in flight per thread (one 4-byte load per row and thread would leave the kernel latency bound at a
+        // third of the HBM rate); the sums are still taken row by row in ascending order
+        int r = r_begin + ry;
+        for (; r + 24 < r_end; r += 32) {
+            float xv[4], yv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                xv[u] = X[(size_t)(r + 8 * u) * ldx + c];
+                yv[u] = Y ? Y[(size_t)(r + 8 * u) * ldy + c] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (Y) { a0 += (double)yv[u]; a1 += (double)yv[u] * (double)xv[u]; }
+                else { a0 += (double)xv[u]; a1 += (double)xv[u] * (double)xv[u]; }
+            }
+        }
+        for (; r < r_end; r += 8) {
             const float x = X[(size_t)r * ldx + c];
             if (Y) {
                 const float y = Y[(size_t)r * ldy + c];
@@ -279,32 +302,69 @@ __global__ void __launch_bounds__(256) bn_finalize_bwd_kernel(const double *__re
     coef[2 * C + c] = (float)(dg / R);                               // m2 = mean(dy * xhat)
 }
 
+// Row-wise element kernels below: VEC = 1 handles four consecutive columns per thread with 16-byte accesses (C, the row
+// strides and the base addresses multiples of 4 floats / 16 bytes -- every wide layer of the networks); the scalar form
+// ran at a third to a half of the HBM rate.  `amax` (optional) receives max |output| through one ordered-int atomic per
+// warp: the fp16-split tensor-core GEMM that consumes the output needs its range and would otherwise re-read it.
+template <int VEC>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float *__restrict__ x, int ldx, int R, int C,
                                                        const float *__restrict__ scale, const float *__restrict__ shift,
-                                                       float *__restrict__ y, int ldy) {
-    const int64_t total = (int64_t)R * C;
+                                                       float *__restrict__ y, int ldy, float *amax) {
+    constexpr int W = VEC ? 4 : 1;
+    const int CW = C / W;
+    const int64_t total = (int64_t)R * CW;
+    float am = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const int64_t r = i / C;
-        y[(size_t)r * ldy + c] = fmaf(x[(size_t)r * ldx + c], scale[c], shift[c]);
+        const int64_t r = i / CW;
+        const int c = (int)(i - r * CW) * W;
+        if (VEC) {
+            const float4 v = *reinterpret_cast<const float4 *>(x + (size_t)r * ldx + c);
+            const float4 sc = *reinterpret_cast<const float4 *>(scale + c), sh = *reinterpret_cast<const float4 *>(shift + c);
+            const float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+            *reinterpret_cast<float4 *>(y + (size_t)r * ldy + c) = o;
+            am = fmaxf(fmaxf(am, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+        } else {
+            const float o = fmaf(x[(size_t)r * ldx + c], scale[c], shift[c]);
+            y[(size_t)r * ldy + c] = o;
+            am = fmaxf(am, fabsf(o));
+        }
     }
+    if (amax) amax_commit_block(amax, am);
 }
 
 // dz = mask * a * (dy - m1 - xhat * m2), xhat = (x - mean) * invstd; mask = [x > 0] when the block has a ReLU in front of
 // the BatchNorm (x is the ReLU output, so x > 0 <=> pre-activation > 0; torch's relu'(0) = 0)
+template <int VEC>
 __global__ void __launch_bounds__(256) bn_relu_bwd_kernel(const float *__restrict__ dy, int lddy, const float *__restrict__ x,
                                                           int ldx, int R, int C, const float *__restrict__ mean,
                                                           const float *__restrict__ invstd, const float *__restrict__ coef,
-                                                          int relu, float *__restrict__ dz, int lddz) {
-    const int64_t total = (int64_t)R * C;
+                                                          int relu, float *__restrict__ dz, int lddz, float *amax) {
+    constexpr int W = VEC ? 4 : 1;
+    const int CW = C / W;
+    const int64_t total = (int64_t)R * CW;
+    float am = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const int64_t r = i / C;
-        const float xv = x[(size_t)r * ldx + c];
-        const float xhat = (xv - mean[c]) * invstd[c];
-        const float g = coef[c] * (dy[(size_t)r * lddy + c] - coef[C + c] - xhat * coef[2 * C + c]);
-        dz[(size_t)r * lddz + c] = (!relu || xv > 0.f) ? g : 0.f;
+        const int64_t r = i / CW;
+        const int c = (int)(i - r * CW) * W;
+        float xv[W], dv[W], o[W];
+        if (VEC) {
+            *reinterpret_cast<float4 *>(xv) = *reinterpret_cast<const float4 *>(x + (size_t)r * ldx + c);
+            *reinterpret_cast<float4 *>(dv) = *reinterpret_cast<const float4 *>(dy + (size_t)r * lddy + c);
+        } else {
+            xv[0] = x[(size_t)r * ldx + c];
+            dv[0] = dy[(size_t)r * lddy + c];
+        }
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            const float xhat = (xv[q] - mean[c + q]) * invstd[c + q];
+            const float g = coef[c + q] * (dv[q] - coef[C + c + q] - xhat * coef[2 * C + c + q]);
+            o[q] = (!relu || xv[q] > 0.f) ? g : 0.f;
+            am = fmaxf(am, fabsf(o[q]));
+        }
+        if (VEC) *reinterpret_cast<float4 *>(dz + (size_t)r * lddz + c) = *reinterpret_cast<const float4 *>(o);
+        else dz[(size_t)r * lddz + c] = o[0];
     }
+    if (amax) amax_commit_block(amax, am);
 }
 
 // dz = [y > 0] * dy : backward of a bare ReLU (Linear -> ReLU without BatchNorm is not used by the rigging nets, but the
@@ -320,16 +380,31 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const float *__restrict__
 }
 
 // ---- per-edge first layer after factorisation: h[e] = relu(P[tgt[e]] + Q[col[e]]) --------------------------------------
+template <int VEC>
 __global__ void __launch_bounds__(256) edge_gather_relu_kernel(const float *__restrict__ P, int ldp, const float *__restrict__ Q,
                                                                int ldq, const int32_t *__restrict__ tgt,
                                                                const int32_t *__restrict__ col, int E, int C,
-                                                               float *__restrict__ h, int ldh) {
-    const int64_t total = (int64_t)E * C;
+                                                               float *__restrict__ h, int ldh, float *amax) {
+    constexpr int W = VEC ? 4 : 1;
+    const int CW = C / W;
+    const int64_t total = (int64_t)E * CW;
+    float am = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const int e = (int)(i / C);
-        h[(size_t)e * ldh + c] = fmaxf(P[(size_t)tgt[e] * ldp + c] + Q[(size_t)col[e] * ldq + c], 0.f);
+        const int e = (int)(i / CW);
+        const int c = (int)(i - (int64_t)e * CW) * W;
+        if (VEC) {
+            const float4 a = *reinterpret_cast<const float4 *>(P + (size_t)tgt[e] * ldp + c);
+            const float4 b = *reinterpret_cast<const float4 *>(Q + (size_t)col[e] * ldq + c);
+            const float4 o = make_float4(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f));
+            *reinterpret_cast<float4 *>(h + (size_t)e * ldh + c) = o;
+            am = fmaxf(fmaxf(am, fmaxf(o.x, o.y)), fmaxf(o.z, o.w));
+        } else {
+            const float o = fmaxf(P[(size_t)tgt[e] * ldp + c] + Q[(size_t)col[e] * ldq + c], 0.f);
+            h[(size_t)e * ldh + c] = o;
+            am = fmaxf(am, o);
+        }
     }
+    if (amax) amax_commit_block(amax, am);
 }
 
 // dP[v] = sum over the CSR segment of v of [h > 0] dh   (one thread per (v, c): fixed order)
@@ -665,7 +740,7 @@ static WgradPlan wgrad_plan(int M, int N, int K) {
     if (p.tc) {
         p.bkw = K > 128 ? 256 : 128;
         const int tiles = ceil_div(N, tcw::W_BN) * ceil_div(K, p.bkw);
-        int want = ceil_div(sm_count(), tiles);                     // one CTA per SM, about one wave
+        int want = sm_count() / tiles;                              // one CTA per SM, at most one wave
         const int max_by_rows = M / 512;                            // at least 16 stages of 32 rows per slice
         if (want > max_by_rows) want = max_by_rows;
         if (want > 256) want = 256;
@@ -771,7 +846,7 @@ static int launch_colstats(const float *X, int ldx, const float *Y, int ldy, int
 extern "C" MORIG_API int morig_bn_train_fwd(const float *x, int32_t ldx, int32_t R, int32_t C, const float *gamma,
                                             const float *beta, float eps, float momentum, float *running_mean,
                                             float *running_var, float *mean, float *invstd, float *scale, float *shift,
-                                            float *y, int32_t ldy, void *ws, size_t ws_bytes, void *stream_) {
+                                            float *y, int32_t ldy, float *y_amax, void *ws, size_t ws_bytes, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MORIG_CHECK_ARG(x && mean && invstd && scale && shift && R > 0 && C > 0 && ldx >= C, "bn_train_fwd: bad argument");
     if (!ws || ws_bytes < morig_colstats_workspace(R, C)) { set_error("bn_train_fwd: workspace too small"); return MORIG_E_WORKSPACE; }
@@ -783,7 +858,10 @@ extern "C" MORIG_API int morig_bn_train_fwd(const float *x, int32_t ldx, int32_t
     MORIG_LAUNCH_CHECK("bn_finalize_fwd_kernel");
     if (y) {
         MORIG_CHECK_ARG(ldy >= C, "bn_train_fwd: ldy < C");
-        bn_apply_kernel<<<grid1d((int64_t)R * C, 256, 8), 256, 0, stream>>>(x, ldx, R, C, scale, shift, y, ldy);
+        if (vec4_ok(C, {ldx, ldy}, {x, y, scale, shift}))
+            bn_apply_kernel<1><<<grid1d((int64_t)R * C / 4, 256, 8), 256, 0, stream>>>(x, ldx, R, C, scale, shift, y, ldy, y_amax);
+        else
+            bn_apply_kernel<0><<<grid1d((int64_t)R * C, 256, 8), 256, 0, stream>>>(x, ldx, R, C, scale, shift, y, ldy, y_amax);
         MORIG_LAUNCH_CHECK("bn_apply_kernel");
     }
     return 0;
@@ -793,7 +871,10 @@ extern "C" MORIG_API int morig_col_affine(const float *x, int32_t ldx, int32_t R
                                           float *y, int32_t ldy, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MORIG_CHECK_ARG(x && y && scale && shift && R > 0 && C > 0 && ldx >= C && ldy >= C, "col_affine: bad argument");
-    bn_apply_kernel<<<grid1d((int64_t)R * C, 256, 8), 256, 0, stream>>>(x, ldx, R, C, scale, shift, y, ldy);
+    if (vec4_ok(C, {ldx, ldy}, {x, y, scale, shift}))
+        bn_apply_kernel<1><<<grid1d((int64_t)R * C / 4, 256, 8), 256, 0, stream>>>(x, ldx, R, C, scale, shift, y, ldy, nullptr);
+    else
+        bn_apply_kernel<0><<<grid1d((int64_t)R * C, 256, 8), 256, 0, stream>>>(x, ldx, R, C, scale, shift, y, ldy, nullptr);
     MORIG_LAUNCH_CHECK("bn_apply_kernel");
     return 0;
 }
@@ -801,8 +882,8 @@ extern "C" MORIG_API int morig_col_affine(const float *x, int32_t ldx, int32_t R
 /* backward of Linear -> [ReLU] -> BatchNorm(train) at the BatchNorm input x (= ReLU output): dz, dgamma, dbeta */
 extern "C" MORIG_API int morig_bn_relu_bwd(const float *dy, int32_t lddy, const float *x, int32_t ldx, int32_t R, int32_t C,
                                            const float *gamma, const float *mean, const float *invstd, int32_t relu,
-                                           float *dz, int32_t lddz, float *dgamma, float *dbeta, float *coef, void *ws,
-                                           size_t ws_bytes, void *stream_) {
+                                           float *dz, int32_t lddz, float *dgamma, float *dbeta, float *coef, float *dz_amax,
+                                           void *ws, size_t ws_bytes, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MORIG_CHECK_ARG(dy && x && mean && invstd && dz && coef && R > 0 && C > 0 && lddy >= C && ldx >= C && lddz >= C,
                     "bn_relu_bwd: bad argument");
@@ -812,8 +893,12 @@ extern "C" MORIG_API int morig_bn_relu_bwd(const float *dy, int32_t lddy, const 
     bn_finalize_bwd_kernel<<<ceil_div(C * 32, 256), 256, 0, stream>>>(reinterpret_cast<double *>(ws), chunks, R, C, gamma, mean, invstd,
                                                                 dgamma, dbeta, coef);
     MORIG_LAUNCH_CHECK("bn_finalize_bwd_kernel");
-    bn_relu_bwd_kernel<<<grid1d((int64_t)R * C, 256, 8), 256, 0, stream>>>(dy, lddy, x, ldx, R, C, mean, invstd, coef, relu, dz,
-                                                                          lddz);
+    if (vec4_ok(C, {lddy, ldx, lddz}, {dy, x, dz}))
+        bn_relu_bwd_kernel<1><<<grid1d((int64_t)R * C / 4, 256, 8), 256, 0, stream>>>(dy, lddy, x, ldx, R, C, mean, invstd, coef, relu,
+                                                                                    dz, lddz, dz_amax);
+    else
+        bn_relu_bwd_kernel<0><<<grid1d((int64_t)R * C, 256, 8), 256, 0, stream>>>(dy, lddy, x, ldx, R, C, mean, invstd, coef, relu, dz,
+                                                                                 lddz, dz_amax);
     MORIG_LAUNCH_CHECK("bn_relu_bwd_kernel");
     return 0;
 }
@@ -829,10 +914,13 @@ extern "C" MORIG_API int morig_relu_bwd(const float *dy, int32_t lddy, const flo
 
 extern "C" MORIG_API int morig_edge_gather_relu(const float *P, int32_t ldp, const float *Q, int32_t ldq, const int32_t *tgt,
                                                 const int32_t *col, int32_t E, int32_t C, float *h, int32_t ldh,
-                                                void *stream_) {
+                                                float *h_amax, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MORIG_CHECK_ARG(P && Q && tgt && col && h && E > 0 && C > 0 && ldh >= C, "edge_gather_relu: bad argument");
-    edge_gather_relu_kernel<<<grid1d((int64_t)E * C, 256, 8), 256, 0, stream>>>(P, ldp, Q, ldq, tgt, col, E, C, h, ldh);
+    if (vec4_ok(C, {ldp, ldq, ldh}, {P, Q, h}))
+        edge_gather_relu_kernel<1><<<grid1d((int64_t)E * C / 4, 256, 8), 256, 0, stream>>>(P, ldp, Q, ldq, tgt, col, E, C, h, ldh, h_amax);
+    else
+        edge_gather_relu_kernel<0><<<grid1d((int64_t)E * C, 256, 8), 256, 0, stream>>>(P, ldp, Q, ldq, tgt, col, E, C, h, ldh, h_amax);
     MORIG_LAUNCH_CHECK("edge_gather_relu_kernel");
     return 0;
 }

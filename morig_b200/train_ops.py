@@ -43,6 +43,26 @@ def _sp() -> int:
     return _lib.stream_ptr()
 
 
+# ---- operand ranges for the fp16-split tensor-core GEMMs -------------------------------------------------------------------
+# The kernels that produce the big activation / gradient matrices (BatchNorm apply, BatchNorm-ReLU backward, edge gather)
+# also reduce max |output| into a device scalar, which travels with the tensor object as `_morig_amax` =
+# (scalar, data_ptr, version).  A consumer only trusts it for exactly that tensor in exactly that state; anything else
+# (views, copies, in-place edits, tensors from elsewhere) falls back to the |max| pass of `engine._amax_in`.
+def _new_amax(dev) -> torch.Tensor:
+    return torch.zeros(1, dtype=torch.float32, device=dev)
+
+
+def _tag_amax(t: torch.Tensor, amax: torch.Tensor) -> None:
+    t._morig_amax = (amax, t.data_ptr(), t._version)
+
+
+def _known_amax(t: torch.Tensor) -> int:
+    tag = getattr(t, "_morig_amax", None)
+    if tag is not None and tag[1] == t.data_ptr() and tag[2] == t._version and tag[0].device == t.device:
+        return tag[0].data_ptr()
+    return 0
+
+
 def _tc_ok(M: int, K: int, N: int, A: torch.Tensor) -> bool:
     """shapes the tcgen05 split-fp16 engine takes (csrc/gemm_tc.cuh); MORIG_TRAIN_TC=0 keeps training on the fp32 engine"""
     import os
@@ -56,7 +76,11 @@ def dense_tc(A: torch.Tensor, w: torch.Tensor, transposed: bool, n_out: int, k: 
     the fp16-split weight image is packed on the device (the weights change every optimisation step)"""
     from . import engine, packing
     lib = _lib.load()
+    known = _known_amax(A)
+    A0 = A
     A = mat(A)
+    if A is not A0:
+        known = 0
     M = A.shape[0]
     dev = A.device
     bn = packing.tc_tile_n(n_out)
@@ -75,7 +99,7 @@ def dense_tc(A: torch.Tensor, w: torch.Tensor, transposed: bool, n_out: int, k: 
     d.relu = 1 if relu else 0
     d.Wtc, d.tc_bn, d.tc_kind, d.tc_w_inv = blob.data_ptr(), bn, packing.KIND_F16, 0.0
     d.tc_w_inv_dev = scal.data_ptr()
-    d.a_amax = engine._amax_in(A, 0, _ld(A), M, k)
+    d.a_amax = known if (known and A.shape[1] == k) else engine._amax_in(A, 0, _ld(A), M, k)
     _lib.check(lib.morig_dense_fwd(ctypes.byref(d), _sp()), "morig_dense_fwd")
     return C_
 
@@ -155,12 +179,14 @@ def bn_train_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, runni
     dev = x.device
     y = torch.empty(R, C, dtype=torch.float32, device=dev)
     stats = torch.empty(4, C, dtype=torch.float32, device=dev)          # mean, invstd, scale, shift
+    amax = _new_amax(dev)
     nbytes = lib.morig_colstats_workspace(R, C)
     ws = _ws(nbytes, dev)
     _lib.check(lib.morig_bn_train_fwd(x.data_ptr(), _ld(x), R, C, gamma.data_ptr(), beta.data_ptr(), eps, momentum,
                                       _lib.ptr(running_mean), _lib.ptr(running_var), stats[0].data_ptr(),
                                       stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(), y.data_ptr(), C,
-                                      ws.data_ptr(), nbytes, _sp()), "morig_bn_train_fwd")
+                                      amax.data_ptr(), ws.data_ptr(), nbytes, _sp()), "morig_bn_train_fwd")
+    _tag_amax(y, amax)
     return y, stats[0], stats[1]
 
 
@@ -175,11 +201,13 @@ def bn_relu_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: to
     dg = torch.empty(C, dtype=torch.float32, device=dev)
     db = torch.empty(C, dtype=torch.float32, device=dev)
     coef = torch.empty(3 * C, dtype=torch.float32, device=dev)
+    amax = _new_amax(dev)
     nbytes = lib.morig_colstats_workspace(R, C)
     ws = _ws(nbytes, dev)
     _lib.check(lib.morig_bn_relu_bwd(dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), R, C, gamma.data_ptr(), mean.data_ptr(),
                                      invstd.data_ptr(), 1 if relu else 0, dz.data_ptr(), C, dg.data_ptr(), db.data_ptr(),
-                                     coef.data_ptr(), ws.data_ptr(), nbytes, _sp()), "morig_bn_relu_bwd")
+                                     coef.data_ptr(), amax.data_ptr(), ws.data_ptr(), nbytes, _sp()), "morig_bn_relu_bwd")
+    _tag_amax(dz, amax)
     return dz, dg, db
 
 
@@ -188,9 +216,11 @@ def edge_gather_relu(P: torch.Tensor, Q: torch.Tensor, g) -> torch.Tensor:
     P, Q = mat(P), mat(Q)
     C = P.shape[1]
     h = torch.empty(g.e_real, C, dtype=torch.float32, device=P.device)
+    amax = _new_amax(P.device)
     _lib.check(_lib.load().morig_edge_gather_relu(P.data_ptr(), _ld(P), Q.data_ptr(), _ld(Q), g.tgt.data_ptr(),
-                                                  g.col.data_ptr(), g.e_real, C, h.data_ptr(), C, _sp()),
+                                                  g.col.data_ptr(), g.e_real, C, h.data_ptr(), C, amax.data_ptr(), _sp()),
                "morig_edge_gather_relu")
+    _tag_amax(h, amax)
     return h
 
 

@@ -160,7 +160,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(_lib.EXPORTS) == declared                      # the ctypes table covers the whole header
-    assert _lib.load().morig_version() == _lib.ABI_VERSION == 6
+    assert _lib.load().morig_version() == _lib.ABI_VERSION == 7
 
 
 def test_tensor_core_weight_image_layout():
