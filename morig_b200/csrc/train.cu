@@ -407,30 +407,98 @@ __global__ void __launch_bounds__(256) edge_gather_relu_kernel(const float *__re
     if (amax) amax_commit_block(amax, am);
 }
 
-// dP[v] = sum over the CSR segment of v of [h > 0] dh   (one thread per (v, c): fixed order)
+// dP[v] = sum over the CSR segment of v of [h > 0] dh   (one thread per (v, column group): fixed order)
+template <int VEC>
 __global__ void __launch_bounds__(256) edge_gather_bwd_p_kernel(const float *__restrict__ dh, int lddh, const float *__restrict__ h,
                                                                 int ldh, const int32_t *__restrict__ rowptr, int N, int C,
                                                                 float *__restrict__ dP, int ldp) {
-    const int64_t total = (int64_t)N * C;
+    constexpr int W = VEC ? 4 : 1;
+    const int CW = C / W;
+    const int64_t total = (int64_t)N * CW;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const int v = (int)(i / C);
-        float s = 0.f;
-        for (int e = rowptr[v]; e < rowptr[v + 1]; ++e)
-            if (h[(size_t)e * ldh + c] > 0.f) s += dh[(size_t)e * lddh + c];
-        dP[(size_t)v * ldp + c] = s;
+        const int v = (int)(i / CW);
+        const int c = (int)(i - (int64_t)v * CW) * W;
+        float s[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) s[q] = 0.f;
+        for (int e = rowptr[v]; e < rowptr[v + 1]; ++e) {
+            float hv[W], dv[W];
+            if (VEC) {
+                *reinterpret_cast<float4 *>(hv) = *reinterpret_cast<const float4 *>(h + (size_t)e * ldh + c);
+                *reinterpret_cast<float4 *>(dv) = *reinterpret_cast<const float4 *>(dh + (size_t)e * lddh + c);
+            } else {
+                hv[0] = h[(size_t)e * ldh + c];
+                dv[0] = dh[(size_t)e * lddh + c];
+            }
+#pragma unroll
+            for (int q = 0; q < W; ++q)
+                if (hv[q] > 0.f) s[q] += dv[q];
+        }
+        if (VEC) *reinterpret_cast<float4 *>(dP + (size_t)v * ldp + c) = *reinterpret_cast<const float4 *>(s);
+        else dP[(size_t)v * ldp + c] = s[0];
     }
 }
 
-// dQ[col[e]] += [h > 0] dh   (dQ zeroed by the caller; fp32 atomics: the one order-dependent sum of the path)
+// dQ[col[e]] += [h > 0] dh   (dQ zeroed by the caller; fp32 atomics: the one order-dependent sum of the path).
+// VEC: one 16-byte vector reduction (red.global.add.v4.f32, sm_90+) per four columns instead of four scalar atomics.
+template <int VEC>
 __global__ void __launch_bounds__(256) edge_gather_bwd_q_kernel(const float *__restrict__ dh, int lddh, const float *__restrict__ h,
                                                                 int ldh, const int32_t *__restrict__ col, int E, int C,
                                                                 float *__restrict__ dQ, int ldq) {
-    const int64_t total = (int64_t)E * C;
+    constexpr int W = VEC ? 4 : 1;
+    const int CW = C / W;
+    const int64_t total = (int64_t)E * CW;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const int e = (int)(i / C);
-        if (h[(size_t)e * ldh + c] > 0.f) atomicAdd(dQ + (size_t)col[e] * ldq + c, dh[(size_t)e * lddh + c]);
+        const int e = (int)(i / CW);
+        const int c = (int)(i - (int64_t)e * CW) * W;
+        if (VEC) {
+            const float4 hv = *reinterpret_cast<const float4 *>(h + (size_t)e * ldh + c);
+            float4 dv = *reinterpret_cast<const float4 *>(dh + (size_t)e * lddh + c);
+            dv.x = hv.x > 0.f ? dv.x : 0.f; dv.y = hv.y > 0.f ? dv.y : 0.f;
+            dv.z = hv.z > 0.f ? dv.z : 0.f; dv.w = hv.w > 0.f ? dv.w : 0.f;
+            if (hv.x > 0.f || hv.y > 0.f || hv.z > 0.f || hv.w > 0.f)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                             :: "l"(dQ + (size_t)col[e] * ldq + c), "f"(dv.x), "f"(dv.y), "f"(dv.z), "f"(dv.w) : "memory");
+        } else {
+            if (h[(size_t)e * ldh + c] > 0.f) atomicAdd(dQ + (size_t)col[e] * ldq + c, dh[(size_t)e * lddh + c]);
+        }
+    }
+}
+
+// ---- segmented max, short segments (the max aggregation over a vertex's in-edges: ~8 / ~17 rows per segment) --------------
+// One thread per (segment, column group) walks the segment's rows in order and keeps the first maximum (strict >), with
+// 16-byte loads when VEC: no shared memory and no block barriers (segmax_kernel below spends two __syncthreads per
+// segment, which is right for the per-graph pooling over thousands of rows and wrong for 17).
+template <int VEC>
+__global__ void __launch_bounds__(256) segmax_short_kernel(const float *__restrict__ y, int ldy, const int32_t *__restrict__ ptr,
+                                                           int S, int C, float *__restrict__ out, int ldo,
+                                                           int32_t *__restrict__ arg, int lda) {
+    constexpr int W = VEC ? 4 : 1;
+    const int CW = C / W;
+    const int64_t total = (int64_t)S * CW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int sgm = (int)(i / CW);
+        const int c = (int)(i - (int64_t)sgm * CW) * W;
+        const int lo = ptr[sgm], hi = ptr[sgm + 1];
+        float best[W];
+        int bi[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) { best[q] = 0.f; bi[q] = -1; }
+        for (int r = lo; r < hi; ++r) {
+            float v[W];
+            if (VEC) *reinterpret_cast<float4 *>(v) = *reinterpret_cast<const float4 *>(y + (size_t)r * ldy + c);
+            else v[0] = y[(size_t)r * ldy + c];
+#pragma unroll
+            for (int q = 0; q < W; ++q)
+                if (bi[q] < 0 || v[q] > best[q]) { best[q] = v[q]; bi[q] = r; }
+        }
+        if (VEC) {                                                    // empty segment: 0 / -1
+            *reinterpret_cast<float4 *>(out + (size_t)sgm * ldo + c) = *reinterpret_cast<const float4 *>(best);
+            if (arg) *reinterpret_cast<int4 *>(arg + (size_t)sgm * lda + c) = *reinterpret_cast<const int4 *>(bi);
+        } else {
+            out[(size_t)sgm * ldo + c] = best[0];
+            if (arg) arg[(size_t)sgm * lda + c] = bi[0];
+        }
     }
 }
 
@@ -932,10 +1000,13 @@ extern "C" MORIG_API int morig_edge_gather_relu_bwd(const float *dh, int32_t ldd
                                                     void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MORIG_CHECK_ARG(dh && h && rowptr && col && dP && dQ && N > 0 && E > 0 && C > 0, "edge_gather_relu_bwd: bad argument");
-    edge_gather_bwd_p_kernel<<<grid1d((int64_t)N * C, 256, 8), 256, 0, stream>>>(dh, lddh, h, ldh, rowptr, N, C, dP, ldp);
+    const bool vec = vec4_ok(C, {lddh, ldh, ldp, ldq}, {dh, h, dP, dQ});
+    if (vec) edge_gather_bwd_p_kernel<1><<<grid1d((int64_t)N * C / 4, 256, 8), 256, 0, stream>>>(dh, lddh, h, ldh, rowptr, N, C, dP, ldp);
+    else edge_gather_bwd_p_kernel<0><<<grid1d((int64_t)N * C, 256, 8), 256, 0, stream>>>(dh, lddh, h, ldh, rowptr, N, C, dP, ldp);
     MORIG_LAUNCH_CHECK("edge_gather_bwd_p_kernel");
     MORIG_CUDA(cudaMemset2DAsync(dQ, (size_t)ldq * sizeof(float), 0, (size_t)C * sizeof(float), (size_t)N, stream));
-    edge_gather_bwd_q_kernel<<<grid1d((int64_t)E * C, 256, 8), 256, 0, stream>>>(dh, lddh, h, ldh, col, E, C, dQ, ldq);
+    if (vec) edge_gather_bwd_q_kernel<1><<<grid1d((int64_t)E * C / 4, 256, 8), 256, 0, stream>>>(dh, lddh, h, ldh, col, E, C, dQ, ldq);
+    else edge_gather_bwd_q_kernel<0><<<grid1d((int64_t)E * C, 256, 8), 256, 0, stream>>>(dh, lddh, h, ldh, col, E, C, dQ, ldq);
     MORIG_LAUNCH_CHECK("edge_gather_bwd_q_kernel");
     return 0;
 }
@@ -944,6 +1015,14 @@ extern "C" MORIG_API int morig_segmax_fwd(const float *y, int32_t ldy, const int
                                           int32_t ldo, int32_t *arg, int32_t lda, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MORIG_CHECK_ARG(y && ptr && out && S > 0 && C > 0 && ldy >= C && ldo >= C, "segmax_fwd: bad argument");
+    if (S >= 1024) {
+        // many segments = the per-vertex aggregation over in-edges (short segments); few = the per-graph pooling
+        const bool vec = vec4_ok(C, {ldy, ldo, arg ? lda : 4}, {y, out, arg});
+        if (vec) segmax_short_kernel<1><<<grid1d((int64_t)S * C / 4, 256, 8), 256, 0, stream>>>(y, ldy, ptr, S, C, out, ldo, arg, lda);
+        else segmax_short_kernel<0><<<grid1d((int64_t)S * C, 256, 8), 256, 0, stream>>>(y, ldy, ptr, S, C, out, ldo, arg, lda);
+        MORIG_LAUNCH_CHECK("segmax_short_kernel");
+        return 0;
+    }
     const int gy = S < 65535 ? S : 65535;
     segmax_kernel<<<dim3(ceil_div(C, 32), gy), 256, 0, stream>>>(y, ldy, ptr, S, C, out, ldo, arg, lda);
     MORIG_LAUNCH_CHECK("segmax_kernel");
