@@ -48,8 +48,17 @@ def _sp() -> int:
 # also reduce max |output| into a device scalar, which travels with the tensor object as `_morig_amax` =
 # (scalar, data_ptr, version).  A consumer only trusts it for exactly that tensor in exactly that state; anything else
 # (views, copies, in-place edits, tensors from elsewhere) falls back to the |max| pass of `engine._amax_in`.
+_amax_pool: dict = {}                    # device -> [zeroed block, cursor]: one memset per 4096 scalars, not one per tensor
+
+
 def _new_amax(dev) -> torch.Tensor:
-    return torch.zeros(1, dtype=torch.float32, device=dev)
+    """a zeroed device scalar; slices of a block that stays alive as long as any tag refers to it and is never reused"""
+    ent = _amax_pool.get(dev)
+    if ent is None or ent[1] >= ent[0].numel():
+        ent = _amax_pool[dev] = [torch.zeros(4096, dtype=torch.float32, device=dev), 0]
+    i = ent[1]
+    ent[1] = i + 1
+    return ent[0][i:i + 1]
 
 
 def _tag_amax(t: torch.Tensor, amax: torch.Tensor) -> None:
