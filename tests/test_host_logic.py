@@ -315,3 +315,20 @@ def test_standalone_forwards_validate_shapes(emulated):
     ec = morig_b200.EdgeConvMotion(morig_b200.MLP([6, 32, 32]), morig_b200.MLP([6, 16, 16])).eval()
     with pytest.raises(ValueError):
         ec(torch.zeros(64, 4), torch.zeros(64, 3), data.tpl_edge_index)
+
+
+def test_operand_range_tags_are_only_trusted_for_the_exact_tensor_state():
+    """train_ops tags a produced matrix with the device scalar holding max |value| (reduced by the producing kernel); a
+    consumer may use it only for that tensor object in that state -- views, copies and in-place edits fall back to the
+    |max| pass"""
+    from morig_b200 import train_ops as T
+    t = torch.arange(12, dtype=torch.float32).reshape(3, 4)
+    a = T._new_amax(t.device)
+    b = T._new_amax(t.device)
+    assert a.data_ptr() != b.data_ptr() and float(a) == 0.0 and a.numel() == 1       # slices of one zeroed block
+    assert T._known_amax(t) == 0
+    T._tag_amax(t, a)
+    assert T._known_amax(t) == a.data_ptr()
+    assert T._known_amax(t[:, :2]) == 0 and T._known_amax(t.clone()) == 0            # a view / a copy: not tagged
+    t.add_(1.0)                                                                      # in-place edit: version moved on
+    assert T._known_amax(t) == 0
