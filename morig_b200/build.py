@@ -35,7 +35,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     objs = []
     procs = []
-    bdir = os.path.join(PKG, "build_trace" if os.environ.get("MORIG_TRACE") == "1" else "build")
+    bdir = os.path.join(PKG, "build_trace" if (os.environ.get("MORIG_TRACE") == "1" or os.environ.get("MORIG_NVCC_FLAGS")) else "build")
     os.makedirs(bdir, exist_ok=True)
     for src in sources():
         obj = os.path.join(bdir, os.path.basename(src) + ".o")
@@ -44,6 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             cmd += ["-Xptxas", "-v"]
         if os.environ.get("MORIG_TRACE") == "1":         # role timeline of scripts/tc_trace.py
             cmd += ["-DMORIG_TRACE"]
+        cmd += os.environ.get("MORIG_NVCC_FLAGS", "").split()      # experiment builds (e.g. -DMORIG_BSPLIT=4)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

@@ -1357,8 +1357,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
             // this CTA's 128 (64) rows of the hi and of the lo image of chunk (n_tile, kc) -> dst
             auto fetch_chunk = [&](uint32_t dst, int n_tile, int kc, uint32_t bar) {
                 const uint8_t *src = gB + ((size_t)n_tile * nK + kc) * chunk_bytes + rank * HALF_B;
-                bulk_g2s(dst, src, HALF_B, bar);
-                bulk_g2s(dst + HALF_B, src + BN2 * 128, HALF_B, bar);
+#ifndef MORIG_BSPLIT
+#define MORIG_BSPLIT 1
+#endif
+                constexpr uint32_t PART = HALF_B / MORIG_BSPLIT;       // experiment knob: several smaller bulk copies per half
+#pragma unroll
+                for (int q = 0; q < MORIG_BSPLIT; ++q) {
+                    bulk_g2s(dst + q * PART, src + q * PART, PART, bar);
+                    bulk_g2s(dst + HALF_B + q * PART, src + BN2 * 128 + q * PART, PART, bar);
+                }
             };
             auto fetch_next = [&]() {                              // streaming mode only
                 if (leader) {
