@@ -1353,31 +1353,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
             const uint8_t *gB = reinterpret_cast<const uint8_t *>(tp.Bblob);
             const uint32_t chunk_bytes = 2u * BN2 * 128;           // full hi|lo image of one k-chunk in global memory
             const int my_tiles = tm.my_tiles();
-            int f_li = 0, f_kc = 0, f_s = 0, f_ntile = (my_tiles > 0) ? tm.decode(tm.first).n_tile : 0;
+            const int f_ntile = (my_tiles > 0) ? tm.decode(tm.first).n_tile : 0;
             // this CTA's 128 (64) rows of the hi and of the lo image of chunk (n_tile, kc) -> dst
             auto fetch_chunk = [&](uint32_t dst, int n_tile, int kc, uint32_t bar) {
                 const uint8_t *src = gB + ((size_t)n_tile * nK + kc) * chunk_bytes + rank * HALF_B;
-#ifndef MORIG_BSPLIT
-#define MORIG_BSPLIT 1
-#endif
-                constexpr uint32_t PART = HALF_B / MORIG_BSPLIT;       // experiment knob: several smaller bulk copies per half
-#pragma unroll
-                for (int q = 0; q < MORIG_BSPLIT; ++q) {
-                    bulk_g2s(dst + q * PART, src + q * PART, PART, bar);
-                    bulk_g2s(dst + HALF_B + q * PART, src + BN2 * 128 + q * PART, PART, bar);
-                }
-            };
-            auto fetch_next = [&]() {                              // streaming mode only
-                if (leader) {
-                    mbar_arrive_expect_tx(bar_b(f_s), 2 * HALF_B);
-                    fetch_chunk(base + b_region + f_s * b_stride, f_ntile, f_kc, bar_b(f_s));
-                }
-                if (++f_s == S) f_s = 0;
-                if (++f_kc == nK) {
-                    f_kc = 0;
-                    ++f_li;
-                    if (f_li < my_tiles) f_ntile = tm.decode(tm.first + f_li * tm.step).n_tile;
-                }
+                bulk_g2s(dst, src, HALF_B, bar);
+                bulk_g2s(dst + HALF_B, src + BN2 * 128, HALF_B, bar);
             };
             if (resb) {
                 if (my_tiles > 0) {
@@ -1389,12 +1370,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
                     if (rank == 0) mbar_wait<true>(bar_bp(0), 0);          // the peer's half image landed too
                     else if (leader) mbar_arrive_cluster(bar_bp(0), 0);
                 }
-            } else {
-                for (int i = 0; i < S - 1 && f_li < my_tiles; ++i) fetch_next();
             }
-            int s = 0, prev_s = 0;
-            uint32_t ph = 0, prev_ph = 0;
-            bool first = true;
+            // (streaming mode: the weight chunks are fetched by the dedicated warp below, which only follows the ring --
+            //  with the fetch in this loop a late chunk delayed the NEXT request too: the issuer cannot reach "stage free,
+            //  request chunk i + 2" before it has issued chunk i's MMAs, so the requests trailed the MMAs at L / 2 per stage)
+            int s = 0;
+            uint32_t ph = 0;
             const uint32_t idesc = make_idesc<KIND>(BN2, 2 * BM);     // M = 256 channels, N = 256 rows over the pair
             Tracer tr{(tp.trace && blockIdx.x == 0 && leader) ? tp.trace + 2048 : nullptr, 0};
             if (!(resb && rank != 0)) {                            // resident mode: the peer's control warp is done
@@ -1432,15 +1413,33 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_gemm_kernel(const TcP tp) {
                         } else if (leader) {
                             mbar_arrive_cluster(bar_bp(s), 0);                 // tell the leader CTA
                         }
-                        if (!resb && f_li < my_tiles) {
-                            if (!first) mbar_wait(bar_m(prev_s), prev_ph);     // previous chunk's MMAs retired (multicast)
-                            fetch_next();
-                        }
-                        first = false;
-                        prev_s = s; prev_ph = ph;
                         if (++s == S) { s = 0; ph ^= 1; }
                     }
                     if (rank == 0 && leader) umma_commit<2>(bar_accf(buf));    // both CTAs: accumulator complete
+                }
+            }
+        } else if (warp == CONTROL_WARP + 1 && !resb) {
+            // ================= weight-chunk fetcher (streaming mode) =================
+            // Walks the same (tile, k-chunk) sequence as the MMA issuer and requests chunk j into ring slot j % S as soon as
+            // the MMAs that read the slot one ring turn ago have retired (multicast commit on bar_m) -- never later.
+            const bool leader = lane == 0;
+            const uint8_t *gB = reinterpret_cast<const uint8_t *>(tp.Bblob);
+            const uint32_t chunk_bytes = 2u * BN2 * 128;
+            const int my_tiles = tm.my_tiles();
+            int s = 0;
+            uint32_t free_ph = 1;                                  // passes on the fresh barriers of the first ring turn
+            for (int li = 0; li < my_tiles; ++li) {
+                const int n_tile = tm.decode(tm.first + li * tm.step).n_tile;
+                for (int kc = 0; kc < nK; ++kc) {
+                    mbar_wait(bar_m(s), free_ph);
+                    if (leader) {
+                        const uint32_t dst = base + b_region + s * b_stride;
+                        const uint8_t *src = gB + ((size_t)n_tile * nK + kc) * chunk_bytes + rank * HALF_B;
+                        mbar_arrive_expect_tx(bar_b(s), 2 * HALF_B);
+                        bulk_g2s(dst, src, HALF_B, bar_b(s));
+                        bulk_g2s(dst + HALF_B, src + BN2 * 128, HALF_B, bar_b(s));
+                    }
+                    if (++s == S) { s = 0; free_ph ^= 1; }
                 }
             }
         }
