@@ -520,19 +520,24 @@ __device__ __forceinline__ void producer_role(const GemmP &p, float a_scale, uin
         }
     };
 
-    float4 pb0[RPT], pb1[RPT];
-    float4 qb0[GATHER ? RPT : 1], qb1[GATHER ? RPT : 1];
-    long long remaining = (long long)tm.my_tiles() * nU;      // units still to be stored
-    issue(pb0, qb0);
-    issue(pb1, qb1);
+    // NB register buffers rotate (an even number, and a tile has an even number of units, so buffer b always holds unit
+    // b & 1 of an fp16 stage).  Plain rows need 16 registers per buffer: four of them keep two whole stages of loads in
+    // flight -- with the weight chunks no longer late (dedicated fetch warp) the dense layers wait for these loads.
+    constexpr int NB = GATHER ? 2 : 4;
+    float4 pb[NB][RPT];
+    float4 qb[NB][GATHER ? RPT : 1];
+    int remaining = tm.my_tiles() * nU;                       // units still to be stored
+#pragma unroll
+    for (int b = 0; b < NB; ++b) issue(pb[b], qb[b]);
     while (remaining > 0) {
-        store_unit(0, pb0, qb0);
-        issue(pb0, qb0);
-        if (remaining > 1) {
-            store_unit(1, pb1, qb1);
-            issue(pb1, qb1);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            if (remaining > b) {
+                store_unit(b & 1, pb[b], qb[b]);
+                issue(pb[b], qb[b]);
+            }
         }
-        remaining -= 2;
+        remaining -= NB;
     }
 }
 
