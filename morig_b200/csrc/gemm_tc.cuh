@@ -1161,22 +1161,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
             const uint32_t b_bytes = (uint32_t)C::B_CHUNK_BYTES;
             const uint8_t *gB = reinterpret_cast<const uint8_t *>(tp.Bblob);
             const int my_tiles = tm.my_tiles();
-            // All ring positions are tracked incrementally (no div/mod on this latency-critical warp).
-            // fetch cursor: next (tile, k-chunk) whose weight image has to be requested, and its stage
-            int f_li = 0, f_kc = 0, f_s = 0, f_ntile = (my_tiles > 0) ? tm.decode(tm.first).n_tile : 0;
-            auto fetch_next = [&]() {                              // streaming mode only
-                const uint32_t dst = base + b_region + f_s * b_stride;
-                if (leader) {
-                    mbar_arrive_expect_tx(bar_b(f_s), b_bytes);
-                    bulk_g2s(dst, gB + ((size_t)f_ntile * nK + f_kc) * b_bytes, b_bytes, bar_b(f_s));
-                }
-                if (++f_s == S) f_s = 0;
-                if (++f_kc == nK) {
-                    f_kc = 0;
-                    ++f_li;
-                    if (f_li < my_tiles) f_ntile = tm.decode(tm.first + f_li * tm.step).n_tile;
-                }
-            };
+            const int f_ntile = (my_tiles > 0) ? tm.decode(tm.first).n_tile : 0;
             if (resb) {
                 // one n-tile for the whole kernel: fetch every k-chunk of the image once
                 if (my_tiles > 0) {
@@ -1188,12 +1173,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
                     }
                     mbar_wait(bar_b(0), 0);
                 }
-            } else {
-                for (int i = 0; i < S - 1 && f_li < my_tiles; ++i) fetch_next();
             }
-            int s = 0, prev_s = 0;
-            uint32_t ph = 0, prev_ph = 0;
-            bool first = true;
+            // (streaming mode: the weight chunks are requested by the dedicated warp below, see tc2_gemm_kernel)
+            int s = 0;
+            uint32_t ph = 0;
             for (int li = 0; li < my_tiles; ++li) {
                 const int buf = li & (C::NBUF - 1);
                 tr(20);
@@ -1226,17 +1209,28 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcP tp) {
                         umma_commit<1>(bar_m(s));                    // frees stage s when these MMAs retire
                     }
                     tr(24);
-                    if (!resb && f_li < my_tiles) {
-                        // the stage to refill was last read by the PREVIOUS chunk's MMAs
-                        if (!first) mbar_wait(bar_m(prev_s), prev_ph);
-                        tr(25);
-                        fetch_next();
-                    }
-                    first = false;
-                    prev_s = s; prev_ph = ph;
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
                 if (leader) umma_commit<1>(bar_accf(buf));       // accumulator complete -> epilogue
+            }
+        } else if (warp == CONTROL_WARP + 1 && !resb) {
+            // ================= weight-chunk fetcher (streaming mode): follows the ring, never the MMA issuer =================
+            const bool leader = lane == 0;
+            const uint32_t b_bytes = (uint32_t)C::B_CHUNK_BYTES;
+            const uint8_t *gB = reinterpret_cast<const uint8_t *>(tp.Bblob);
+            const int my_tiles = tm.my_tiles();
+            int s = 0;
+            uint32_t free_ph = 1;                                  // passes on the fresh barriers of the first ring turn
+            for (int li = 0; li < my_tiles; ++li) {
+                const int n_tile = tm.decode(tm.first + li * tm.step).n_tile;
+                for (int kc = 0; kc < nK; ++kc) {
+                    mbar_wait(bar_m(s), free_ph);                  // the MMAs that read this slot one ring turn ago retired
+                    if (leader) {
+                        mbar_arrive_expect_tx(bar_b(s), b_bytes);
+                        bulk_g2s(base + b_region + s * b_stride, gB + ((size_t)n_tile * nK + kc) * b_bytes, b_bytes, bar_b(s));
+                    }
+                    if (++s == S) { s = 0; free_ph ^= 1; }
+                }
             }
         }
     } else if (warp < PRODUCER_WARPS) {
