@@ -20,19 +20,25 @@
 // 128-byte row segment -- no shared-memory transposition (an earlier version staged every 32x32 block through shared
 // memory; timeline traces showed the epilogue warps, not the MMAs, bounding the fused EdgeConv kernels).
 //
-// One CTA per SM walks tiles; three roles run decoupled through mbarriers:
-//   warps 0-7   A producers: 32 k-columns per stage written straight into 128B-swizzled K-major shared memory;
-//               plain activation rows, or relu(P[tgt[e]] + Q[col[e]]) gathered per CSR slot (fused EdgeConv);
-//               the raw operands of the next chunk are in flight in registers while the current one is stored
-//   warp  16    one elected lane: cp.async.bulk of the pre-split / pre-swizzled weight image of each
-//               (n-tile, k-chunk) (TMA engine, mbarrier complete_tx) and the 12 tcgen05.mma per 128 channels and
-//               stage; tcgen05.commit releases stages and publishes accumulators
-//   warps 8-15  epilogue, two per TMEM lane quarter (= 32 channels), alternating 32-row blocks of one of the TWO
-//               accumulator buffers (the next tile's MMAs overlap):
-//               bias (+ per-graph bias) -> ReLU -> BatchNorm affine and
-//                 coalesced row stores / per-graph column max / segmented max over the CSR target
-//               (running max restarted at segment heads, flushed at tails; segments cut by a 32-row block merge
-//                with the ordered-int atomic max: exact and order independent, hence deterministic)
+// One CTA per SM walks tiles; the roles run decoupled through mbarriers:
+//   warps 0-7   A producers: 32 k-columns per stage unit written straight into 128B-swizzled K-major shared memory;
+//               plain activation rows (producer_role: four 16-register load buffers = two stages of loads in flight), or
+//               relu(P[tgt[e]] + Q[col[e]]) gathered per CSR slot (producer_gather_role, the fused EdgeConv: tile body
+//               unrolled over the K / 32 units, ReLU folded into the fp16 conversion)
+//   warp  16    one elected lane issues the 12 tcgen05.mma per 128 channels and stage; tcgen05.commit releases stages
+//               and publishes accumulators
+//   warp  17    streaming mode: cp.async.bulk of the pre-split / pre-swizzled weight image of each (n-tile, k-chunk)
+//               (TMA engine, mbarrier complete_tx), requested as soon as the ring slot's previous MMAs retired --
+//               independent of the issuer, which a late chunk would otherwise keep from requesting the next one.
+//               (Resident mode: the issuer loads the whole image once.)
+//   warps 8-15  epilogue, two per TMEM lane quarter (= 32 channels), working on one of the 2-4 accumulator buffers while
+//               the next tiles' MMAs run:
+//               dense layers (epilogue_role): alternating 32-row blocks; bias (+ per-graph bias) -> ReLU -> BatchNorm
+//                 affine and coalesced row stores / per-graph column max
+//               fused EdgeConv (epilogue_segmax_role): a contiguous half of the tile's rows per warp; running max over
+//                 the CSR segments in registers, written back to TMEM, segment tails read back by runtime column address;
+//                 bias -> ReLU -> BatchNorm once per segment; segments that leave the warp's range merge with the
+//                 ordered-int atomic max: exact and order independent, hence deterministic
 //
 // Two kernels share the role code:
 //   tc_gemm_kernel<BN,...>   cta_group::1, BN / 128 UMMAs of 128 x 128 per k-step; weight image streamed per stage or,
