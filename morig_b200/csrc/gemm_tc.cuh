@@ -787,6 +787,17 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_
             load_keys(t + tm.step);                  // in flight during this tile
         }
         const uint32_t frame_base = (EPI == EPI_SEGMAX) ? (uint32_t)(tcd.frame * p.n_vtx_frame) : 0u;
+        // per-channel constants of the tile's channels: requested BEFORE the wait for the accumulator, so that their
+        // L2 latency hides behind it (loaded per 32-row unit they cost the short-K layers ~400 cycles per unit)
+        float bias_t[NH], scale_t[NH], shift_t[NH];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            const int nl = n0 + h * 128;
+            const bool ok = nl < p.N;
+            bias_t[h] = (ok && p.bias) ? p.bias[nl] : 0.f;
+            scale_t[h] = (ok && p.scale) ? p.scale[nl] : 1.f;
+            shift_t[h] = (ok && p.shift) ? p.shift[nl] : 0.f;
+        }
 
         tr(10);
         mbar_wait(aux_addr + AUX_ACC_FULL + 8u * buf, (uint32_t)((li >> NBUF_LOG) & 1));
@@ -807,10 +818,9 @@ __device__ __forceinline__ void epilogue_role(const GemmP &p, float inv, uint32_
             const int valid_rows = min(32, max(0, M - rbase));
             const int nl = n0 + h * 128;             // this lane's output channel
             const bool nl_ok = nl < p.N;
-            // per-channel constants (L1/L2 hits; their latency hides behind the accumulator load)
-            const float bias_l = (nl_ok && p.bias) ? p.bias[nl] : 0.f;
-            const float scale_l = (nl_ok && p.scale) ? p.scale[nl] : 1.f;
-            const float shift_l = (nl_ok && p.shift) ? p.shift[nl] : 0.f;
+            const float bias_l = (NH == 1 || h == 0) ? bias_t[0] : bias_t[NH - 1];
+            const float scale_l = (NH == 1 || h == 0) ? scale_t[0] : scale_t[NH - 1];
+            const float shift_l = (NH == 1 || h == 0) ? shift_t[0] : shift_t[NH - 1];
             // segment structure of the block: warp-uniform masks
             const int *kblk = kstrip + 32 * i;
             uint32_t tails = 0x80000000u;
