@@ -364,8 +364,14 @@ def run_ours(args):
             roof_hbm = {"bound": "hbm", "kernel": narrow["kernel"], "achieved": narrow["gbs"], "peak": peaks["hbm_gbs"],
                         "unit": "GB/s", "frac": narrow["gbs"] / peaks["hbm_gbs"], "traffic": tr,
                         "avg_launch_ms": narrow["avg_ms"], "alg_mb_per_launch": narrow["alg_mb_per_launch"],
-                        "note": "86 FLOP/B and 1.39 M random 128-byte gathers per launch: bound by L2 gather latency and the "
-                                "warp-level MMAs, not by HBM"}
+                        # ncu (profiles/r02_ncu_dominant_kernels.txt): L2 read sectors from L1/TEX per launch
+                        "l2_read_mb_per_launch_ncu": 151.7,
+                        "l2_gbs_ncu": round(151.7e-3 / (narrow["avg_ms"] * 1e-3), 1) if narrow["avg_ms"] else None,
+                        "l2_cap_gbs": 12400.0,
+                        "note": "86 FLOP/B and 1.39 M random 128-byte gathers per launch: neither HBM (6 %) nor L2 bandwidth "
+                                "(152 MB of L2 reads per launch = ~1.7 TB/s = 14 % of the ~12.4 TB/s L2->SM cap) binds; ncu: issue "
+                                "slots 54 % busy at 16 resident warps per SM -- instruction issue and gather / shuffle latency of "
+                                "the warp-level MMA kernel (more occupancy through a register cap was measured: slower)"}
         cpu = cpu_reference_run(steps=3, warmup=1, n_meshes=1) if world == 1 else None
         # BASELINE.json configs[0] (1 x 1024 vertices, the reference's own CPU-runnable case): both sides, informational
         cfg0 = None
