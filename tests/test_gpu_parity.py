@@ -171,6 +171,46 @@ def test_edgeconv_tensor_core_kinds(H, frames, mag, kind):
         assert helpers.max_abs_diff(out[f * n:(f + 1) * n], ref) < 1e-5 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("H,frames", [(64, 1), (128, 1), (128, 5), (256, 1), (256, 6)])
+def test_edgeconv_segment_boundaries_are_exact(H, frames):
+    """fused EdgeConv epilogue (contiguous row ranges per warp, register carry across 32-row blocks, atomic merge only for
+    segments that leave a warp's range, selective -inf start values): in-degrees chosen so that segments of 1 .. 700 slots
+    start at every alignment relative to the 32 / 64 / 128 / 256-row boundaries; integer-valued operands and weights, scale
+    +-1, so every sum is exact and the result must equal the fp64 evaluation BIT FOR BIT.  frames = 1 runs the
+    cta_group::1 kernels (two accumulators per buffer for H = 256), more key-frames the 2-CTA pair kernel."""
+    g = torch.Generator().manual_seed(H + frames)
+    degs = [0, 30, 31, 32, 33, 1, 62, 63, 64, 65, 2, 126, 127, 128, 129, 3, 254, 255, 256, 257, 5, 700, 17, 8, 96, 160, 7]
+    degs = (degs * 4)[: 4 * len(degs)]
+    n = len(degs) + 40                                       # trailing vertices: self loop only
+    tgt = torch.cat([torch.full((d,), v, dtype=torch.long) for v, d in enumerate(degs)])
+    src = torch.randint(0, n, (tgt.numel(),), generator=g)
+    src = torch.where(src == tgt, (src + 1) % n, src)        # no explicit self loops (graph_prep appends them)
+    perm = torch.randperm(tgt.numel(), generator=g)
+    ei = torch.stack([src, tgt])[:, perm]
+    gr = engine.graph_prep(ei.to(DEV), n)
+    pq = torch.randint(-4, 5, (n * frames, 2 * H), generator=g).float()
+    W1 = torch.randint(-2, 3, (H, H), generator=g).double()
+    b1 = torch.randint(-3, 4, (H,), generator=g).float()
+    sc = (torch.randint(0, 2, (H,), generator=g) * 2 - 1).float()
+    sh = torch.randint(-2, 3, (H,), generator=g).float()
+    blob, w_inv = packing.pack_edge_tc_blob(W1, sc, packing.KIND_F16)
+    br = packing.EdgeBranch(W1=packing._pack_wt(W1).to(DEV), b1=b1.to(DEV), scale=sc.to(DEV), shift=sh.to(DEV), H=H,
+                            W1tc=blob.to(DEV), tc_kind=packing.KIND_F16, tc_w_inv=w_inv)
+    ld = H + 8
+    out = torch.full((n * frames, ld), 123.0, device=DEV)     # garbage start values: only fill_cut prepares the buffer
+    engine.fill_cut([(gr, out, ld, 4, H)], n, frames, float("-inf"))
+    engine.edgeconv(br, pq.to(DEV), 2 * H, 0, H, gr, frames, out, ld, 4)
+    e_real = int(gr.rowptr[n])
+    i, j = gr.tgt[:e_real].long().cpu(), gr.col[:e_real].long().cpu()
+    res = out.cpu().reshape(frames, n, ld)
+    assert bool((res[:, :, :4] == 123.0).all()) and bool((res[:, :, 4 + H:] == 123.0).all())   # neighbours untouched
+    for f in range(frames):
+        P, Q = pq[f * n:(f + 1) * n, :H].double(), pq[f * n:(f + 1) * n, H:].double()
+        z = torch.relu(torch.relu(P[i] + Q[j]) @ W1.t() + b1.double()) * sc.double() + sh.double()
+        ref = torch.full((n, H), float("-inf"), dtype=torch.float64).scatter_reduce(0, i[:, None].expand_as(z), z, "amax")
+        assert torch.equal(res[f, :, 4:4 + H].double(), ref), (H, frames, f)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,e,frames", [(300, 2500, 1), (1024, 16384, 5), (64, 9000, 2)])
 def test_fill_cut_touches_exactly_the_straddling_segments(n, e, frames):
