@@ -1075,14 +1075,27 @@ __device__ __forceinline__ void epilogue_segmax_role(const GemmP &p, float inv, 
                 const int r = __ffs(tl) - 1;
                 const int k_seg = kblk[r];
                 float m = tmem_ld1_sync(tcol + (uint32_t)r);
-                if (k_seg < 0 || cb == nullptr) continue;        // rows past the end of the matrix / channels past N
+                const bool ok = k_seg >= 0 && cb != nullptr;     // not: rows past the end of the matrix / channels past N
                 m = fmaf(fmaxf(fmaf(m, sinv_h, bias_h), 0.f), scale_h, shift_h);
-                float *dst = cb + (uint32_t)k_seg * (uint32_t)p.ldc;
+                float *dst = cb + (uint32_t)(k_seg < 0 ? 0 : k_seg) * (uint32_t)p.ldc;
                 // a segment that leaves the warp's range is merged with the ordered-int atomic max (exact and order
-                // independent, hence deterministic); everything else is a plain store
-                if ((r == first_tail && first_cut && open_cut) || (r == 31 && last_cut)) atomic_max_f32(dst, m);
-                else *dst = m;
-                amax_l = fmaxf(amax_l, fabsf(m));                // only the maxima are stored
+                // independent, hence deterministic; same rule as atomic_max_f32), everything else is a plain store.
+                // Predicated, not branched: the lanes of a warp differ in `ok` and in the sign, and a divergent region
+                // between two warp-synchronous tcgen05.ld costs a reconvergence barrier per tail.
+                const bool at = (r == first_tail && first_cut && open_cut) || (r == 31 && last_cut);
+                const float v = m + 0.0f;                        // canonicalise -0.0
+                const int p_st = (ok && !at) ? 1 : 0, p_mx = (ok && at && v >= 0.0f) ? 1 : 0, p_mn = (ok && at && !(v >= 0.0f)) ? 1 : 0;
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p0, p1, p2;\n\t"
+                    "setp.ne.s32 p0, %2, 0;\n\t"
+                    "setp.ne.s32 p1, %3, 0;\n\t"
+                    "setp.ne.s32 p2, %4, 0;\n\t"
+                    "@p0 st.global.f32 [%0], %1;\n\t"
+                    "@p1 red.global.max.s32 [%0], %5;\n\t"
+                    "@p2 red.global.min.u32 [%0], %5;\n\t"
+                    "}" ::"l"(dst), "f"(m), "r"(p_st), "r"(p_mx), "r"(p_mn), "r"(__float_as_int(v)) : "memory");
+                amax_l = ok ? fmaxf(amax_l, fabsf(m)) : amax_l;  // only the maxima are stored
             }
             if (h + 1 < NH || i + 1 < RBW) {                  // next unit: the other channel half, or the next row block
                 const uint32_t tnext = tbase + (uint32_t)((h + 1 < NH) ? (h + 1) * 128 + i * 32 : (i + 1) * 32);
