@@ -349,7 +349,9 @@ MORIG_API int    morig_wgrad_f32(const float *dY, int32_t lddy, const float *X, 
 /* train-mode BatchNorm1d over the R rows of x [R, C] (torch semantics, models/basic_modules.py:33): batch mean and
  * biased variance normalise, running_mean / running_var (optional) move by `momentum` towards the batch mean / unbiased
  * variance.  Writes mean, invstd, scale = gamma * invstd, shift = beta - mean * scale [C] and, if y != NULL,
- * y = x * scale + shift.  ws: morig_colstats_workspace(R, C) bytes. */
+ * y = x * scale + shift.  y_amax (optional): device scalar, zeroed by the caller, that receives max |y| (ordered-int atomic max
+ * per thread block) -- the operand range the fp16-split tensor-core GEMM consuming y needs; the same for dz_amax of
+ * morig_bn_relu_bwd and h_amax of morig_edge_gather_relu.  ws: morig_colstats_workspace(R, C) bytes. */
 MORIG_API size_t morig_colstats_workspace(int32_t R, int32_t C);
 MORIG_API int    morig_bn_train_fwd(const float *x, int32_t ldx, int32_t R, int32_t C, const float *gamma, const float *beta,
                                     float eps, float momentum, float *running_mean, float *running_var, float *mean,
