@@ -50,13 +50,13 @@
 #pragma once
 #include <cuda_fp16.h>
 #include "gemm_simt.cuh"
+#include "tile_iter.cuh"
 
 namespace morig {
 namespace tc {
 
 enum { KIND_TF32 = 0, KIND_F16 = 1 };
 
-constexpr int BM = 128;
 constexpr int KC = 32;                       // fp32 k-columns per producer ring unit
 // one stage = 128-byte swizzle rows: 32 tf32 (one ring unit) or 64 fp16 (two ring units)
 template <int KIND> struct KindCfg {
@@ -335,8 +335,6 @@ struct TcP {
     long long *trace;        // debug timeline (CTA 0): [role 0..2][2048] (tag, clock64) pairs, or NULL
 };
 
-struct TileCoord { int n_tile, m0, frame; };
-
 // role timeline for scripts/tc_trace.py; compiled in only with -DMORIG_TRACE (MORIG_TRACE=1 python -m morig_b200.build)
 struct Tracer {
     long long *buf; int n;
@@ -346,50 +344,6 @@ struct Tracer {
 #else
         (void)tag;
 #endif
-    }
-};
-
-// tile stream of one CTA: t = first, first + step, ... < total;  m0 = ((r % ntm) * mult + rank) * BM
-struct TileMap {
-    int ntn, ntm, total, first, step, mult, rank;
-    __device__ __forceinline__ TileCoord decode(int t) const {
-        TileCoord c;
-        c.n_tile = t % ntn;
-        const int r = t / ntn;
-        c.m0 = ((r % ntm) * mult + rank) * BM;
-        c.frame = r / ntm;
-        return c;
-    }
-    __device__ __forceinline__ int my_tiles() const { return total > first ? (total - 1 - first) / step + 1 : 0; }
-};
-
-// The same stream with the coordinates kept incrementally: one add / compare / select chain per tile instead of the
-// four integer divisions of decode() (ncu: ~190 of a producer warp's ~880 instructions per tile were tile arithmetic).
-struct TileIter {
-    int t, n_tile, mi, frame;        // mi = m-tile (cta_group::2: pair-tile) index inside the key-frame
-    int d_n, d_m, d_f;               // `step` decomposed in the mixed radix (ntn, ntm)
-    int ntn, ntm, total, step, mult, rank;
-    __device__ __forceinline__ void init(const TileMap &tm) {
-        ntn = tm.ntn; ntm = tm.ntm; total = tm.total; step = tm.step; mult = tm.mult; rank = tm.rank;
-        t = tm.first;
-        n_tile = t % ntn;
-        const int r = t / ntn;
-        mi = r % ntm; frame = r / ntm;
-        d_n = step % ntn;
-        const int a = step / ntn;
-        d_m = a % ntm; d_f = a / ntm;
-    }
-    __device__ __forceinline__ bool valid() const { return t < total; }
-    __device__ __forceinline__ int m0() const { return (mi * mult + rank) * BM; }
-    __device__ __forceinline__ void next() {
-        t += step;
-        n_tile += d_n;
-        int c = (n_tile >= ntn) ? 1 : 0;
-        n_tile -= c ? ntn : 0;
-        mi += d_m + c;
-        c = (mi >= ntm) ? 1 : 0;
-        mi -= c ? ntm : 0;
-        frame += d_f + c;
     }
 };
 

@@ -332,3 +332,18 @@ def test_operand_range_tags_are_only_trusted_for_the_exact_tensor_state():
     assert T._known_amax(t[:, :2]) == 0 and T._known_amax(t.clone()) == 0            # a view / a copy: not tagged
     t.add_(1.0)                                                                      # in-place edit: version moved on
     assert T._known_amax(t) == 0
+
+
+def test_tile_stream_arithmetic_of_the_persistent_kernels(tmp_path):
+    """morig_b200/csrc/tile_iter.cuh (the header the tcgen05 kernels include): the incremental tile iterator visits exactly
+    the coordinates of TileMap::decode, for 20 000 random tile grids / CTA strides; host build with g++"""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    exe = tmp_path / "tile_iter_test"
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host", "tile_iter_test.cpp")
+    subprocess.run([cxx, "-O1", "-std=c++17", "-o", str(exe), src], check=True)
+    r = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout
