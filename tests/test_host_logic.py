@@ -347,3 +347,68 @@ def test_tile_stream_arithmetic_of_the_persistent_kernels(tmp_path):
     subprocess.run([cxx, "-O1", "-std=c++17", "-o", str(exe), src], check=True)
     r = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True)
     assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout
+
+
+@pytest.mark.parametrize("rbw,tile_rows", [(2, 128), (4, 256)])
+def test_segmax_epilogue_protocol_model(rbw, tile_rows):
+    """Executable model of the fused-EdgeConv epilogue protocol (csrc/gemm_tc.cuh epilogue_segmax_role) and of its contract with
+    morig_fill_cut_f32: every epilogue warp owns `rbw` contiguous 32-row blocks of a tile, carries a segment that runs across
+    its blocks, stores a segment it sees completely with a PLAIN store and merges one that leaves its range with an atomic
+    max on a destination that was pre-filled with -inf iff the segment straddles a multiple of 32 slots.  The model replays
+    those rules in a random order of warps on random segment layouts (lengths 1..700, ragged ends) over an output that
+    starts as garbage, and checks (1) the result is the segmented max, (2) no vertex receives a plain store AND any other
+    write (the race the selective fill must exclude), (3) atomics only ever hit pre-filled vertices."""
+    import numpy as np
+    rng = np.random.default_rng(rbw)
+    for trial in range(60):
+        lens = rng.choice([1, 2, 7, 17, 31, 32, 33, 63, 64, 65, 127, 129, 255, 257, 700], size=rng.integers(3, 60))
+        tgt = np.repeat(np.arange(len(lens)), lens)                      # CSR target of every slot (sorted)
+        M = len(tgt)
+        val = rng.standard_normal(M)
+        rowptr = np.concatenate([[0], np.cumsum(lens)])
+        a, b = rowptr[:-1], rowptr[1:]
+        prefilled = (a >> 5) != ((b - 1) >> 5)                           # morig_fill_cut_f32
+        out = np.full(len(lens), 123.0)                                  # garbage start values
+        out[prefilled] = -np.inf
+        plain = np.zeros(len(lens), int)
+        atomic = np.zeros(len(lens), int)
+        span = 32 * rbw
+        ranges = list(range(0, (M + tile_rows - 1) // tile_rows * tile_rows, span))
+        rng.shuffle(ranges)                                              # warps / CTAs finish in any order
+        key = lambda r: tgt[r] if 0 <= r < M else (-2 if r < 0 else -1)
+        for r0 in ranges:
+            carry, open_cut = None, False
+            for i in range(rbw):
+                base = r0 + 32 * i
+                k = [key(base + j) for j in range(32)]
+                first_cut = k[0] == key(base - 1)
+                last_cut = k[31] == key(base + 32)
+                tails = [j for j in range(32) if j == 31 or k[j] != k[j + 1]]
+                cont = i > 0 and first_cut
+                if i == 0:
+                    open_cut = first_cut
+                defer = last_cut and i < rbw - 1
+                run, w = None, []
+                for j in range(32):
+                    v = val[base + j] if base + j < M else 0.0
+                    head = (j == 0 and not cont) or (j > 0 and k[j] != k[j - 1])
+                    run = v if head else max(run if run is not None else carry, v)
+                    w.append(run)
+                for j in tails:
+                    if defer and j == 31:
+                        continue
+                    if k[j] < 0:
+                        continue
+                    at = (j == tails[0] and first_cut and open_cut) or (j == 31 and last_cut)
+                    if at:
+                        assert prefilled[k[j]], "atomic merge into a vertex that was not pre-filled"
+                        out[k[j]] = max(out[k[j]], w[j])
+                        atomic[k[j]] += 1
+                    else:
+                        out[k[j]] = w[j]
+                        plain[k[j]] += 1
+                carry = w[31]
+                open_cut = defer and tails[0] == 31 and first_cut and open_cut
+        want = np.array([val[s:e].max() for s, e in zip(a, b)])
+        assert np.array_equal(out, want)
+        assert ((plain == 1) & (atomic == 0) | (plain == 0) & (atomic >= 1)).all()
